@@ -1,0 +1,204 @@
+/*
+ * quimb_b200 -- C ABI of the B200-native tensor-network contraction engine.
+ *
+ * This header is the drop-in boundary.  Every entry point replaces one
+ * library call that quimb's hot path bottoms out in (all reference citations
+ * are relative to the quimb source tree):
+ *
+ *   qb_contract_pair      <- autoray do("tensordot") / do("einsum") issued by the
+ *                            cotengra pairwise loop under
+ *                            quimb/tensor/contraction.py:272-292 (array_contract)
+ *                            and by Tensor.__matmul__, quimb/tensor/tensor_core.py:3786-3808
+ *   qb_permute            <- do("transpose")+do("reshape") materialisation in
+ *                            quimb/tensor/array_ops.py:148-180 (fuse)
+ *   qb_svd_trunc          <- svd_truncated, quimb/tensor/decomp.py:829-1118
+ *   qb_qr_stab            <- qr_stabilized, quimb/tensor/decomp.py:2055-2216
+ *   qb_lanczos_* / qb_axpy / qb_dot ...
+ *                         <- ARPACK dsaupd vector algebra behind
+ *                            quimb/linalg/scipy_linalg.py:113-128 (eigs_scipy)
+ *
+ * Conventions
+ *   - plain C, no C++/torch types; device pointers are borrowed, never freed
+ *     or retained by the library beyond the call.
+ *   - all strides are in ELEMENTS (not bytes) and may describe any
+ *     non-overlapping strided view (torch.Tensor.stride()).
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).
+ *   - return value: 0 = success; <0 = invalid argument (-(index+1));
+ *     >0 = CUDA / numerical failure.  qb_last_error() gives a message.
+ *   - thread safety: no global mutable state except the thread-local error
+ *     string; calls on different streams may run concurrently.
+ */
+#ifndef QUIMB_B200_H
+#define QUIMB_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QB_MAX_RANK 32
+#define QB_ABI_VERSION 1
+
+typedef enum {
+  QB_F32 = 0,
+  QB_F64 = 1,
+  QB_C64 = 2,
+  QB_C128 = 3
+} qb_dtype_t;
+
+/* A strided device tensor view (mirrors what quimb keeps in Tensor._data). */
+typedef struct {
+  void *ptr;
+  int32_t dtype; /* qb_dtype_t */
+  int32_t rank;
+  int64_t shape[QB_MAX_RANK];
+  int64_t stride[QB_MAX_RANK]; /* elements */
+} qb_tensor_t;
+
+/* quimb's absorb codes, decomp.py:201-211 (QB_ABSORB_FULL stands for None). */
+enum {
+  QB_ABSORB_FULL = 100, /* 'U,s,VH' : return the three parts */
+  QB_ABSORB_S = 2,      /* 's' */
+  QB_ABSORB_LSQRT = -12,
+  QB_ABSORB_RORTHOG = -11,
+  QB_ABSORB_LFACTOR = -10,
+  QB_ABSORB_LEFT = -1,
+  QB_ABSORB_BOTH = 0,
+  QB_ABSORB_RIGHT = 1,
+  QB_ABSORB_LORTHOG = 10,
+  QB_ABSORB_RFACTOR = 11,
+  QB_ABSORB_RSQRT = 12
+};
+
+/* quimb's cutoff modes, decomp.py:265-270 */
+enum {
+  QB_CUTOFF_ABS = 1,
+  QB_CUTOFF_REL = 2,
+  QB_CUTOFF_SUM2 = 3,
+  QB_CUTOFF_RSUM2 = 4,
+  QB_CUTOFF_SUM1 = 5,
+  QB_CUTOFF_RSUM1 = 6
+};
+
+/* contraction engine selection for qb_contract_pair */
+enum {
+  QB_ENGINE_AUTO = 0, /* heuristic                                    */
+  QB_ENGINE_DMMA = 1, /* native fp64 tensor-core path (DMMA)          */
+  QB_ENGINE_OZAKI = 2 /* tcgen05 int8 error-free-split path (fp64)    */
+};
+
+/* ---- library ---------------------------------------------------------- */
+int qb_abi_version(void);
+const char *qb_last_error(void);
+/* number of kernels launched by this library in this process (monotonic) */
+int64_t qb_launch_count(void);
+
+/* ---- pairwise contraction --------------------------------------------- */
+/*
+ * C[labelsC] = sum over labels not in C of  op(A)[labelsA] * op(B)[labelsB]
+ *
+ * Labels are arbitrary int32 mode names (the integer image of quimb's index
+ * names).  A label in A and B but not C is contracted; in A, B and C it is a
+ * batch ("hyper") index; in only one input and not C it is summed over; a
+ * label repeated inside one input takes that input's diagonal.  Every label
+ * of C must appear in A or B.  No operand is transposed or copied: the index
+ * permutation is folded into the kernel's tile loads / stores.
+ * conjA / conjB conjugate complex inputs on load.
+ * workspace may be NULL when qb_contract_pair_workspace() returns 0.
+ */
+int qb_contract_pair(const qb_tensor_t *A, const int32_t *labelsA,
+                     const qb_tensor_t *B, const int32_t *labelsB,
+                     qb_tensor_t *C, const int32_t *labelsC, int conjA,
+                     int conjB, int engine, void *workspace,
+                     size_t workspace_bytes, void *stream);
+
+int64_t qb_contract_pair_workspace(const qb_tensor_t *A,
+                                   const int32_t *labelsA,
+                                   const qb_tensor_t *B,
+                                   const int32_t *labelsB, const qb_tensor_t *C,
+                                   const int32_t *labelsC, int engine);
+
+/*
+ * Host-only: run the planner and report the GEMM view it derived.
+ * out[0..7] = M, N, K, batch, n_m_modes, n_n_modes, n_k_modes, n_batch_modes
+ * out[8] = tile config id, out[9] = split-k factor, out[10] = vecA,
+ * out[11] = vecB, out[12] = vecC.  Needs no GPU; used by the CPU test-suite.
+ */
+int qb_contract_pair_plan(const qb_tensor_t *A, const int32_t *labelsA,
+                          const qb_tensor_t *B, const int32_t *labelsB,
+                          const qb_tensor_t *C, const int32_t *labelsC,
+                          int64_t *out16);
+
+/*
+ * Many independent same-signature contractions in one launch: A[i], B[i], C[i]
+ * share shape/stride/labels (taken from A0/B0/C0) but have their own base
+ * pointers given in device arrays of `count` pointers.
+ */
+int qb_contract_batched(const qb_tensor_t *A0, const int32_t *labelsA,
+                        const qb_tensor_t *B0, const int32_t *labelsB,
+                        qb_tensor_t *C0, const int32_t *labelsC,
+                        const void *const *dA, const void *const *dB,
+                        void *const *dC, int64_t count, int conjA, int conjB,
+                        void *stream);
+
+/* ---- layout / element-wise -------------------------------------------- */
+/* dst (any strides) = src (any strides), same shape; optional conjugation */
+int qb_permute(const qb_tensor_t *src, qb_tensor_t *dst, int conj,
+               void *stream);
+/* y = alpha * x + beta * y over n contiguous elements (alpha,beta: re,im) */
+int qb_axpby(int dtype, int64_t n, const double alpha[2], const void *x,
+             const double beta[2], void *y, void *stream);
+/* x *= alpha / (*dev_scalar)  (dev_scalar may be NULL); Lanczos normalise */
+int qb_scale(int dtype, int64_t n, const double alpha[2],
+             const void *dev_div_scalar, void *x, void *stream);
+/* out[0] (device, same dtype as x; complex: conj(x).y) = <x|y>; deterministic
+ * two-stage reduction; workspace >= qb_dot_workspace(n) bytes */
+int qb_dot(int dtype, int64_t n, const void *x, const void *y, void *out,
+           void *workspace, void *stream);
+int64_t qb_dot_workspace(int64_t n);
+/* x (rows x cols, row-major contiguous) *= d[col]^p  (side=1) or d[row]^p
+ * (side=0); p in {1, 0.5}; d is real (f32 for F32/C64, f64 otherwise) */
+int qb_scale_diag(int dtype, int64_t rows, int64_t cols, void *x,
+                  const void *d, int side, int sqrt_d, void *stream);
+
+/* ---- decompositions ---------------------------------------------------- */
+/*
+ * Stabilised thin QR of a row-major contiguous m x n matrix X (m >= n):
+ * Q (m x n, row-major), R (n x n, row-major, upper triangular, diag >= 0).
+ * Either output may be NULL.  decomp.py:2055-2216.
+ */
+int qb_qr_stab(int dtype, int64_t m, int64_t n, const void *X, void *Q,
+               void *R, int stabilized, void *workspace,
+               size_t workspace_bytes, void *stream);
+int64_t qb_qr_workspace(int dtype, int64_t m, int64_t n);
+
+/*
+ * Thin SVD of a row-major contiguous m x n matrix X by one-sided block
+ * Jacobi: U (m x k), S (k, real, descending), VH (k x n), k = min(m, n).
+ * sweeps_out / offnorm_out (host) report convergence.
+ */
+int qb_svd(int dtype, int64_t m, int64_t n, const void *X, void *U, void *S,
+           void *VH, void *workspace, size_t workspace_bytes,
+           int *sweeps_out, void *stream);
+int64_t qb_svd_workspace(int dtype, int64_t m, int64_t n);
+
+/*
+ * Host-side truncation rule of svd_truncated's numba core,
+ * decomp.py:901-937 (_compute_number_svals_to_keep_numba) followed by the
+ * max_bond clamp of decomp.py:1000-1004.  s: host array, descending.
+ */
+int qb_svals_to_keep(const double *s, int64_t n, double cutoff,
+                     int cutoff_mode, int64_t max_bond, int renorm,
+                     int64_t *n_keep, double *renorm_factor,
+                     double *trunc_error);
+
+/* ---- device queries / microbenchmarks ---------------------------------- */
+/* sustained DMMA (fp64 tensor core) rate of the current device in TFLOP/s */
+int qb_measure_dmma_peak(double *tflops, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QUIMB_B200_H */

@@ -1,0 +1,292 @@
+"""Device array type of the ``quimb_b200`` backend.
+
+quimb keeps whatever object it is given in ``Tensor._data`` as long as it has
+a ``.shape`` (quimb/tensor/array_ops.py:31-33) and dispatches every numeric
+call through autoray on ``type(x).__module__.split('.')[0]`` -- which for this
+class is ``"quimb_b200"``, so ``do("tensordot", a, b, axes)`` lands on
+:func:`quimb_b200.tensordot`.
+
+The array wraps a ``torch.Tensor`` living on a CUDA device.  torch is the
+*container* (allocator, strides, streams); the arithmetic on the hot path
+(contraction, permute-copy, QR/SVD, Lanczos algebra) is done by the CUDA
+kernels behind the C ABI.  Views (``transpose``, slicing, ``conj`` of real
+data) never copy: the contraction kernel consumes arbitrary strides.
+"""
+
+import numbers
+
+import numpy as np
+import torch
+
+from . import _lib
+
+_NP2TORCH = {
+    np.dtype("float32"): torch.float32,
+    np.dtype("float64"): torch.float64,
+    np.dtype("complex64"): torch.complex64,
+    np.dtype("complex128"): torch.complex128,
+    np.dtype("int64"): torch.int64,
+    np.dtype("int32"): torch.int32,
+    np.dtype("bool"): torch.bool,
+}
+_TORCH2NP = {v: k for k, v in _NP2TORCH.items()}
+
+
+def torch_dtype(dt):
+    if isinstance(dt, torch.dtype):
+        return dt
+    if isinstance(dt, str) and dt.startswith("torch."):
+        dt = dt[6:]
+    return _NP2TORCH[np.dtype(dt)]
+
+
+def default_device():
+    if not torch.cuda.is_available():
+        raise _lib.QuimbB200Error(
+            "quimb_b200 needs a CUDA device (no CPU fallback exists)")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+class Array:
+    """A strided view of device memory (``torch.Tensor`` on cuda) plus a lazy
+    conjugation flag that the contraction kernel folds into its loads."""
+
+    __slots__ = ("t", "cj")
+    __array_priority__ = 1000
+
+    def __init__(self, t, cj=False):
+        if isinstance(t, Array):
+            t, cj = t.t, (t.cj != cj)
+        if not isinstance(t, torch.Tensor):
+            raise TypeError(f"expected torch.Tensor, got {type(t)}")
+        self.t = t
+        # conjugating real data is the identity
+        self.cj = bool(cj) and t.dtype.is_complex
+
+    # ---- protocol quimb relies on -------------------------------------
+    @property
+    def shape(self):
+        return tuple(self.t.shape)
+
+    @property
+    def ndim(self):
+        return self.t.dim()
+
+    @property
+    def size(self):
+        return self.t.numel()
+
+    @property
+    def dtype(self):
+        return _TORCH2NP[self.t.dtype]
+
+    @property
+    def device(self):
+        return self.t.device
+
+    def __len__(self):
+        return self.t.shape[0]
+
+    def __repr__(self):
+        return (f"quimb_b200.Array(shape={self.shape}, dtype={self.dtype.name},"
+                f" device={self.t.device}{', conj' if self.cj else ''})")
+
+    # ---- materialisation ----------------------------------------------
+    def resolve(self):
+        """torch view with any pending conjugation applied (may copy)."""
+        if self.cj:
+            from .ops import materialize
+            return materialize(self).t
+        return self.t
+
+    def item(self):
+        v = self.t.item()
+        return v.conjugate() if self.cj else v
+
+    def __float__(self):
+        return float(self.item().real if isinstance(self.item(), complex)
+                     else self.item())
+
+    def __complex__(self):
+        return complex(self.item())
+
+    def __int__(self):
+        return int(self.item())
+
+    def __bool__(self):
+        return bool(self.item())
+
+    def __array__(self, dtype=None, copy=None):
+        out = self.resolve().detach().cpu().numpy()
+        return out if dtype is None else out.astype(dtype)
+
+    def to_numpy(self):
+        return self.__array__()
+
+    # ---- views ----------------------------------------------------------
+    def conj(self):
+        return Array(self.t, not self.cj)
+
+    conjugate = conj
+
+    @property
+    def real(self):
+        return Array(self.resolve().real)
+
+    @property
+    def imag(self):
+        t = self.resolve()
+        return Array(t.imag if t.dtype.is_complex else torch.zeros_like(t))
+
+    @property
+    def T(self):
+        return Array(self.t.permute(*reversed(range(self.t.dim()))), self.cj)
+
+    @property
+    def H(self):
+        return self.T.conj()
+
+    def transpose(self, *axes):
+        if len(axes) == 1 and not isinstance(axes[0], numbers.Integral):
+            axes = tuple(axes[0])
+        if not axes:
+            axes = tuple(reversed(range(self.t.dim())))
+        return Array(self.t.permute(*axes), self.cj)
+
+    def swapaxes(self, a, b):
+        return Array(self.t.transpose(a, b), self.cj)
+
+    def reshape(self, *shape):
+        from .ops import reshape
+        if len(shape) == 1 and not isinstance(shape[0], numbers.Integral):
+            shape = tuple(shape[0])
+        return reshape(self, shape)
+
+    def ravel(self):
+        return self.reshape(-1)
+
+    flatten = ravel
+
+    def squeeze(self, axis=None):
+        t = self.t.squeeze() if axis is None else self.t.squeeze(axis)
+        return Array(t, self.cj)
+
+    def astype(self, dtype, copy=True):
+        td = torch_dtype(dtype)
+        t = self.resolve()
+        if td == t.dtype:
+            return Array(t.clone() if copy else t)
+        if t.dtype.is_complex and not td.is_complex:
+            t = t.real
+        return Array(t.to(td))
+
+    def copy(self):
+        from .ops import materialize
+        return materialize(self, force=True)
+
+    def clone(self):
+        return self.copy()
+
+    def __getitem__(self, idx):
+        if isinstance(idx, Array):
+            idx = idx.t
+        elif isinstance(idx, tuple):
+            idx = tuple(i.t if isinstance(i, Array) else i for i in idx)
+        return Array(self.t[idx], self.cj)
+
+    def __setitem__(self, idx, val):
+        if self.cj:
+            raise ValueError("cannot assign into a lazily conjugated view")
+        if isinstance(val, Array):
+            val = val.resolve()
+        self.t[idx] = val
+
+    def __iter__(self):
+        for i in range(self.t.shape[0]):
+            yield Array(self.t[i], self.cj)
+
+    # ---- arithmetic (element-wise: torch as the container library) -------
+    def _bin(self, other, fn, reflect=False):
+        a = self.resolve()
+        if isinstance(other, Array):
+            b = other.resolve()
+        elif isinstance(other, np.ndarray):
+            b = torch.as_tensor(other, device=a.device)
+        elif isinstance(other, (numbers.Number, np.generic)):
+            b = other.item() if isinstance(other, np.generic) else other
+        elif isinstance(other, torch.Tensor):
+            b = other
+        else:
+            return NotImplemented
+        return Array(fn(b, a) if reflect else fn(a, b))
+
+    def __add__(self, o): return self._bin(o, torch.add)
+    def __radd__(self, o): return self._bin(o, torch.add, True)
+    def __sub__(self, o): return self._bin(o, torch.sub)
+    def __rsub__(self, o): return self._bin(o, lambda x, y: x - y, True)
+    def __mul__(self, o): return self._bin(o, torch.mul)
+    def __rmul__(self, o): return self._bin(o, torch.mul, True)
+    def __truediv__(self, o): return self._bin(o, torch.div)
+    def __rtruediv__(self, o): return self._bin(o, lambda x, y: x / y, True)
+    def __pow__(self, o): return self._bin(o, torch.pow)
+    def __rpow__(self, o): return self._bin(o, lambda x, y: x ** y, True)
+    def __neg__(self): return Array(-self.resolve())
+    def __pos__(self): return self
+    def __abs__(self): return Array(self.t.abs())
+    def __lt__(self, o): return self._bin(o, torch.lt)
+    def __le__(self, o): return self._bin(o, torch.le)
+    def __gt__(self, o): return self._bin(o, torch.gt)
+    def __ge__(self, o): return self._bin(o, torch.ge)
+    def __eq__(self, o): return self._bin(o, torch.eq)
+    def __ne__(self, o): return self._bin(o, torch.ne)
+    __hash__ = None
+
+    def __iadd__(self, o):
+        r = self + o
+        self.t, self.cj = r.t, False
+        return self
+
+    def __isub__(self, o):
+        r = self - o
+        self.t, self.cj = r.t, False
+        return self
+
+    def __imul__(self, o):
+        r = self * o
+        self.t, self.cj = r.t, False
+        return self
+
+    def __itruediv__(self, o):
+        r = self / o
+        self.t, self.cj = r.t, False
+        return self
+
+    def __matmul__(self, other):
+        from .ops import matmul
+        return matmul(self, other)
+
+    def __rmatmul__(self, other):
+        from .ops import matmul, asarray
+        return matmul(asarray(other), self)
+
+    # reductions used by quimb on arrays directly
+    def sum(self, axis=None, **kw):
+        from .ops import sum as _sum
+        return _sum(self, axis=axis, **kw)
+
+    def max(self, axis=None):
+        from .ops import max as _max
+        return _max(self, axis=axis)
+
+    def min(self, axis=None):
+        from .ops import min as _min
+        return _min(self, axis=axis)
+
+    def all(self):
+        return bool(self.t.all().item())
+
+    def any(self):
+        return bool(self.t.any().item())
+
+    def tolist(self):
+        return self.__array__().tolist()

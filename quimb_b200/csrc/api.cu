@@ -1,0 +1,152 @@
+// extern "C" entry points declared in include/quimb_b200.h
+#include <stdarg.h>
+#include <stdlib.h>
+
+#include <vector>
+
+#include "common.cuh"
+#include "plan.h"
+
+namespace qb {
+
+static thread_local char g_err[1024] = "";
+std::atomic<int64_t> g_launch_count{0};
+
+void set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) !=
+            cudaSuccess)
+      n = 148;
+  }
+  return n;
+}
+
+int launch_contract_f64(const PairPlan &plan, cudaStream_t st);
+int launch_contract_c128(const PairPlan &plan, cudaStream_t st);
+int launch_fill_zero(const qb_tensor_t *C, cudaStream_t st);
+
+static int check_device_dtype(int dt) {
+  if (dt != QB_F64 && dt != QB_C128) {
+    set_error("dtype %d is not supported by the contraction engine yet "
+              "(supported: f64, c128)", dt);
+    return -1;
+  }
+  return 0;
+}
+
+}  // namespace qb
+
+using namespace qb;
+
+extern "C" {
+
+int qb_abi_version(void) { return QB_ABI_VERSION; }
+const char *qb_last_error(void) { return g_err; }
+int64_t qb_launch_count(void) { return g_launch_count.load(); }
+
+int qb_contract_pair_plan(const qb_tensor_t *A, const int32_t *la,
+                          const qb_tensor_t *B, const int32_t *lb,
+                          const qb_tensor_t *C, const int32_t *lc,
+                          int64_t *out) {
+  PairPlan plan;
+  int rc = plan_pair(A, la, B, lb, C, lc, 0, 0, plan);
+  if (rc) return rc;
+  const ContractParams &p = plan.p;
+  out[0] = p.M; out[1] = p.N; out[2] = p.K; out[3] = p.nbatch;
+  out[4] = p.m.n; out[5] = p.n.n; out[6] = p.k.n; out[7] = p.b.n;
+  out[8] = plan.cfg; out[9] = p.splitk; out[10] = p.vecA; out[11] = p.vecB;
+  out[12] = p.vecC; out[13] = p.thrA; out[14] = p.thrB;
+  out[15] = plan.empty_out ? 2 : (plan.zero_fill ? 1 : 0);
+  return 0;
+}
+
+int64_t qb_contract_pair_workspace(const qb_tensor_t *A, const int32_t *la,
+                                   const qb_tensor_t *B, const int32_t *lb,
+                                   const qb_tensor_t *C, const int32_t *lc,
+                                   int engine) {
+  (void)engine;
+  PairPlan plan;
+  int rc = plan_pair(A, la, B, lb, C, lc, 0, 0, plan);
+  if (rc) return rc;
+  return plan_workspace_bytes(plan);
+}
+
+int qb_contract_pair(const qb_tensor_t *A, const int32_t *la,
+                     const qb_tensor_t *B, const int32_t *lb, qb_tensor_t *C,
+                     const int32_t *lc, int conjA, int conjB, int engine,
+                     void *workspace, size_t workspace_bytes, void *stream) {
+  (void)engine;
+  PairPlan plan;
+  // QB_FORCE_CFG: tuning/debug override of the tile configuration
+  static const int force_cfg = [] {
+    const char *e = getenv("QB_FORCE_CFG");
+    return e ? atoi(e) : -1;
+  }();
+  int rc = plan_pair(A, la, B, lb, C, lc, conjA, conjB, plan, force_cfg);
+  if (rc) return rc;
+  if ((rc = check_device_dtype(plan.dtype))) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (plan.empty_out) return 0;
+  if (plan.zero_fill) return launch_fill_zero(C, st);
+  int64_t need = plan_workspace_bytes(plan);
+  if (need > 0) {
+    if (!workspace || (int64_t)workspace_bytes < need) {
+      set_error("workspace too small: need %lld bytes, got %lld",
+                (long long)need, (long long)workspace_bytes);
+      return -10;
+    }
+    plan.p.partial = static_cast<double *>(workspace);
+  }
+  if (plan.dtype == QB_F64) return launch_contract_f64(plan, st);
+  return launch_contract_c128(plan, st);
+}
+
+int qb_contract_batched(const qb_tensor_t *A0, const int32_t *la,
+                        const qb_tensor_t *B0, const int32_t *lb,
+                        qb_tensor_t *C0, const int32_t *lc,
+                        const void *const *dA, const void *const *dB,
+                        void *const *dC, int64_t count, int conjA, int conjB,
+                        void *stream) {
+  PairPlan plan;
+  int rc = plan_pair(A0, la, B0, lb, C0, lc, conjA, conjB, plan);
+  if (rc) return rc;
+  if ((rc = check_device_dtype(plan.dtype))) return rc;
+  if (plan.p.b.n) {
+    set_error("qb_contract_batched: batch labels are not allowed inside the "
+              "per-item signature");
+    return -2;
+  }
+  if (count <= 0 || plan.empty_out) return 0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (plan.zero_fill) {
+    set_error("qb_contract_batched: zero-extent contracted index");
+    return -2;
+  }
+  // pointer-array batch: no split-K (tiles x count is the parallelism)
+  plan.p.splitk = 1;
+  plan.p.k_per_split = cdiv(plan.p.K, 16) * 16;
+  plan.p.dA = dA; plan.p.dB = dB; plan.p.dC = dC;
+  int64_t done = 0;
+  while (done < count) {
+    int64_t chunk = std::min<int64_t>(count - done, 65535);
+    plan.p.nbatch = chunk;
+    plan.p.dA = dA + done; plan.p.dB = dB + done; plan.p.dC = dC + done;
+    if (plan.dtype == QB_F64) rc = launch_contract_f64(plan, st);
+    else rc = launch_contract_c128(plan, st);
+    if (rc) return rc;
+    done += chunk;
+  }
+  return 0;
+}
+
+}  // extern "C"

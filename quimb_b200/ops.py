@@ -1,0 +1,441 @@
+"""Function surface of the ``quimb_b200`` array backend (what
+``autoray.do(name, ..., like="quimb_b200")`` resolves to).
+
+Hot-path functions (``tensordot``, ``einsum``, ``transpose``, ``reshape``,
+``linalg.qr``, ``linalg.svd`` and the fused quimb drivers) run on the CUDA
+kernels behind the C ABI.  Cold element-wise helpers forward to torch on the
+wrapped tensor (torch is the container library here).
+"""
+
+import ctypes
+import numbers
+
+import numpy as np
+import torch
+
+from . import _lib
+from .array import Array, default_device, torch_dtype
+from .contract import contract_pair
+
+
+# ------------------------------------------------------------ conversion ---
+def asarray(x, dtype=None, device=None):
+    if isinstance(x, Array):
+        return x if dtype is None else x.astype(dtype, copy=False)
+    if isinstance(x, torch.Tensor):
+        t = x
+    else:
+        t = torch.as_tensor(np.asarray(x))
+    dev = device or (t.device if t.device.type == "cuda" else default_device())
+    if t.device != dev:
+        if t.device.type == "cpu" and t.numel() * t.element_size() >= (1 << 20):
+            t = t.pin_memory()
+        t = t.to(dev, non_blocking=True)
+    if dtype is not None:
+        t = t.to(torch_dtype(dtype))
+    return Array(t)
+
+
+array = asarray
+
+
+def to_numpy(x):
+    return x.__array__() if isinstance(x, Array) else np.asarray(x)
+
+
+def _t(x):
+    return x.resolve() if isinstance(x, Array) else x
+
+
+def _wrap(fn):
+    def wrapped(*args, **kwargs):
+        args = [_t(a) for a in args]
+        kwargs = {k: _t(v) for k, v in kwargs.items()}
+        if "axis" in kwargs:
+            ax = kwargs.pop("axis")
+            if ax is not None:
+                kwargs["dim"] = ax
+        out = fn(*args, **kwargs)
+        if isinstance(out, torch.Tensor):
+            return Array(out)
+        if isinstance(out, tuple) and hasattr(out, "_fields"):
+            return out[0] if not isinstance(out[0], torch.Tensor) else Array(out[0])
+        return out
+    return wrapped
+
+
+# ------------------------------------------------------------- layout ------
+def materialize(x, force=False):
+    """Contiguous copy of a strided / lazily conjugated view through the
+    permute kernel (this is quimb's fuse transpose-copy)."""
+    if not isinstance(x, Array):
+        x = asarray(x)
+    t = x.t
+    if not force and not x.cj and t.is_contiguous():
+        return x
+    _lib.require_cuda(t)
+    out = torch.empty(t.shape, dtype=t.dtype, device=t.device)
+    if t.numel():
+        lib = _lib.load()
+        rc = lib.qb_permute(_lib.desc(t), _lib.desc(out), int(x.cj),
+                            _lib.stream_ptr())
+        _lib.check(rc, "qb_permute")
+    return Array(out)
+
+
+def reshape(x, shape):
+    if not isinstance(x, Array):
+        x = asarray(x)
+    if isinstance(shape, numbers.Integral):
+        shape = (shape,)
+    shape = tuple(int(s) for s in shape)
+    try:
+        return Array(x.t.view(shape), x.cj)  # free when strides allow it
+    except RuntimeError:
+        return Array(materialize(x).t.view(shape))
+
+
+def transpose(x, axes=None):
+    if not isinstance(x, Array):
+        x = asarray(x)
+    return x.transpose() if axes is None else x.transpose(*axes)
+
+
+def swapaxes(x, a, b):
+    return x.swapaxes(a, b)
+
+
+def moveaxis(x, src, dst):
+    return Array(torch.movedim(x.t, src, dst), x.cj)
+
+
+def conj(x):
+    return x.conj() if isinstance(x, Array) else np.conj(x)
+
+
+conjugate = conj
+
+
+def real(x):
+    return x.real
+
+
+def imag(x):
+    return x.imag
+
+
+def shape(x):
+    return tuple(x.shape)
+
+
+def ndim(x):
+    return x.ndim
+
+
+def size(x):
+    return x.size
+
+
+def squeeze(x, axis=None):
+    return x.squeeze(axis)
+
+
+def expand_dims(x, axis):
+    return Array(x.t.unsqueeze(axis), x.cj)
+
+
+def ravel(x):
+    return x.ravel()
+
+
+def astype(x, dtype, **kw):
+    return x.astype(dtype)
+
+
+def copy(x):
+    return x.copy()
+
+
+# ---------------------------------------------------------- contraction ----
+def tensordot(a, b, axes=2):
+    """numpy.tensordot semantics; one kernel launch, no transposes."""
+    a, b = asarray(a), asarray(b)
+    if a.dtype != b.dtype:
+        dt = np.result_type(a.dtype, b.dtype)
+        a, b = a.astype(dt, copy=False), b.astype(dt, copy=False)
+    na, nb = a.ndim, b.ndim
+    if isinstance(axes, numbers.Integral):
+        axa = list(range(na - axes, na))
+        axb = list(range(axes))
+    else:
+        axa, axb = axes
+        axa = [axa] if isinstance(axa, numbers.Integral) else list(axa)
+        axb = [axb] if isinstance(axb, numbers.Integral) else list(axb)
+    axa = [ax % na if na else ax for ax in axa]
+    axb = [ax % nb if nb else ax for ax in axb]
+    if len(axa) != len(axb):
+        raise ValueError("shape-mismatch for sum")
+    for i, j in zip(axa, axb):
+        if a.shape[i] != b.shape[j]:
+            raise ValueError("shape-mismatch for sum")
+    la = list(range(na))
+    lb = [na + j for j in range(nb)]
+    for i, j in zip(axa, axb):
+        lb[j] = la[i]
+    lc = [l for i, l in enumerate(la) if i not in axa] + [
+        l for j, l in enumerate(lb) if j not in axb
+    ]
+    out = contract_pair(a.t, la, b.t, lb, lc, conj_a=a.cj, conj_b=b.cj)
+    return Array(out)
+
+
+def matmul(a, b):
+    a, b = asarray(a), asarray(b)
+    if a.ndim <= 2 and b.ndim <= 2:
+        if a.ndim == 0 or b.ndim == 0:
+            raise ValueError("matmul: scalar operands")
+        return tensordot(a, b, axes=((a.ndim - 1,), (0,)))
+    # broadcast batched matmul via einsum labels
+    nb = max(a.ndim, b.ndim) - 2
+    la = list(range(nb - (a.ndim - 2), nb)) + [100, 101]
+    lb = list(range(nb - (b.ndim - 2), nb)) + [101, 102]
+    lc = list(range(nb)) + [100, 102]
+    return Array(contract_pair(a.t, la, b.t, lb, lc, conj_a=a.cj, conj_b=b.cj))
+
+
+def dot(a, b):
+    return matmul(a, b)
+
+
+def _parse_einsum(eq, nops):
+    eq = eq.replace(" ", "")
+    if "..." in eq:
+        raise NotImplementedError("einsum ellipsis is not supported")
+    if "->" in eq:
+        lhs, rhs = eq.split("->")
+    else:
+        lhs = eq
+        counts = {}
+        for c in lhs.replace(",", ""):
+            counts[c] = counts.get(c, 0) + 1
+        rhs = "".join(sorted(c for c, n in counts.items() if n == 1))
+    terms = lhs.split(",")
+    if len(terms) != nops:
+        raise ValueError("einsum: operand count does not match equation")
+    return terms, rhs
+
+
+def einsum(eq, *operands):
+    """einsum for any number of operands: unary/pairwise cases are one kernel
+    launch (batch, summed and diagonal indices included); more operands go
+    through the tree executor."""
+    ops = [asarray(o) for o in operands]
+    terms, rhs = _parse_einsum(eq, len(ops))
+    sym = {}
+    for c in "".join(terms) + rhs:
+        sym.setdefault(c, len(sym))
+    if len(ops) == 1:
+        x = ops[0]
+        one = Array(torch.ones((), dtype=x.t.dtype, device=x.t.device))
+        out = contract_pair(x.t, [sym[c] for c in terms[0]], one.t, [],
+                            [sym[c] for c in rhs], conj_a=x.cj)
+        return Array(out)
+    if len(ops) == 2:
+        a, b = ops
+        if a.dtype != b.dtype:
+            dt = np.result_type(a.dtype, b.dtype)
+            a, b = a.astype(dt, copy=False), b.astype(dt, copy=False)
+        out = contract_pair(a.t, [sym[c] for c in terms[0]], b.t,
+                            [sym[c] for c in terms[1]], [sym[c] for c in rhs],
+                            conj_a=a.cj, conj_b=b.cj)
+        return Array(out)
+    from .tree import array_contract
+    return array_contract(ops, [tuple(t) for t in terms], tuple(rhs))
+
+
+def trace(x, axis1=0, axis2=1):
+    x = asarray(x)
+    lab = list(range(x.ndim))
+    lab[axis2] = lab[axis1]
+    out_l = [l for i, l in enumerate(lab) if i not in (axis1, axis2)]
+    one = torch.ones((), dtype=x.t.dtype, device=x.t.device)
+    return Array(contract_pair(x.t, lab, one, [], out_l, conj_a=x.cj))
+
+
+def diagonal(x, offset=0, axis1=0, axis2=1):
+    return Array(torch.diagonal(x.resolve(), offset, axis1, axis2))
+
+
+def diag(x, k=0):
+    return Array(torch.diag(x.resolve(), k))
+
+
+# ------------------------------------------------- element-wise / reductions
+sqrt = _wrap(torch.sqrt)
+exp = _wrap(torch.exp)
+log = _wrap(torch.log)
+log2 = _wrap(torch.log2)
+log10 = _wrap(torch.log10)
+sin = _wrap(torch.sin)
+cos = _wrap(torch.cos)
+tanh = _wrap(torch.tanh)
+sign = _wrap(torch.sgn)
+cumsum = _wrap(torch.cumsum)
+count_nonzero = _wrap(torch.count_nonzero)
+where = _wrap(torch.where)
+clip = _wrap(torch.clamp)
+flip = _wrap(torch.flip)
+isfinite = _wrap(torch.isfinite)
+isnan = _wrap(torch.isnan)
+argmax = _wrap(torch.argmax)
+argmin = _wrap(torch.argmin)
+kron = _wrap(torch.kron)
+equal = _wrap(torch.eq)
+power = _wrap(torch.pow)
+multiply = _wrap(torch.mul)
+add = _wrap(torch.add)
+subtract = _wrap(torch.sub)
+divide = _wrap(torch.div)
+take = _wrap(torch.take)
+tril = _wrap(torch.tril)
+triu = _wrap(torch.triu)
+
+
+def abs(x):  # noqa: A001
+    return Array(torch.abs(x.t)) if isinstance(x, Array) else np.abs(x)
+
+
+absolute = abs
+
+
+def sum(x, axis=None, **kw):  # noqa: A001
+    t = _t(x)
+    return Array(t.sum() if axis is None else t.sum(dim=axis))
+
+
+def max(x, axis=None):  # noqa: A001
+    t = _t(x)
+    return Array(t.max() if axis is None else t.max(dim=axis).values)
+
+
+def min(x, axis=None):  # noqa: A001
+    t = _t(x)
+    return Array(t.min() if axis is None else t.min(dim=axis).values)
+
+
+def mean(x, axis=None):
+    t = _t(x)
+    return Array(t.mean() if axis is None else t.mean(dim=axis))
+
+
+def all(x):  # noqa: A001
+    return bool(_t(x).all().item())
+
+
+def any(x):  # noqa: A001
+    return bool(_t(x).any().item())
+
+
+def allclose(a, b, rtol=1e-5, atol=1e-8):
+    a, b = _t(asarray(a)), _t(asarray(b))
+    return bool(torch.allclose(a, b.to(a.dtype), rtol=rtol, atol=atol))
+
+
+def stack(arrays, axis=0):
+    return Array(torch.stack([_t(asarray(a)) for a in arrays], dim=axis))
+
+
+def concatenate(arrays, axis=0):
+    return Array(torch.cat([_t(asarray(a)) for a in arrays], dim=axis))
+
+
+def pad(x, pad_width, mode="constant", constant_values=0):
+    flat = []
+    for lo, hi in reversed(list(pad_width)):
+        flat += [lo, hi]
+    return Array(torch.nn.functional.pad(_t(x), flat, value=constant_values))
+
+
+def zeros(shape, dtype="float64", device=None):
+    return Array(torch.zeros(shape, dtype=torch_dtype(dtype),
+                             device=device or default_device()))
+
+
+def ones(shape, dtype="float64", device=None):
+    return Array(torch.ones(shape, dtype=torch_dtype(dtype),
+                            device=device or default_device()))
+
+
+def empty(shape, dtype="float64", device=None):
+    return Array(torch.empty(shape, dtype=torch_dtype(dtype),
+                             device=device or default_device()))
+
+
+def eye(n, m=None, dtype="float64", device=None):
+    return Array(torch.eye(n, m if m is not None else n,
+                           dtype=torch_dtype(dtype),
+                           device=device or default_device()))
+
+
+def arange(*args, dtype="int64", device=None):
+    return Array(torch.arange(*args, dtype=torch_dtype(dtype),
+                              device=device or default_device()))
+
+
+def zeros_like(x):
+    return Array(torch.zeros_like(x.t))
+
+
+def ones_like(x):
+    return Array(torch.ones_like(x.t))
+
+
+# ---------------------------------------------- Lanczos vector algebra -----
+_DOT_WS = {}
+
+
+def _dot_ws(dev):
+    ws = _DOT_WS.get(dev.index)
+    if ws is None:
+        n = _lib.load().qb_dot_workspace(0)
+        ws = torch.empty(n, dtype=torch.uint8, device=dev)
+        _DOT_WS[dev.index] = ws
+    return ws
+
+
+def vdot(x, y):
+    """<x|y> = sum conj(x) * y as a 0-d device Array (deterministic)."""
+    x, y = materialize(asarray(x)), materialize(asarray(y))
+    lib = _lib.load()
+    out = torch.empty((), dtype=x.t.dtype, device=x.t.device)
+    rc = lib.qb_dot(_lib.qb_dtype(x.t.dtype), x.t.numel(), x.t.data_ptr(),
+                    y.t.data_ptr(), out.data_ptr(), _dot_ws(x.t.device).data_ptr(),
+                    _lib.stream_ptr())
+    _lib.check(rc, "qb_dot")
+    return Array(out)
+
+
+def axpby(alpha, x, beta, y):
+    """y <- alpha * x + beta * y in place (contiguous); returns y."""
+    lib = _lib.load()
+    a = (ctypes.c_double * 2)(complex(alpha).real, complex(alpha).imag)
+    b = (ctypes.c_double * 2)(complex(beta).real, complex(beta).imag)
+    if not (x.t.is_contiguous() and y.t.is_contiguous()) or x.cj or y.cj:
+        raise ValueError("axpby needs contiguous, resolved operands")
+    rc = lib.qb_axpby(_lib.qb_dtype(x.t.dtype), x.t.numel(), a, x.t.data_ptr(),
+                      b, y.t.data_ptr(), _lib.stream_ptr())
+    _lib.check(rc, "qb_axpby")
+    return y
+
+
+def scale_(x, alpha=1.0, div_by=None):
+    """x <- x * alpha / div_by (div_by: 0-d real device Array) in place."""
+    lib = _lib.load()
+    a = (ctypes.c_double * 2)(complex(alpha).real, complex(alpha).imag)
+    if not x.t.is_contiguous() or x.cj:
+        raise ValueError("scale_ needs a contiguous, resolved operand")
+    dptr = None if div_by is None else ctypes.c_void_p(div_by.t.data_ptr())
+    rc = lib.qb_scale(_lib.qb_dtype(x.t.dtype), x.t.numel(), a, dptr,
+                      x.t.data_ptr(), _lib.stream_ptr())
+    _lib.check(rc, "qb_scale")
+    return x

@@ -1,0 +1,291 @@
+"""Contraction-tree executor: the host-side mirror of what cotengra does for
+``quimb.tensor.contraction.array_contract`` (contraction.py:272-292) and
+``array_contract_expression`` (:296-299).
+
+A tree is a list of SSA steps ``(i, j) -> k``.  Every step is ONE launch of
+the pairwise contraction kernel, with the output written directly in the
+index order the next consumer wants -- so, unlike the numpy path
+(tensordot + transpose per node), no standalone transpose ever runs.
+
+External trees are accepted unchanged: anything with a ``get_path()`` method
+(cotengra.ContractionTree) or an explicit opt_einsum-style linear path.
+"""
+
+import itertools
+import math
+
+from . import ops
+from .array import Array
+from .contract import contract_pair
+
+
+# ------------------------------------------------------------- bookkeeping --
+def gen_output_inds(all_inds):
+    """Indices appearing exactly once in first-appearance order; an index
+    appearing more than twice is an error unless output_inds is given
+    (mirrors quimb/tensor/tensor_core.py:158-170)."""
+    freq = {}
+    for ix in all_inds:
+        freq[ix] = freq.get(ix, 0) + 1
+    for ix, f in freq.items():
+        if f > 2:
+            raise ValueError(
+                f"The index {ix} appears more than twice! If this is "
+                "intentionally a 'hyper' tensor network you will need to "
+                "explicitly supply `output_inds` when contracting for example."
+            )
+    return tuple(ix for ix, f in freq.items() if f == 1)
+
+
+class Tree:
+    """SSA contraction tree over ``inputs`` with per-node index tuples."""
+
+    def __init__(self, inputs, output, size_dict, ssa_steps):
+        self.inputs = [tuple(t) for t in inputs]
+        self.output = tuple(output)
+        self.size_dict = dict(size_dict)
+        self.steps = []  # (i, j, k, inds_k)
+        self._build(ssa_steps)
+
+    def _build(self, ssa_steps):
+        n = len(self.inputs)
+        inds = {i: t for i, t in enumerate(self.inputs)}
+        alive = set(range(n))
+        # appearance counts to know which indices are still needed
+        nxt = n
+        for i, j in ssa_steps:
+            alive.discard(i)
+            alive.discard(j)
+            need = set(self.output)
+            for a in alive:
+                need.update(inds[a])
+            ti, tj = inds[i], inds[j]
+            res = tuple(ix for ix in dict.fromkeys(ti + tj) if ix in need)
+            inds[nxt] = res
+            self.steps.append((i, j, nxt, res))
+            alive.add(nxt)
+            nxt += 1
+        if self.steps:
+            # last node is produced directly in the requested output order
+            i, j, k, res = self.steps[-1]
+            if set(res) != set(self.output):
+                raise ValueError("tree does not produce the requested output")
+            self.steps[-1] = (i, j, k, self.output)
+        self.node_inds = inds
+
+    def contraction_cost(self):
+        """sum over nodes of M*N*K (scalar multiply-adds), cotengra's
+        ``contraction_cost`` convention."""
+        inds = dict(enumerate(self.inputs))
+        tot = 0
+        for i, j, k, res in self.steps:
+            allix = set(inds[i]) | set(inds[j])
+            tot += math.prod(self.size_dict[ix] for ix in allix)
+            inds[k] = res
+        return tot
+
+    def contraction_width(self):
+        w = 1
+        for _, _, _, res in self.steps:
+            w = max(w, math.prod(self.size_dict[ix] for ix in res))
+        return math.log2(w)
+
+
+def linear_to_ssa(path, n):
+    ids = list(range(n))
+    nxt = n
+    ssa = []
+    for con in path:
+        con = sorted(con)
+        if len(con) != 2:
+            raise ValueError("only pairwise contraction paths are supported")
+        i, j = con
+        a, b = ids[i], ids[j]
+        ssa.append((a, b))
+        ids = [x for k, x in enumerate(ids) if k not in (i, j)] + [nxt]
+        nxt += 1
+    return ssa
+
+
+# ---------------------------------------------------------------- finders ---
+def _greedy_ssa(inputs, output, size_dict):
+    """Greedy: repeatedly contract the pair (sharing an index if any exists)
+    that minimises size(result) - size(a) - size(b)."""
+    inds = {i: tuple(t) for i, t in enumerate(inputs)}
+    sz = lambda t: math.prod(size_dict[ix] for ix in t)  # noqa: E731
+    ssa, nxt = [], len(inputs)
+    while len(inds) > 1:
+        keys = list(inds)
+        best = None
+        for a, b in itertools.combinations(keys, 2):
+            sa, sb = set(inds[a]), set(inds[b])
+            need = set(output)
+            for c in keys:
+                if c != a and c != b:
+                    need.update(inds[c])
+            res = tuple(ix for ix in dict.fromkeys(inds[a] + inds[b]) if ix in need)
+            key = (0 if sa & sb else 1, sz(res) - sz(inds[a]) - sz(inds[b]),
+                   math.prod(size_dict[ix] for ix in sa | sb))
+            if best is None or key < best[0]:
+                best = (key, a, b, res)
+        _, a, b, res = best
+        ssa.append((a, b))
+        del inds[a], inds[b]
+        inds[nxt] = res
+        nxt += 1
+    return ssa
+
+
+def _optimal_ssa(inputs, output, size_dict):
+    """Exact minimum-flop tree by dynamic programming over subsets."""
+    n = len(inputs)
+    inputs = [tuple(t) for t in inputs]
+
+    def boundary(mask):
+        outside = set(output)
+        for k in range(n):
+            if not mask >> k & 1:
+                outside.update(inputs[k])
+        seen = []
+        for k in range(n):
+            if mask >> k & 1:
+                for ix in inputs[k]:
+                    if ix in outside and ix not in seen:
+                        seen.append(ix)
+        return tuple(seen)
+
+    bnd = {1 << k: inputs[k] for k in range(n)}
+    cost = {1 << k: (0, None) for k in range(n)}
+    for r in range(2, n + 1):
+        for combo in itertools.combinations(range(n), r):
+            mask = 0
+            for k in combo:
+                mask |= 1 << k
+            bnd[mask] = boundary(mask)
+            best = None
+            sub = (mask - 1) & mask
+            while sub:
+                oth = mask ^ sub
+                if sub > oth:
+                    fl = math.prod(size_dict[ix]
+                                   for ix in set(bnd[sub]) | set(bnd[oth]))
+                    c = cost[sub][0] + cost[oth][0] + fl
+                    if best is None or c < best[0]:
+                        best = (c, sub, oth)
+                sub = (sub - 1) & mask
+            cost[mask] = (best[0], (best[1], best[2]))
+    ssa, ids, counter = [], {1 << k: k for k in range(n)}, [n]
+
+    def rec(mask):
+        if mask in ids:
+            return ids[mask]
+        a, b = cost[mask][1]
+        ia, ib = rec(a), rec(b)
+        ssa.append((ia, ib))
+        ids[mask] = counter[0]
+        counter[0] += 1
+        return ids[mask]
+
+    rec((1 << n) - 1)
+    return ssa
+
+
+def find_tree(inputs, output, size_dict, optimize="auto"):
+    n = len(inputs)
+    if hasattr(optimize, "get_path"):          # cotengra.ContractionTree
+        ssa = linear_to_ssa(optimize.get_path(), n)
+    elif isinstance(optimize, Tree):
+        return optimize
+    elif isinstance(optimize, (list, tuple)):  # explicit linear path
+        ssa = linear_to_ssa(optimize, n)
+    elif n <= 1:
+        ssa = []
+    elif optimize in ("optimal", "dp") or (
+            optimize in ("auto", "auto-hq", None) and n <= 9):
+        ssa = _optimal_ssa(inputs, output, size_dict)
+    elif optimize in ("greedy", "auto", "auto-hq", None):
+        ssa = _greedy_ssa(inputs, output, size_dict)
+    else:
+        raise ValueError(f"unknown optimize strategy {optimize!r}")
+    return Tree(inputs, output, size_dict, ssa)
+
+
+# --------------------------------------------------------------- executor ---
+def _labels(inds, table):
+    return [table.setdefault(ix, len(table)) for ix in inds]
+
+
+def execute(tree, arrays):
+    table = {}
+    nodes = {i: ops.asarray(a) for i, a in enumerate(arrays)}
+    inds = dict(enumerate(tree.inputs))
+    if not tree.steps:
+        (x,) = nodes.values()
+        t = inds[0]
+        if t == tree.output:
+            return x
+        one = ops.ones((), dtype=x.dtype, device=x.device)
+        return Array(contract_pair(x.t, _labels(t, table), one.t, [],
+                                   _labels(tree.output, table), conj_a=x.cj))
+    for i, j, k, res in tree.steps:
+        a, b = nodes.pop(i), nodes.pop(j)
+        if a.dtype != b.dtype:
+            import numpy as np
+            dt = np.result_type(a.dtype, b.dtype)
+            a, b = a.astype(dt, copy=False), b.astype(dt, copy=False)
+        out = contract_pair(a.t, _labels(inds[i], table), b.t,
+                            _labels(inds[j], table), _labels(res, table),
+                            conj_a=a.cj, conj_b=b.cj)
+        nodes[k] = Array(out)
+        inds[k] = res
+    (out,) = nodes.values()
+    return out
+
+
+def _sizes(inputs, arrays):
+    size_dict = {}
+    for t, x in zip(inputs, arrays):
+        if len(t) != len(x.shape):
+            raise ValueError(f"indices {t} do not match array rank {x.shape}")
+        for ix, d in zip(t, x.shape):
+            if size_dict.setdefault(ix, int(d)) != int(d):
+                raise ValueError(f"size mismatch on index {ix}")
+    return size_dict
+
+
+def array_contract(arrays, inputs, output=None, optimize="auto"):
+    """Contract device arrays labelled by hashable indices."""
+    arrays = [ops.asarray(a) for a in arrays]
+    inputs = [tuple(t) for t in inputs]
+    if output is None:
+        output = gen_output_inds(itertools.chain.from_iterable(inputs))
+    tree = find_tree(inputs, tuple(output), _sizes(inputs, arrays), optimize)
+    return execute(tree, arrays)
+
+
+class ContractExpression:
+    """Reusable contraction (quimb's ``get='expression'`` with ``constants``,
+    tensor_core.py:176-193): the tree is found once, constants stay resident
+    on the device."""
+
+    def __init__(self, inputs, output, shapes, optimize="auto", constants=None):
+        self.inputs = [tuple(t) for t in inputs]
+        self.output = tuple(output)
+        size_dict = {}
+        for t, s in zip(self.inputs, shapes):
+            for ix, d in zip(t, s):
+                size_dict[ix] = int(d)
+        self.tree = find_tree(self.inputs, self.output, size_dict, optimize)
+        self.constants = {i: ops.asarray(c) for i, c in (constants or {}).items()}
+        self.var_pos = [i for i in range(len(self.inputs))
+                        if i not in self.constants]
+
+    def __call__(self, *arrays):
+        if len(arrays) != len(self.var_pos):
+            raise ValueError("wrong number of variable arrays")
+        full = [None] * len(self.inputs)
+        for i, c in self.constants.items():
+            full[i] = c
+        for i, a in zip(self.var_pos, arrays):
+            full[i] = a
+        return execute(self.tree, full)
