@@ -114,6 +114,16 @@ int qb_contract_pair(const qb_tensor_t *A, const int32_t *labelsA,
                      int conjB, int engine, void *workspace,
                      size_t workspace_bytes, void *stream);
 
+/* as qb_contract_pair, but C = alpha * op(A).op(B) + beta * C (real scalars;
+ * beta != 0 accumulates into the existing contents of C).  This is the
+ * building block of the Lanczos orthogonalisation and of the blocked
+ * Householder updates. */
+int qb_contract_pair_ab(const qb_tensor_t *A, const int32_t *labelsA,
+                        const qb_tensor_t *B, const int32_t *labelsB,
+                        qb_tensor_t *C, const int32_t *labelsC, int conjA,
+                        int conjB, double alpha, double beta, void *workspace,
+                        size_t workspace_bytes, void *stream);
+
 int64_t qb_contract_pair_workspace(const qb_tensor_t *A,
                                    const int32_t *labelsA,
                                    const qb_tensor_t *B,

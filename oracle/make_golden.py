@@ -1,0 +1,236 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference
+(/root/reference, quimb @ 97ceeae) on its numpy backend.
+
+The reference's third-party layer (autoray / cotengra / cytoolz) is not
+installable offline; oracle/shims provides functional stand-ins that only
+route calls -- all arithmetic is the reference's own code (tensor_core,
+decomp incl. its numba kernels, dmrg, scipy ARPACK) on numpy.
+
+Run in the build container only:   python oracle/make_golden.py
+(the GPU box has no /root/reference; tests read the committed fixtures).
+"""
+
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+REF = os.environ.get("QUIMB_REFERENCE", "/root/reference")
+sys.path.insert(0, os.path.join(HERE, "shims"))
+sys.path.insert(0, REF)
+sys.path.insert(0, ROOT)
+
+import quimb as qu  # noqa: E402
+import quimb.tensor as qtn  # noqa: E402
+from quimb.tensor import decomp  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+os.makedirs(OUT, exist_ok=True)
+
+
+def contract_cases():
+    rng = np.random.default_rng(0)
+    cases = [
+        # (name, [(shape, inds), ...], output_inds or None, dtype)
+        ("pair_cfg1", [((6, 5, 4, 3), "abcd"), ((4, 3, 7, 2), "cdef")], None, "float64"),
+        ("pair_perm", [((6, 4, 5, 3), "acbd"), ((3, 2, 4, 7), "dfce")], None, "float64"),
+        ("outer", [((3, 4), "ab"), ((5,), "c")], None, "float64"),
+        ("scalar", [((3, 4, 5), "abc"), ((5, 4, 3), "cba")], None, "float64"),
+        ("three", [((3, 4), "ab"), ((4, 5), "bc"), ((5, 6), "cd")], None, "float64"),
+        ("env4", [((7, 5, 7), "xwa"), ((7, 2, 6), "apb"), ((5, 4, 2, 2), "wvqp"),
+                  ((7, 2, 6), "xqy")], None, "float64"),
+        ("hyper_out", [((3, 4), "ab"), ((4, 5), "bc"), ((4, 2), "bd")], "abcd"[0:1] + "cd", "float64"),
+        ("batch_keep", [((3, 4), "ab"), ((3, 5), "ac")], "abc", "float64"),
+        ("cplx_pair", [((4, 3, 5), "abc"), ((5, 3, 2), "cbd")], None, "complex128"),
+        ("cplx_scalar", [((4, 3), "ab"), ((4, 3), "ab")], None, "complex128"),
+        ("order_out", [((2, 3, 4), "abc"), ((4, 5), "cd")], "dab", "float64"),
+        ("rank0", [((), ""), ((3, 2), "ab")], None, "float64"),
+    ]
+    store = {}
+    meta = {}
+    for name, tensors, out_inds, dtype in cases:
+        ts = []
+        for k, (shape, inds) in enumerate(tensors):
+            x = rng.standard_normal(shape)
+            if dtype.startswith("complex"):
+                x = x + 1j * rng.standard_normal(shape)
+            x = np.asarray(x, dtype=dtype)
+            store[f"{name}__in{k}"] = x
+            ts.append(qtn.Tensor(x, inds=tuple(inds)))
+        kw = {} if out_inds is None else {"output_inds": tuple(out_inds)}
+        res = qtn.tensor_contract(*ts, preserve_tensor=True, **kw)
+        store[f"{name}__out"] = np.asarray(res.data)
+        meta[name] = {
+            "inds": [list(i) for _, i in tensors],
+            "output_inds": None if out_inds is None else list(out_inds),
+            "result_inds": list(res.inds),
+            "dtype": dtype,
+        }
+    # error behaviour: index appearing three times without output_inds
+    try:
+        qtn.tensor_contract(qtn.rand_tensor((2, 2), "ab"), qtn.rand_tensor((2, 2), "bc"),
+                            qtn.rand_tensor((2, 2), "bd"))
+        meta["_triple_index_error"] = None
+    except ValueError as e:
+        meta["_triple_index_error"] = str(e)
+    np.savez_compressed(os.path.join(OUT, "contract.npz"), **store)
+    json.dump(meta, open(os.path.join(OUT, "contract.json"), "w"), indent=1)
+
+
+def decomp_cases():
+    rng = np.random.default_rng(1)
+    store, meta = {}, {}
+    # known answers restated from the reference's own tests
+    s = np.array([3.0, 2.0, 1.0, 0.1])
+    meta["svals_to_keep"] = {
+        "s": s.tolist(),
+        "cases": [
+            [c, m, int(decomp._compute_number_svals_to_keep_numba(s, c, m))]
+            for c, m in [(1.1, 1), (0.5, 2), (1.02, 3), (0.1, 4), (1.2, 5),
+                         (0.2, 6), (1e-12, 3), (100.0, 3), (0.0, 1), (5.0, 6)]
+        ],
+    }
+    mats = {
+        "rect_tall": rng.standard_normal((24, 10)),
+        "rect_wide": rng.standard_normal((9, 20)),
+        "square": rng.standard_normal((16, 16)),
+        "lowrank": rng.standard_normal((20, 4)) @ rng.standard_normal((4, 18)),
+        "cplx": rng.standard_normal((12, 14)) + 1j * rng.standard_normal((12, 14)),
+        "decay": (np.linalg.qr(rng.standard_normal((20, 20)))[0]
+                  * (0.5 ** np.arange(20))[None, :])
+                 @ np.linalg.qr(rng.standard_normal((20, 20)))[0],
+    }
+    svd_cases = []
+    for mname, x in mats.items():
+        store[f"mat__{mname}"] = x
+        for (cutoff, mode, max_bond, absorb, renorm) in [
+            (-1.0, 4, -1, None, 0),
+            (1e-2, 4, -1, 0, 0),
+            (1e-3, 3, -1, -1, 0),
+            (1e-1, 1, -1, 1, 0),
+            (1e-2, 2, 6, 0, 0),
+            (-1.0, 4, 5, 1, 0),
+            (1e-2, 4, -1, 0, 2),
+            (1e-2, 6, -1, 0, 1),
+            (0.3, 5, -1, None, 0),
+            (0.0, 3, 7, -1, 0),
+        ]:
+            info = {"error": None}
+            left, sv, right = decomp.svd_truncated(
+                x, cutoff=cutoff, cutoff_mode=mode, max_bond=max_bond,
+                absorb=absorb, renorm=renorm, info=info)
+            key = f"svd__{mname}__{len(svd_cases)}"
+            if left is not None and right is not None:
+                rec = left @ (np.diag(sv) @ right if sv is not None else right)
+            else:
+                rec = None
+            k = (left.shape[1] if left is not None else right.shape[0])
+            if sv is not None:
+                store[key + "__s"] = sv
+            if rec is not None:
+                store[key + "__rec"] = rec
+            svd_cases.append({
+                "key": key, "mat": mname, "cutoff": cutoff, "cutoff_mode": mode,
+                "max_bond": max_bond, "absorb": absorb, "renorm": renorm,
+                "n_keep": int(k), "error": float(info["error"]),
+            })
+    meta["svd_cases"] = svd_cases
+    qr_cases = []
+    for mname in ("rect_tall", "square", "cplx", "rect_wide"):
+        x = mats[mname]
+        for absorb in (1, 10, 11, -1, -10, -11):
+            left, _, right = decomp.qr_stabilized(x.copy(), absorb=absorb)
+            key = f"qr__{mname}__{absorb}"
+            if left is not None:
+                store[key + "__left"] = left
+            if right is not None:
+                store[key + "__right"] = right
+            qr_cases.append({"key": key, "mat": mname, "absorb": absorb})
+    meta["qr_cases"] = qr_cases
+    # tensor_split through the Tensor interface (transpose + fuse + split + unfuse)
+    x = rng.standard_normal((4, 3, 5, 2))
+    store["split__x"] = x
+    t = qtn.Tensor(x, inds="abcd")
+    split_cases = []
+    for kw in [
+        dict(left_inds="ac", method="svd", cutoff=1e-10, absorb="both"),
+        dict(left_inds="ca", right_inds="db", method="svd", max_bond=4, cutoff=0.0, absorb="right"),
+        dict(left_inds="b", method="svd", cutoff=1e-1, cutoff_mode="sum2", absorb="left"),
+        dict(left_inds="ab", method="qr"),
+        dict(left_inds="ab", method="lq"),
+        dict(left_inds="d", method="svd", absorb=None, cutoff=0.0),
+    ]:
+        kw = {k: (tuple(v) if k.endswith("inds") else v) for k, v in kw.items()}
+        arrs = t.split(get="arrays", **kw)
+        key = f"split__{len(split_cases)}"
+        for j, a in enumerate(arrs):
+            if a is not None:
+                store[f"{key}__{j}"] = np.asarray(a)
+        split_cases.append({"key": key, "n_out": len(arrs),
+                            "kw": {k: (list(v) if k.endswith("inds") else v)
+                                   for k, v in kw.items()}})
+    meta["split_cases"] = split_cases
+    # parse_split_opts codes
+    meta["parse_split_opts"] = []
+    for kw in [dict(), dict(method="svd", absorb="left", max_bond=7, cutoff=1e-3, cutoff_mode="sum2"),
+               dict(method="svd", renorm=True, cutoff_mode="rsum1"), dict(method="qr"),
+               dict(method="svd", absorb=None, cutoff=None, max_bond=None)]:
+        method, opts = decomp.parse_split_opts(**kw)
+        meta["parse_split_opts"].append({"kw": kw, "method": method, "opts": opts})
+    np.savez_compressed(os.path.join(OUT, "decomp.npz"), **store)
+    json.dump(meta, open(os.path.join(OUT, "decomp.json"), "w"), indent=1, default=str)
+
+
+def mps_dmrg_cases():
+    store, meta = {}, {}
+    # Heisenberg MPO of the reference, as arrays (lrud layout) + dense check
+    H = qtn.MPO_ham_heis(6)
+    for i in range(6):
+        store[f"heis6__{i}"] = np.asarray(H[i].data)
+    meta["heis6_inds"] = [list(map(str, H[i].inds)) for i in range(6)]
+    store["heis6__dense"] = np.asarray(H.to_dense())
+    # MPS norm / expectation
+    p = qtn.MPS_rand_state(12, 7, seed=3, normalize=False)
+    for i in range(12):
+        store[f"mps12__{i}"] = np.asarray(p[i].data)
+    meta["mps12_inds"] = [list(map(str, p[i].inds)) for i in range(12)]
+    meta["mps12_norm2"] = float(p.H @ p)
+    meta["mps12_norm"] = float(p.norm())
+    H12 = qtn.MPO_ham_heis(12)
+    meta["mps12_expec_heis"] = float(qtn.expec_TN_1D(p.H, H12, p))
+    # complex MPS
+    pc = qtn.MPS_rand_state(8, 5, seed=4, normalize=False, dtype="complex128")
+    for i in range(8):
+        store[f"cmps8__{i}"] = np.asarray(pc[i].data)
+    meta["cmps8_norm2"] = float(np.real(pc.H @ pc))
+    meta["cmps8_expec_heis"] = float(np.real(qtn.expec_TN_1D(pc.H, qtn.MPO_ham_heis(8), pc)))
+    # DMRG2 energies of the reference itself
+    runs = []
+    for L, bond_dims, cutoffs, tol in [(10, [8, 16, 32], 1e-10, 1e-8),
+                                       (20, [10, 20, 40], 1e-10, 1e-6),
+                                       (32, [16, 32], 1e-9, 1e-6)]:
+        Hm = qtn.MPO_ham_heis(L)
+        dm = qtn.DMRG2(Hm, bond_dims=bond_dims, cutoffs=cutoffs)
+        conv = dm.solve(tol=tol, max_sweeps=8, verbosity=0)
+        exact = None
+        if L <= 14:
+            exact = float(qu.groundenergy(qu.ham_heis(L, cyclic=False, sparse=True)))
+        runs.append({"L": L, "bond_dims": bond_dims, "cutoffs": cutoffs, "tol": tol,
+                     "converged": bool(conv), "energies": [float(e) for e in dm.energies],
+                     "exact": exact, "max_bond": int(dm.state.max_bond())})
+    meta["dmrg2_runs"] = runs
+    meta["heisenberg_energy_100_periodic"] = float(qu.heisenberg_energy(100))
+    np.savez_compressed(os.path.join(OUT, "mps_dmrg.npz"), **store)
+    json.dump(meta, open(os.path.join(OUT, "mps_dmrg.json"), "w"), indent=1)
+
+
+if __name__ == "__main__":
+    contract_cases()
+    decomp_cases()
+    mps_dmrg_cases()
+    print("golden fixtures written to", OUT)
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))

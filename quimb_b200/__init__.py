@@ -1,0 +1,38 @@
+"""quimb_b200 -- a B200-native array backend for quimb's hot path.
+
+The module *is* the backend: arrays are :class:`quimb_b200.Array`, so
+``autoray.infer_backend(x) == "quimb_b200"`` and
+``autoray.do("tensordot", a, b, axes)`` resolves to
+:func:`quimb_b200.tensordot`, ``do("linalg.svd", x)`` to
+:func:`quimb_b200.linalg.svd`, and so on.  With quimb
+installed, ``quimb_b200.register_with_quimb()`` additionally installs the
+fused overrides of quimb's composed split drivers (``svd_truncated``,
+``qr_stabilized``, ``fuse`` ...), exactly as quimb itself does for its numpy
+backend (quimb/tensor/decomp.py:1058, :2198).
+
+All arithmetic on the hot path runs in hand-written sm_100a CUDA kernels
+behind a C ABI (``include/quimb_b200.h``); there is no CPU fallback.
+"""
+
+from . import _lib
+from .array import Array
+from .ops import *  # noqa: F401,F403  (the autoray-visible function surface)
+from .ops import (abs, all, any, max, min, sum)  # noqa: F401,A004
+from . import linalg  # noqa: F401
+from .contract import contract_pair, plan_pair  # noqa: F401
+from .tree import (ContractExpression, Tree, array_contract,  # noqa: F401
+                   find_tree, gen_output_inds)
+from .mps import (env_left_step, env_right_step, mps_expec, mps_norm,  # noqa: F401
+                  mps_norm2)
+from .split import (array_split, qr_stabilized, svd_truncated,  # noqa: F401
+                    tensor_split)
+from .lanczos import eigh_lanczos  # noqa: F401
+from .dmrg import DMRG2  # noqa: F401
+from .integration import register_with_quimb  # noqa: F401
+
+__version__ = "0.1.0"
+
+
+def launch_count():
+    """Number of CUDA kernels this library has launched in this process."""
+    return _lib.launch_count()

@@ -79,6 +79,9 @@ def load(build_if_missing=True):
     sig("qb_launch_count", i64, [])
     sig("qb_contract_pair", ci,
         [T, I32P, T, I32P, T, I32P, ci, ci, ci, vp, ctypes.c_size_t, vp])
+    sig("qb_contract_pair_ab", ci,
+        [T, I32P, T, I32P, T, I32P, ci, ci, ctypes.c_double, ctypes.c_double,
+         vp, ctypes.c_size_t, vp])
     sig("qb_contract_pair_workspace", i64, [T, I32P, T, I32P, T, I32P, ci])
     sig("qb_contract_pair_plan", ci, [T, I32P, T, I32P, T, I32P, P(i64)])
     sig("qb_contract_batched", ci,

@@ -27,7 +27,7 @@ def _workspace(nbytes, device):
 
 
 def contract_pair(a, la, b, lb, lc, conj_a=False, conj_b=False, out=None,
-                  engine=0):
+                  engine=0, alpha=1.0, beta=0.0):
     """``out[lc] = sum op(a)[la] * op(b)[lb]`` with integer mode labels.
 
     Parameters
@@ -38,6 +38,8 @@ def contract_pair(a, la, b, lb, lc, conj_a=False, conj_b=False, out=None,
         Mode labels of ``a``, ``b`` and the output (its axis order).
     out : torch.Tensor, optional
         Pre-allocated (possibly strided) output view.
+    alpha, beta : float
+        ``out = alpha * contraction + beta * out`` (beta != 0 needs ``out``).
     """
     _lib.require_cuda(a, "a")
     _lib.require_cuda(b, "b")
@@ -69,9 +71,15 @@ def contract_pair(a, la, b, lb, lc, conj_a=False, conj_b=False, out=None,
     if need > 0:
         ws = _workspace(need, a.device)
         ws_ptr, ws_n = ctypes.c_void_p(ws.data_ptr()), ws.numel()
-    rc = lib.qb_contract_pair(da, pla, db, plb, dc, plc, int(bool(conj_a)),
-                              int(bool(conj_b)), engine, ws_ptr, ws_n,
-                              _lib.stream_ptr())
+    if alpha == 1.0 and beta == 0.0:
+        rc = lib.qb_contract_pair(da, pla, db, plb, dc, plc, int(bool(conj_a)),
+                                  int(bool(conj_b)), engine, ws_ptr, ws_n,
+                                  _lib.stream_ptr())
+    else:
+        rc = lib.qb_contract_pair_ab(da, pla, db, plb, dc, plc,
+                                     int(bool(conj_a)), int(bool(conj_b)),
+                                     float(alpha), float(beta), ws_ptr, ws_n,
+                                     _lib.stream_ptr())
     _lib.check(rc, "qb_contract_pair")
     return out
 

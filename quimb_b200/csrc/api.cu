@@ -4,8 +4,7 @@
 
 #include <vector>
 
-#include "common.cuh"
-#include "plan.h"
+#include "internal.h"
 
 namespace qb {
 
@@ -31,9 +30,30 @@ int sm_count() {
   return n;
 }
 
-int launch_contract_f64(const PairPlan &plan, cudaStream_t st);
-int launch_contract_c128(const PairPlan &plan, cudaStream_t st);
-int launch_fill_zero(const qb_tensor_t *C, cudaStream_t st);
+int gemm_f64(const double *A, int64_t a_rs, int64_t a_cs, const double *B,
+             int64_t b_rs, int64_t b_cs, double *C, int64_t c_rs, int64_t c_cs,
+             int64_t M, int64_t N, int64_t K, double alpha, double beta,
+             cudaStream_t st) {
+  if (M <= 0 || N <= 0) return 0;
+  qb_tensor_t a, b, c;
+  memset(&a, 0, sizeof(a)); memset(&b, 0, sizeof(b)); memset(&c, 0, sizeof(c));
+  a.ptr = const_cast<double *>(A); a.dtype = QB_F64; a.rank = 2;
+  a.shape[0] = M; a.shape[1] = K; a.stride[0] = a_rs; a.stride[1] = a_cs;
+  b.ptr = const_cast<double *>(B); b.dtype = QB_F64; b.rank = 2;
+  b.shape[0] = K; b.shape[1] = N; b.stride[0] = b_rs; b.stride[1] = b_cs;
+  c.ptr = C; c.dtype = QB_F64; c.rank = 2;
+  c.shape[0] = M; c.shape[1] = N; c.stride[0] = c_rs; c.stride[1] = c_cs;
+  const int32_t la[2] = {0, 1}, lb[2] = {1, 2}, lc[2] = {0, 2};
+  PairPlan plan;
+  int rc = plan_pair(&a, la, &b, lb, &c, lc, 0, 0, plan, -1, /*max_splitk=*/1);
+  if (rc) return rc;
+  if (plan.zero_fill) {
+    if (beta == 0.0) return launch_fill_zero(&c, st);
+    return 0;
+  }
+  plan.p.alpha = alpha; plan.p.beta = beta;
+  return launch_contract_f64(plan, st);
+}
 
 static int check_device_dtype(int dt) {
   if (dt != QB_F64 && dt != QB_C128) {
@@ -81,11 +101,12 @@ int64_t qb_contract_pair_workspace(const qb_tensor_t *A, const int32_t *la,
   return plan_workspace_bytes(plan);
 }
 
-int qb_contract_pair(const qb_tensor_t *A, const int32_t *la,
-                     const qb_tensor_t *B, const int32_t *lb, qb_tensor_t *C,
-                     const int32_t *lc, int conjA, int conjB, int engine,
-                     void *workspace, size_t workspace_bytes, void *stream) {
-  (void)engine;
+static int contract_pair_impl(const qb_tensor_t *A, const int32_t *la,
+                              const qb_tensor_t *B, const int32_t *lb,
+                              qb_tensor_t *C, const int32_t *lc, int conjA,
+                              int conjB, double alpha, double beta,
+                              void *workspace, size_t workspace_bytes,
+                              void *stream) {
   PairPlan plan;
   // QB_FORCE_CFG: tuning/debug override of the tile configuration
   static const int force_cfg = [] {
@@ -97,7 +118,12 @@ int qb_contract_pair(const qb_tensor_t *A, const int32_t *la,
   if ((rc = check_device_dtype(plan.dtype))) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (plan.empty_out) return 0;
-  if (plan.zero_fill) return launch_fill_zero(C, st);
+  if (plan.zero_fill) {
+    if (beta == 0.0) return launch_fill_zero(C, st);
+    if (beta == 1.0) return 0;
+    set_error("zero-extent contraction with beta not in {0, 1}");
+    return -10;
+  }
   int64_t need = plan_workspace_bytes(plan);
   if (need > 0) {
     if (!workspace || (int64_t)workspace_bytes < need) {
@@ -107,8 +133,27 @@ int qb_contract_pair(const qb_tensor_t *A, const int32_t *la,
     }
     plan.p.partial = static_cast<double *>(workspace);
   }
+  plan.p.alpha = alpha; plan.p.beta = beta;
   if (plan.dtype == QB_F64) return launch_contract_f64(plan, st);
   return launch_contract_c128(plan, st);
+}
+
+int qb_contract_pair(const qb_tensor_t *A, const int32_t *la,
+                     const qb_tensor_t *B, const int32_t *lb, qb_tensor_t *C,
+                     const int32_t *lc, int conjA, int conjB, int engine,
+                     void *workspace, size_t workspace_bytes, void *stream) {
+  (void)engine;
+  return contract_pair_impl(A, la, B, lb, C, lc, conjA, conjB, 1.0, 0.0,
+                            workspace, workspace_bytes, stream);
+}
+
+int qb_contract_pair_ab(const qb_tensor_t *A, const int32_t *la,
+                        const qb_tensor_t *B, const int32_t *lb,
+                        qb_tensor_t *C, const int32_t *lc, int conjA,
+                        int conjB, double alpha, double beta, void *workspace,
+                        size_t workspace_bytes, void *stream) {
+  return contract_pair_impl(A, la, B, lb, C, lc, conjA, conjB, alpha, beta,
+                            workspace, workspace_bytes, stream);
 }
 
 int qb_contract_batched(const qb_tensor_t *A0, const int32_t *la,

@@ -385,6 +385,7 @@ __global__ void __launch_bounds__(WARPS_M *WARPS_N * 32)
     return;
   }
   const bool vecC = CPLX ? true : (p.vecC != 0);
+  const double alpha = p.alpha, beta = p.beta;
 #pragma unroll
   for (int i = 0; i < MT; ++i)
 #pragma unroll
@@ -396,14 +397,26 @@ __global__ void __launch_bounds__(WARPS_M *WARPS_N * 32)
       for (int j = 0; j < NT8; ++j) {
         const int c = wn0 + j * 8 + 2 * t;
         const int64_t on0 = offCn[c], on1 = offCn[c + 1];
+        double v0 = alpha * acc[i][j][2 * h], v1 = alpha * acc[i][j][2 * h + 1];
         if (vecC) {
           // (c, c+1) are contiguous and 16B aligned (planner / complex pair)
-          if (on0 >= 0)
-            *reinterpret_cast<double2 *>(C + om + on0) =
-                make_double2(acc[i][j][2 * h], acc[i][j][2 * h + 1]);
+          if (on0 >= 0) {
+            double2 *dst = reinterpret_cast<double2 *>(C + om + on0);
+            if (beta != 0.0) {
+              double2 old = *dst;
+              v0 += beta * old.x; v1 += beta * old.y;
+            }
+            *dst = make_double2(v0, v1);
+          }
         } else {
-          if (on0 >= 0) C[om + on0] = acc[i][j][2 * h];
-          if (on1 >= 0) C[om + on1] = acc[i][j][2 * h + 1];
+          if (on0 >= 0) {
+            if (beta != 0.0) v0 += beta * C[om + on0];
+            C[om + on0] = v0;
+          }
+          if (on1 >= 0) {
+            if (beta != 0.0) v1 += beta * C[om + on1];
+            C[om + on1] = v1;
+          }
         }
       }
     }
@@ -437,7 +450,10 @@ __global__ void splitk_reduce_f64_kernel(const __grid_constant__ ContractParams 
         q = qq;
       }
     }
-    C[(oc + om + on) * ES + (CPLX ? (nh & 1) : 0)] = s;
+    double *dst = &C[(oc + om + on) * ES + (CPLX ? (nh & 1) : 0)];
+    s *= p.alpha;
+    if (p.beta != 0.0) s += p.beta * *dst;
+    *dst = s;
   }
 }
 

@@ -1,0 +1,19 @@
+// Library-internal helpers shared between translation units.
+#pragma once
+#include "common.cuh"
+#include "plan.h"
+
+namespace qb {
+
+int launch_contract_f64(const PairPlan &plan, cudaStream_t st);
+int launch_contract_c128(const PairPlan &plan, cudaStream_t st);
+int launch_fill_zero(const qb_tensor_t *C, cudaStream_t st);
+
+// C(MxN) = alpha * A(MxK) * B(KxN) + beta * C on strided fp64 matrices
+// (element strides; any of them may describe a transposed view).
+int gemm_f64(const double *A, int64_t a_rs, int64_t a_cs, const double *B,
+             int64_t b_rs, int64_t b_cs, double *C, int64_t c_rs, int64_t c_cs,
+             int64_t M, int64_t N, int64_t K, double alpha, double beta,
+             cudaStream_t st);
+
+}  // namespace qb

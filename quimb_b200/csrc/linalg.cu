@@ -1,0 +1,983 @@
+// Dense factorizations of the split half of quimb's hot path, fp64:
+//
+//   qb_qr_stab  <- qr_stabilized (quimb/tensor/decomp.py:2055-2216): blocked
+//                  Householder QR (compact WY).  The panel factorization is
+//                  ONE CTA that keeps the whole tall panel in registers
+//                  (1024 threads x RPT rows x NB columns) and needs a single
+//                  NB-wide block reduction per column; trailing updates and
+//                  the formation of Q are GEMMs on the contraction kernel.
+//                  The stabilisation (diag(R) >= 0, phase into Q) is a fused
+//                  epilogue kernel.
+//   qb_svd      <- the LAPACK gesdd call inside svd_truncated
+//                  (decomp.py:1032-1055): one-sided block Jacobi on the
+//                  R factor of a QR preconditioner.  Per round, one CTA per
+//                  column-block pair: Gram matrix with DMMA-free register
+//                  tiles, cyclic Jacobi eigen-solve of the 2b x 2b Gram in
+//                  shared memory, rotation applied to the columns of the
+//                  working matrix and of V.  The working set (n x n twice)
+//                  is L2 resident on B200 (126 MB) up to n = 2048.
+//   qb_svals_to_keep <- _compute_number_svals_to_keep_numba + renorm factor
+//                  (decomp.py:901-965), host side, bit-for-bit the same
+//                  summation order as the reference.
+#include <cooperative_groups.h>
+#include <math.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "internal.h"
+
+namespace qb {
+
+// =========================================================================
+//                                   QR
+// =========================================================================
+
+// reduce NB per-thread partials over the warp: lane c (< NB) ends up with
+// the sum over all lanes of p[c] (recursive halving, NB-1 shuffles)
+template <int NB>
+__device__ __forceinline__ double warp_multi_reduce(double (&p)[NB], int lane) {
+#pragma unroll
+  for (int off = NB / 2, cnt = NB / 2; off >= 1; off >>= 1, cnt >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < cnt; ++i) {
+      double send = upper ? p[i] : p[i + cnt];
+      double keep = upper ? p[i + cnt] : p[i];
+      p[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  double v = p[0];  // lane L holds index L % NB, partial over its NB-lane group
+#pragma unroll
+  for (int off = NB; off < 32; off <<= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+  return v;
+}
+
+// Householder factorization of an m x nbw panel (nbw <= NB), row-major with
+// leading dimension lda, m <= 2048 * RPT.  One thread-block CLUSTER of 8 CTAs
+// (256 threads each) keeps the whole panel in registers: thread t of CTA r
+// owns rows i*2048 + r*256 + t.  Per column there is ONE cluster-wide
+// reduction of NB partial dot products through distributed shared memory
+// (double buffered, so a single cluster.sync per column).
+// In place: R on/above the diagonal, Householder vectors below.  Also writes
+// the explicit V (m x NB, unit diagonal, zeros above; row-major ld NB) and
+// the NB x NB upper triangular T of the compact WY form  Q = I - V T V^T.
+constexpr int QR_CLUSTER = 8;
+constexpr int QR_THREADS = 256;
+
+template <int NB, int RPT>
+__global__ void __cluster_dims__(QR_CLUSTER, 1, 1) __launch_bounds__(QR_THREADS, 1)
+    qr_panel_kernel(double *__restrict__ A, int64_t lda, int m, int nbw,
+                    double *__restrict__ Vout, double *__restrict__ Tout) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  constexpr int NW = QR_THREADS / 32;
+  __shared__ double red[NW][NB + 1];
+  __shared__ double part[2][NB];   // this CTA's partial dots (DSMEM-visible)
+  __shared__ double rowj_s[2][NB]; // row j of the panel if this CTA owns it
+  __shared__ double dots[NB];
+  __shared__ double rowj[NB];
+  __shared__ double Ts[NB][NB + 1];
+  __shared__ double hh[3];  // tau, scale, beta
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int ROWS_PER_PASS = QR_CLUSTER * QR_THREADS;
+
+  double a[RPT][NB];
+#pragma unroll
+  for (int i = 0; i < RPT; ++i) {
+    const int row = i * ROWS_PER_PASS + rank * QR_THREADS + tid;
+#pragma unroll
+    for (int c = 0; c < NB; ++c)
+      a[i][c] = (row < m && c < nbw) ? A[(int64_t)row * lda + c] : 0.0;
+  }
+  for (int i = tid; i < NB * (NB + 1); i += QR_THREADS) (&Ts[0][0])[i] = 0.0;
+  __syncthreads();
+
+#pragma unroll 1
+  for (int j = 0; j < nbw; ++j) {
+    const int buf = j & 1;
+    // ---- partial u_c = sum_{row > j} a[row][j] * a[row][c]  for all c ----
+    double p[NB];
+#pragma unroll
+    for (int c = 0; c < NB; ++c) p[c] = 0.0;
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) {
+      const int row = i * ROWS_PER_PASS + rank * QR_THREADS + tid;
+      if (row > j && row < m) {
+        // a[i][j] with runtime j: select through an unrolled scan
+        double x = 0.0;
+#pragma unroll
+        for (int c = 0; c < NB; ++c) x = (c == j) ? a[i][c] : x;
+#pragma unroll
+        for (int c = 0; c < NB; ++c) p[c] += x * a[i][c];
+      }
+      if (row == j) {
+#pragma unroll
+        for (int c = 0; c < NB; ++c) rowj_s[buf][c] = a[i][c];
+      }
+    }
+    double r = warp_multi_reduce<NB>(p, lane);
+    if (lane < NB) red[warp][lane] = r;
+    __syncthreads();
+    if (tid < NB) {
+      double s = 0.0;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) s += red[w][tid];
+      part[buf][tid] = s;
+    }
+    cluster.sync();
+    // ---- every CTA: total dots, row j, Householder scalars, T column -----
+    if (warp == 0) {
+      if (lane < NB) {
+        double s = 0.0;
+#pragma unroll
+        for (int q = 0; q < QR_CLUSTER; ++q) {
+          const double *rp = cluster.map_shared_rank(&part[buf][0], q);
+          s += rp[lane];
+        }
+        dots[lane] = s;
+        const int owner = (j % ROWS_PER_PASS) / QR_THREADS;
+        const double *rr = cluster.map_shared_rank(&rowj_s[buf][0], owner);
+        rowj[lane] = rr[lane];
+      }
+      __syncwarp();
+      // LAPACK dlarfg
+      const double alpha = rowj[j];
+      const double xnorm2 = dots[j];
+      double tau, scale, beta;
+      if (xnorm2 == 0.0) {
+        tau = 0.0; scale = 0.0; beta = alpha;
+      } else {
+        beta = -copysign(sqrt(alpha * alpha + xnorm2), alpha);
+        tau = (beta - alpha) / beta;
+        scale = 1.0 / (alpha - beta);
+      }
+      if (lane == 0) { hh[0] = tau; hh[1] = scale; hh[2] = beta; }
+      // T(0:j, j) = -tau * T(0:j,0:j) * (V^T v_j),
+      // z_c = v_c^T v_j = rowj[c] + scale * u_c   (c < j)
+      double acc = 0.0;
+      if (lane < j && lane < NB) {
+        for (int k = lane; k < j; ++k)
+          acc += Ts[lane][k] * (rowj[k] + scale * dots[k]);
+      }
+      __syncwarp();
+      if (lane < j && lane < NB) Ts[lane][j] = -tau * acc;
+      if (lane == j) Ts[j][j] = tau;
+    }
+    __syncthreads();
+    const double tau = hh[0], scale = hh[1], beta = hh[2];
+    // ---- apply H_j to the trailing panel columns, store v_j --------------
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) {
+      const int row = i * ROWS_PER_PASS + rank * QR_THREADS + tid;
+      if (row >= j && row < m) {
+        double x = 0.0;
+#pragma unroll
+        for (int c = 0; c < NB; ++c) x = (c == j) ? a[i][c] : x;
+        const double v = (row == j) ? 1.0 : x * scale;
+#pragma unroll
+        for (int c = 0; c < NB; ++c) {
+          if (c > j) {
+            const double w = rowj[c] + scale * dots[c];  // v^T a_c
+            a[i][c] -= tau * v * w;
+          } else if (c == j) {
+            a[i][c] = (row == j) ? beta : v;
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+  // nobody may exit while peers can still read its shared memory
+  cluster.sync();
+
+  // ---- write back: factored panel, explicit V, T -------------------------
+#pragma unroll
+  for (int i = 0; i < RPT; ++i) {
+    const int row = i * ROWS_PER_PASS + rank * QR_THREADS + tid;
+    if (row < m) {
+#pragma unroll
+      for (int c = 0; c < NB; ++c) {
+        if (c < nbw) {
+          A[(int64_t)row * lda + c] = a[i][c];
+          double v = (row > c) ? a[i][c] : (row == c ? 1.0 : 0.0);
+          Vout[(int64_t)row * NB + c] = v;
+        } else {
+          Vout[(int64_t)row * NB + c] = 0.0;
+        }
+      }
+    }
+  }
+  if (rank == 0) {
+    for (int i = tid; i < NB * NB; i += QR_THREADS) {
+      int r = i / NB, c = i % NB;
+      Tout[i] = (r < nbw && c < nbw) ? Ts[r][c] : 0.0;
+    }
+  }
+}
+
+// R = upper triangle of the factored matrix (first n rows), zeros below
+__global__ void extract_r_kernel(const double *__restrict__ F, int64_t ldf,
+                                 int k, int n, double *__restrict__ R) {
+  int64_t total = (int64_t)k * n;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int r = (int)(i / n), c = (int)(i - (int64_t)r * n);
+    R[i] = (c >= r) ? F[(int64_t)r * ldf + c] : 0.0;
+  }
+}
+
+__global__ void set_identity_kernel(double *Q, int64_t m, int64_t n) {
+  int64_t total = m * n;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i / n, c = i - r * n;
+    Q[i] = (r == c) ? 1.0 : 0.0;
+  }
+}
+
+// stabilisation: phase_i = sgn(R_ii) (sgn(0) = 1);  Q[:, i] *= phase_i,
+// R[i, :] *= phase_i  (decomp.py:2108-2124 / 2147-2178 for real dtypes)
+__global__ void qr_phase_kernel(double *__restrict__ Q, int64_t m, int64_t kq,
+                                double *__restrict__ R, int64_t k, int64_t n,
+                                const double *__restrict__ Rdiag_src,
+                                int64_t ld_src) {
+  const int64_t totq = Q ? m * kq : 0, totr = R ? k * n : 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+       i < totq + totr; i += (int64_t)gridDim.x * blockDim.x) {
+    if (i < totq) {
+      int64_t c = i % kq;
+      if (Rdiag_src[c * ld_src + c] < 0.0) Q[i] = -Q[i];
+    } else {
+      int64_t j = i - totq, r = j / n;
+      if (Rdiag_src[r * ld_src + r] < 0.0) R[j] = -R[j];
+    }
+  }
+}
+
+template <int NB, int RPT>
+static int launch_panel(double *A, int64_t lda, int m, int nbw, double *V,
+                        double *T, cudaStream_t st) {
+  qr_panel_kernel<NB, RPT><<<QR_CLUSTER, QR_THREADS, 0, st>>>(A, lda, m, nbw, V, T);
+  QB_LAUNCH_CHECK();
+  return 0;
+}
+
+struct QrGeom {
+  int nb;
+  int64_t f_off, v_off, t_off, w_off, w2_off, total;  // in doubles
+};
+
+static bool qr_geometry(int64_t m, int64_t n, QrGeom &g) {
+  const int64_t k = std::min(m, n);
+  if (m <= 4096) g.nb = 32;        // (NB, rows/thread) = (32,1) or (32,2)
+  else if (m <= 8192) g.nb = 16;   // (16,4)
+  else if (m <= 16384) g.nb = 8;   // (8,8)
+  else return false;
+  const int64_t npan = (k + g.nb - 1) / g.nb;
+  auto al = [](int64_t x) { return (x + 31) / 32 * 32; };  // 256-byte sections
+  int64_t off = 0;
+  g.f_off = off; off += al(m * n);                 // factored copy of X
+  g.v_off = off; off += al(npan * m * g.nb);       // explicit V per panel
+  g.t_off = off; off += al(npan * g.nb * g.nb);    // T per panel
+  g.w_off = off; off += al((int64_t)g.nb * std::max(n, k));
+  g.w2_off = off; off += al((int64_t)g.nb * std::max(n, k));
+  g.total = off;
+  return true;
+}
+
+// Householder QR of row-major X (m x n) -> factored F (in workspace), V, T.
+// Q (m x k) and/or R (k x n) formed on request.  k = min(m, n).
+static int qr_f64(int64_t m, int64_t n, const double *X, double *Q, double *R,
+                  int stabilized, double *ws, cudaStream_t st) {
+  QrGeom g;
+  if (!qr_geometry(m, n, g)) {
+    set_error("qb_qr_stab: m = %lld exceeds the register-panel limit 16384",
+              (long long)m);
+    return -2;
+  }
+  const int64_t k = std::min(m, n);
+  const int nb = g.nb;
+  double *F = ws + g.f_off, *V = ws + g.v_off, *T = ws + g.t_off;
+  double *W = ws + g.w_off, *W2 = ws + g.w2_off;
+  QB_CUDA_CHECK(cudaMemcpyAsync(F, X, sizeof(double) * m * n,
+                                cudaMemcpyDeviceToDevice, st));
+  int rc;
+  int64_t pi = 0;
+  for (int64_t j0 = 0; j0 < k; j0 += nb, ++pi) {
+    const int nbw = (int)std::min<int64_t>(nb, k - j0);
+    const int mp = (int)(m - j0);
+    double *Fp = F + j0 * n + j0;
+    double *Vp = V + pi * m * nb;  // (m - j0) x nb used
+    double *Tp = T + pi * nb * nb;
+    if (nb == 32 && mp <= 2048) rc = launch_panel<32, 1>(Fp, n, mp, nbw, Vp, Tp, st);
+    else if (nb == 32) rc = launch_panel<32, 2>(Fp, n, mp, nbw, Vp, Tp, st);
+    else if (nb == 16) rc = launch_panel<16, 4>(Fp, n, mp, nbw, Vp, Tp, st);
+    else rc = launch_panel<8, 8>(Fp, n, mp, nbw, Vp, Tp, st);
+    if (rc) return rc;
+    const int64_t nt = n - (j0 + nbw);
+    if (nt > 0) {
+      double *A2 = F + j0 * n + j0 + nbw;
+      // W = V^T A2            (nb x nt)
+      if ((rc = gemm_f64(Vp, 1, nb, A2, n, 1, W, nt, 1, nb, nt, mp, 1.0, 0.0, st))) return rc;
+      // W2 = T^T W            (nb x nt)
+      if ((rc = gemm_f64(Tp, 1, nb, W, nt, 1, W2, nt, 1, nb, nt, nb, 1.0, 0.0, st))) return rc;
+      // A2 -= V W2
+      if ((rc = gemm_f64(Vp, nb, 1, W2, nt, 1, A2, n, 1, mp, nt, nb, -1.0, 1.0, st))) return rc;
+    }
+  }
+  const int blocks = sm_count() * 4;
+  if (R) {
+    extract_r_kernel<<<blocks, 256, 0, st>>>(F, n, (int)k, (int)n, R);
+    QB_LAUNCH_CHECK();
+  }
+  if (Q) {
+    set_identity_kernel<<<blocks, 256, 0, st>>>(Q, m, k);
+    QB_LAUNCH_CHECK();
+    // Q = H_1 ... H_p [I; 0], panels applied last to first on Q[j0:, j0:]
+    const int64_t npan = (k + nb - 1) / nb;
+    for (int64_t pj = npan - 1; pj >= 0; --pj) {
+      const int64_t j0 = pj * nb;
+      const int mp = (int)(m - j0);
+      const int64_t nq = k - j0;
+      double *Vp = V + pj * m * nb, *Tp = T + pj * nb * nb;
+      double *Qs = Q + j0 * k + j0;
+      if ((rc = gemm_f64(Vp, 1, nb, Qs, k, 1, W, nq, 1, nb, nq, mp, 1.0, 0.0, st))) return rc;
+      if ((rc = gemm_f64(Tp, nb, 1, W, nq, 1, W2, nq, 1, nb, nq, nb, 1.0, 0.0, st))) return rc;
+      if ((rc = gemm_f64(Vp, nb, 1, W2, nq, 1, Qs, k, 1, mp, nq, nb, -1.0, 1.0, st))) return rc;
+    }
+  }
+  if (stabilized && (Q || R)) {
+    qr_phase_kernel<<<blocks, 256, 0, st>>>(Q, m, k, R, k, n, F, n);
+    QB_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+}  // namespace qb
+
+using namespace qb;
+
+extern "C" {
+
+int64_t qb_qr_workspace(int dtype, int64_t m, int64_t n) {
+  if (dtype != QB_F64) return -1;
+  QrGeom g;
+  if (!qr_geometry(m, n, g)) return -2;
+  return g.total * 8;
+}
+
+int qb_qr_stab(int dtype, int64_t m, int64_t n, const void *X, void *Q,
+               void *R, int stabilized, void *workspace,
+               size_t workspace_bytes, void *stream) {
+  if (dtype != QB_F64) {
+    set_error("qb_qr_stab: only f64 is implemented (got dtype %d)", dtype);
+    return -1;
+  }
+  if (m <= 0 || n <= 0) return 0;
+  int64_t need = qb_qr_workspace(dtype, m, n);
+  if (need < 0) {
+    set_error("qb_qr_stab: unsupported shape %lld x %lld", (long long)m, (long long)n);
+    return -2;
+  }
+  if (!workspace || (int64_t)workspace_bytes < need) {
+    set_error("qb_qr_stab: workspace too small (need %lld bytes)", (long long)need);
+    return -8;
+  }
+  return qr_f64(m, n, (const double *)X, (double *)Q, (double *)R, stabilized,
+                (double *)workspace, static_cast<cudaStream_t>(stream));
+}
+
+int qb_svals_to_keep(const double *s, int64_t n, double cutoff,
+                     int cutoff_mode, int64_t max_bond, int renorm,
+                     int64_t *n_keep, double *renorm_factor,
+                     double *trunc_error) {
+  if (!s || n <= 0) return -1;
+  if (cutoff_mode < 1 || cutoff_mode > 6) {
+    set_error("invalid cutoff_mode %d", cutoff_mode);
+    return -4;
+  }
+  int64_t n_chi = n;
+  double f = 1.0, err = 0.0;
+  if (cutoff > 0.0 || renorm > 0) {
+    // decomp.py:901-937
+    if (cutoff_mode == QB_CUTOFF_ABS) {
+      n_chi = 0;
+      for (int64_t i = 0; i < n; ++i) n_chi += s[i] > cutoff;
+    } else if (cutoff_mode == QB_CUTOFF_REL) {
+      n_chi = 0;
+      for (int64_t i = 0; i < n; ++i) n_chi += s[i] > cutoff * s[0];
+    } else {
+      const int pw = (cutoff_mode == QB_CUTOFF_SUM2 || cutoff_mode == QB_CUTOFF_RSUM2) ? 2 : 1;
+      double target = cutoff;
+      if (cutoff_mode == QB_CUTOFF_RSUM2 || cutoff_mode == QB_CUTOFF_RSUM1) {
+        double tot = 0.0;
+        for (int64_t i = 0; i < n; ++i) tot += (pw == 2) ? s[i] * s[i] : s[i];
+        target *= tot;
+      }
+      n_chi = n;
+      double ssum = 0.0;
+      for (int64_t i = n - 1; i >= 0; --i) {
+        double s2 = (pw == 2) ? s[i] * s[i] : s[i];
+        if (!isnan(s2)) ssum += s2;
+        if (ssum > target) break;
+        --n_chi;
+      }
+    }
+    if (n_chi < 1) n_chi = 1;
+    if (max_bond > 0 && n_chi > max_bond) n_chi = max_bond;
+    if (n_chi < n) {
+      for (int64_t i = n_chi; i < n; ++i) err += s[i] * s[i];
+      err = sqrt(err);
+      if (renorm > 0) {
+        // decomp.py:940-965
+        double keep = 0.0, lose = 0.0;
+        for (int64_t i = 0; i < n; ++i) {
+          double s2 = s[i];
+          if (renorm >= 2) s2 = pow(s2, (double)renorm);
+          if (!isnan(s2)) { if (i < n_chi) keep += s2; else lose += s2; }
+        }
+        f = (keep + lose) / keep;
+        if (renorm >= 2) f = pow(f, 1.0 / renorm);
+      }
+    }
+  } else if (max_bond != -1 && max_bond < n) {
+    n_chi = max_bond;
+    for (int64_t i = n_chi; i < n; ++i) err += s[i] * s[i];
+    err = sqrt(err);
+  }
+  if (n_keep) *n_keep = n_chi;
+  if (renorm_factor) *renorm_factor = f;
+  if (trunc_error) *trunc_error = err;
+  return 0;
+}
+
+}  // extern "C"
+
+// =========================================================================
+//                      one-sided block Jacobi SVD
+// =========================================================================
+namespace qb {
+
+constexpr int JB = 16;          // columns per block
+constexpr int JP = 2 * JB;      // columns per pair
+constexpr int JCH = 64;         // rows per streamed chunk
+constexpr int JPITCH = JP + 4;  // smem pitch (== 4 mod 16 doubles)
+
+struct JacobiParams {
+  double *W;       // rows_w x ld  working matrix (columns get orthogonalised)
+  double *V;       // rows_v x ld  accumulated right rotations
+  int64_t ld;
+  int rows_w, rows_v;
+  int nblk;        // number of column blocks (even)
+  int round;       // 0 .. nblk-2
+  double tol;
+  int *flag;       // set to 1 when any pair still needed rotating
+};
+
+__device__ __forceinline__ void rr_pair(int k, int round, int nblk, int &p, int &q) {
+  // circle-method round robin over nblk players
+  const int m = nblk - 1;
+  int a, b;
+  if (k == 0) { a = m; b = round; }
+  else { a = (round + k) % m; b = (round - k + m) % m; }
+  p = min(a, b); q = max(a, b);
+}
+
+__device__ __forceinline__ void jac_load_chunk(double (*Xs)[JPITCH], const double *M,
+                                               int64_t ld, int rows, int row0,
+                                               int cp, int cq, int tid) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int idx = tid + 256 * i;       // 1024 double2 per chunk
+    const int r = idx >> 4, c2 = (idx & 15) * 2;
+    const int gc = (c2 < JB) ? (cp + c2) : (cq + c2 - JB);
+    const int gr = row0 + r;
+    const bool ok = gr < rows;
+    const double *src = ok ? (M + (int64_t)gr * ld + gc) : M;
+    cp_async16(smem_u32(&Xs[r][c2]), src, ok ? 16 : 0);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    jacobi_pair_kernel(const JacobiParams P) {
+  extern __shared__ __align__(16) unsigned char jac_smem[];
+  double(*Xs)[JCH][JPITCH] = reinterpret_cast<double(*)[JCH][JPITCH]>(jac_smem);
+  __shared__ double G[JP][JP + 1];
+  __shared__ __align__(16) double Jm[JP][JPITCH];
+  __shared__ double rot[JB][2];
+  __shared__ int rotpq[JB][2];
+  __shared__ double redmax[8];
+  __shared__ int s_any;
+  __shared__ int rank_s[JP];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  int bp, bq;
+  rr_pair(blockIdx.x, P.round, P.nblk, bp, bq);
+  const int cp = bp * JB, cq = bq * JB;
+
+  // ---------------- phase 1: Gram matrix of the 32 columns -----------------
+  double acc[2][4][4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int v = 0; v < 4; ++v) acc[i][j][v] = 0.0;
+  const int nch = (P.rows_w + JCH - 1) / JCH;
+  jac_load_chunk(Xs[0], P.W, P.ld, P.rows_w, 0, cp, cq, tid);
+  cp_async_commit();
+  for (int ch = 0; ch < nch; ++ch) {
+    if (ch + 1 < nch)
+      jac_load_chunk(Xs[(ch + 1) & 1], P.W, P.ld, P.rows_w, (ch + 1) * JCH, cp, cq, tid);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+    const double(*X)[JPITCH] = Xs[ch & 1];
+    const int kb = warp * 8;  // this warp's 8 rows of the chunk
+    double af[2][4], bf[4][2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      af[i][0] = X[kb + t][i * 16 + g];
+      af[i][1] = X[kb + t][i * 16 + g + 8];
+      af[i][2] = X[kb + t + 4][i * 16 + g];
+      af[i][3] = X[kb + t + 4][i * 16 + g + 8];
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      bf[j][0] = X[kb + t][j * 8 + g];
+      bf[j][1] = X[kb + t + 4][j * 8 + g];
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) dmma_16x8x8(acc[i][j], af[i], bf[j]);
+    __syncthreads();
+  }
+  cp_async_wait<0>();
+  // deterministic reduction over the 8 warps
+  for (int w = 0; w < 8; ++w) {
+    if (warp == w) {
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int r = i * 16 + g + h * 8, c = j * 8 + 2 * t;
+            if (w == 0) {
+              G[r][c] = acc[i][j][2 * h];
+              G[r][c + 1] = acc[i][j][2 * h + 1];
+            } else {
+              G[r][c] += acc[i][j][2 * h];
+              G[r][c + 1] += acc[i][j][2 * h + 1];
+            }
+          }
+    }
+    __syncthreads();
+  }
+  // symmetrise (rounding) and measure the largest scaled off-diagonal
+  {
+    double mx = 0.0;
+    for (int idx = tid; idx < JP * JP; idx += 256) {
+      const int r = idx / JP, c = idx % JP;
+      if (r < c) {
+        const double v = 0.5 * (G[r][c] + G[c][r]);
+        const double d = G[r][r] * G[c][c];
+        if (d > 0.0) mx = fmax(mx, fabs(v) / sqrt(d));
+        else if (v != 0.0) mx = 1.0;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) redmax[warp] = mx;
+    __syncthreads();
+    if (tid == 0) {
+      double m2 = 0.0;
+      for (int w = 0; w < 8; ++w) m2 = fmax(m2, redmax[w]);
+      s_any = (m2 > P.tol) ? 1 : 0;
+      if (s_any) atomicOr(P.flag, 1);
+    }
+    __syncthreads();
+    if (!s_any) return;  // this pair is already orthogonal
+    for (int idx = tid; idx < JP * JP; idx += 256) {
+      const int r = idx / JP, c = idx % JP;
+      if (r < c) {
+        const double v = 0.5 * (G[r][c] + G[c][r]);
+        G[r][c] = v; G[c][r] = v;
+      }
+      Jm[r][c] = (r == c) ? 1.0 : 0.0;
+    }
+    __syncthreads();
+  }
+
+  // ---------------- phase 2: J^T G J = diag by cyclic Jacobi ----------------
+  for (int sweep = 0; sweep < 12; ++sweep) {
+    // convergence of the small problem
+    double mx = 0.0;
+    for (int idx = tid; idx < JP * JP; idx += 256) {
+      const int r = idx / JP, c = idx % JP;
+      if (r < c) {
+        const double d = G[r][r] * G[c][c];
+        const double v = fabs(G[r][c]);
+        if (d > 0.0) mx = fmax(mx, v / sqrt(d));
+        else if (v > 0.0) mx = fmax(mx, 1.0);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) redmax[warp] = mx;
+    __syncthreads();
+    double m2 = 0.0;
+    for (int w = 0; w < 8; ++w) m2 = fmax(m2, redmax[w]);
+    __syncthreads();
+    if (m2 <= 1e-16) break;
+    for (int step = 0; step < JP - 1; ++step) {
+      if (tid < JB) {
+        int p, q;
+        rr_pair(tid, step, JP, p, q);
+        const double app = G[p][p], aqq = G[q][q], apq = G[p][q];
+        double c = 1.0, s = 0.0;
+        if (apq != 0.0 && fabs(apq) > 1e-300) {
+          const double zeta = (aqq - app) / (2.0 * apq);
+          const double tt = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+          c = 1.0 / sqrt(1.0 + tt * tt);
+          s = c * tt;
+        }
+        rot[tid][0] = c; rot[tid][1] = s;
+        rotpq[tid][0] = p; rotpq[tid][1] = q;
+      }
+      __syncthreads();
+      // columns: G <- G R, J <- J R   with R = [c s; -s c] on (p, q)
+      for (int idx = tid; idx < JB * JP; idx += 256) {
+        const int k = idx / JP, r = idx % JP;
+        const double c = rot[k][0], s = rot[k][1];
+        const int p = rotpq[k][0], q = rotpq[k][1];
+        const double gp = G[r][p], gq = G[r][q];
+        G[r][p] = c * gp - s * gq;
+        G[r][q] = s * gp + c * gq;
+        const double jp = Jm[r][p], jq = Jm[r][q];
+        Jm[r][p] = c * jp - s * jq;
+        Jm[r][q] = s * jp + c * jq;
+      }
+      __syncthreads();
+      // rows: G <- R^T G
+      for (int idx = tid; idx < JB * JP; idx += 256) {
+        const int k = idx / JP, r = idx % JP;
+        const double c = rot[k][0], s = rot[k][1];
+        const int p = rotpq[k][0], q = rotpq[k][1];
+        const double gp = G[p][r], gq = G[q][r];
+        G[p][r] = c * gp - s * gq;
+        G[q][r] = s * gp + c * gq;
+      }
+      __syncthreads();
+    }
+  }
+  // sort: larger column norms first (ties by index) -> new column order
+  if (tid < JP) {
+    const double d = G[tid][tid];
+    int rk = 0;
+    for (int j = 0; j < JP; ++j) {
+      const double dj = G[j][j];
+      rk += (dj > d) || (dj == d && j < tid);
+    }
+    rank_s[tid] = rk;
+  }
+  __syncthreads();
+  {
+    // permute the columns of J in place through G as scratch
+    for (int idx = tid; idx < JP * JP; idx += 256) {
+      const int r = idx / JP, c = idx % JP;
+      G[r][rank_s[c]] = Jm[r][c];
+    }
+    __syncthreads();
+    for (int idx = tid; idx < JP * JP; idx += 256) {
+      const int r = idx / JP, c = idx % JP;
+      Jm[r][c] = G[r][c];
+    }
+    __syncthreads();
+  }
+
+  // ---------------- phase 3: apply J to the columns of W and V --------------
+  const int nchw = (P.rows_w + JCH - 1) / JCH;
+  const int nchv = (P.rows_v + JCH - 1) / JCH;
+  const int ntot = nchw + nchv;
+  auto chunk_src = [&](int ch, double *&M, int &rows, int &row0) {
+    if (ch < nchw) { M = P.W; rows = P.rows_w; row0 = ch * JCH; }
+    else { M = P.V; rows = P.rows_v; row0 = (ch - nchw) * JCH; }
+  };
+  {
+    double *M; int rows, row0;
+    chunk_src(0, M, rows, row0);
+    jac_load_chunk(Xs[0], M, P.ld, rows, row0, cp, cq, tid);
+    cp_async_commit();
+  }
+  const int mt = warp & 3, nh = warp >> 2;  // 16 rows x 16 cols per warp
+  for (int ch = 0; ch < ntot; ++ch) {
+    double *M; int rows, row0;
+    if (ch + 1 < ntot) {
+      chunk_src(ch + 1, M, rows, row0);
+      jac_load_chunk(Xs[(ch + 1) & 1], M, P.ld, rows, row0, cp, cq, tid);
+    }
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+    chunk_src(ch, M, rows, row0);
+    const double(*X)[JPITCH] = Xs[ch & 1];
+    double c2[2][4];
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int v = 0; v < 4; ++v) c2[j][v] = 0.0;
+#pragma unroll
+    for (int kk = 0; kk < JP; kk += 8) {
+      double af[4], bf[2][2];
+      af[0] = X[mt * 16 + g][kk + t];
+      af[1] = X[mt * 16 + g + 8][kk + t];
+      af[2] = X[mt * 16 + g][kk + t + 4];
+      af[3] = X[mt * 16 + g + 8][kk + t + 4];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        bf[j][0] = Jm[kk + t][nh * 16 + j * 8 + g];
+        bf[j][1] = Jm[kk + t + 4][nh * 16 + j * 8 + g];
+      }
+#pragma unroll
+      for (int j = 0; j < 2; ++j) dmma_16x8x8(c2[j], af, bf[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int r = row0 + mt * 16 + g + h * 8;
+        const int c = nh * 16 + j * 8 + 2 * t;  // column within the pair
+        if (r < rows) {
+          const int gc = (c < JB) ? (cp + c) : (cq + c - JB);
+          *reinterpret_cast<double2 *>(M + (int64_t)r * P.ld + gc) =
+              make_double2(c2[j][2 * h], c2[j][2 * h + 1]);
+        }
+      }
+    __syncthreads();
+  }
+  cp_async_wait<0>();
+}
+
+// column norms of W (rows x ld, first ncols columns)
+__global__ void __launch_bounds__(256)
+    colnorm_kernel(const double *__restrict__ W, int64_t ld, int rows, int ncols,
+                   double *__restrict__ out) {
+  // one warp per 32 columns chunk-row: simple and coalesced: block handles
+  // 32 columns, threads (32 x 8) walk rows
+  __shared__ double sh[8][33];
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int ry = threadIdx.x >> 5;
+  double s = 0.0;
+  if (c < ncols)
+    for (int r = ry; r < rows; r += 8) {
+      const double v = W[(int64_t)r * ld + c];
+      s += v * v;
+    }
+  sh[ry][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (ry == 0 && c < ncols) {
+    double tot = 0.0;
+    for (int k = 0; k < 8; ++k) tot += sh[k][threadIdx.x & 31];
+    out[c] = sqrt(tot);
+  }
+}
+
+// U_R[:, k] = W[:, perm[k]] / s[perm[k]]   (n x nk, row-major), and
+// VH[k, :] = V[:, perm[k]]^T  (nk x ncols_v rows of V)
+__global__ void __launch_bounds__(256)
+    svd_gather_kernel(const double *__restrict__ W, const double *__restrict__ V,
+                      int64_t ld, int rows_w, int rows_v, int nk,
+                      const int *__restrict__ perm, const double *__restrict__ s,
+                      double *__restrict__ UR, double *__restrict__ VH) {
+  const int64_t tot_u = (int64_t)rows_w * nk, tot_v = (int64_t)nk * rows_v;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < tot_u + tot_v;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    if (i < tot_u) {
+      const int64_t r = i / nk;
+      const int k = (int)(i - r * nk);
+      const int c = perm[k];
+      const double sv = s[c];
+      UR[i] = (sv > 0.0) ? W[r * ld + c] / sv : 0.0;
+    } else {
+      const int64_t j = i - tot_u;
+      const int k = (int)(j / rows_v);
+      const int64_t r = j - (int64_t)k * rows_v;
+      VH[j] = V[r * ld + perm[k]];
+    }
+  }
+}
+
+__global__ void pad_copy_kernel(const double *__restrict__ src, int64_t rows,
+                                int64_t cols, int64_t ld_src, double *__restrict__ dst,
+                                int64_t ld_dst, int64_t rows_dst, int identity) {
+  // dst (rows_dst x ld_dst) = [src | 0] (or the identity when src == null)
+  const int64_t tot = rows_dst * ld_dst;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < tot;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / ld_dst, c = i - r * ld_dst;
+    double v = 0.0;
+    if (identity) v = (r == c) ? 1.0 : 0.0;
+    else if (r < rows && c < cols) v = src[r * ld_src + c];
+    dst[i] = v;
+  }
+}
+
+struct SvdGeom {
+  int64_t npad, qr_off, q1_off, r_off, w_off, v_off, s_off, ur_off, perm_off,
+      flag_off, xt_off, total;
+};
+
+static bool svd_geometry(int64_t m, int64_t n, SvdGeom &g) {
+  // m >= n here
+  QrGeom q;
+  if (!qr_geometry(m, n, q)) return false;
+  g.npad = ((n + JP - 1) / JP) * JP;
+  auto al = [](int64_t x) { return (x + 31) / 32 * 32; };  // 256-byte sections
+  int64_t off = 0;
+  g.qr_off = off; off += al(q.total);
+  g.q1_off = off; off += al(m * n);
+  g.r_off = off; off += al(n * n);
+  g.w_off = off; off += al(n * g.npad);
+  g.v_off = off; off += al(g.npad * g.npad);
+  g.s_off = off; off += al(g.npad);
+  g.ur_off = off; off += al(n * n);
+  g.perm_off = off; off += al((g.npad + 1) / 2 + 1);   // ints
+  g.flag_off = off; off += 32;
+  g.xt_off = off; off += 0;
+  g.total = off;
+  return true;
+}
+
+// SVD of row-major X (m x n), m >= n.  U (m x n), S (n), VH (n x n).
+static int svd_tall_f64(int64_t m, int64_t n, const double *X, double *U,
+                        double *S, double *VH, double *ws, int *sweeps_out,
+                        cudaStream_t st) {
+  SvdGeom g;
+  if (!svd_geometry(m, n, g)) {
+    set_error("qb_svd: unsupported shape %lld x %lld", (long long)m, (long long)n);
+    return -2;
+  }
+  double *Q1 = ws + g.q1_off, *R = ws + g.r_off, *W = ws + g.w_off;
+  double *V = ws + g.v_off, *sv = ws + g.s_off, *UR = ws + g.ur_off;
+  int *perm = reinterpret_cast<int *>(ws + g.perm_off);
+  int *flag = reinterpret_cast<int *>(ws + g.flag_off);
+  const int blocks = sm_count() * 4;
+  int rc = qr_f64(m, n, X, Q1, R, /*stabilized=*/0, ws + g.qr_off, st);
+  if (rc) return rc;
+  const int64_t npad = g.npad;
+  pad_copy_kernel<<<blocks, 256, 0, st>>>(R, n, n, n, W, npad, n, 0);
+  QB_LAUNCH_CHECK();
+  pad_copy_kernel<<<blocks, 256, 0, st>>>(nullptr, 0, 0, 0, V, npad, npad, 1);
+  QB_LAUNCH_CHECK();
+  constexpr int kJacSmem = 2 * JCH * JPITCH * 8;
+  static bool attr_set = false;
+  if (!attr_set) {
+    QB_CUDA_CHECK(cudaFuncSetAttribute(jacobi_pair_kernel,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       kJacSmem));
+    attr_set = true;
+  }
+  JacobiParams P;
+  P.W = W; P.V = V; P.ld = npad; P.rows_w = (int)n; P.rows_v = (int)npad;
+  P.nblk = (int)(npad / JB);
+  P.tol = 1e-15 * sqrt((double)n) * 8.0;
+  P.flag = flag;
+  int sweeps = 0;
+  const int max_sweeps = 40;
+  for (; sweeps < max_sweeps; ++sweeps) {
+    QB_CUDA_CHECK(cudaMemsetAsync(flag, 0, sizeof(int), st));
+    for (int r = 0; r < P.nblk - 1; ++r) {
+      P.round = r;
+      jacobi_pair_kernel<<<P.nblk / 2, 256, kJacSmem, st>>>(P);
+      QB_LAUNCH_CHECK();
+    }
+    int h = 0;
+    QB_CUDA_CHECK(cudaMemcpyAsync(&h, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    QB_CUDA_CHECK(cudaStreamSynchronize(st));
+    if (!h) break;
+  }
+  if (sweeps_out) *sweeps_out = sweeps;
+  if (sweeps >= max_sweeps) {
+    set_error("qb_svd: Jacobi did not converge in %d sweeps", max_sweeps);
+    return 2;
+  }
+  colnorm_kernel<<<(unsigned)(npad / 32), 256, 0, st>>>(W, npad, (int)n, (int)npad, sv);
+  QB_LAUNCH_CHECK();
+  std::vector<double> hs(npad);
+  QB_CUDA_CHECK(cudaMemcpyAsync(hs.data(), sv, sizeof(double) * npad,
+                                cudaMemcpyDeviceToHost, st));
+  QB_CUDA_CHECK(cudaStreamSynchronize(st));
+  std::vector<int> hp(npad);
+  for (int i = 0; i < npad; ++i) hp[i] = i;
+  std::stable_sort(hp.begin(), hp.end(), [&](int a, int b) {
+    const bool pa = a >= n, pb = b >= n;  // padding columns last
+    if (pa != pb) return pb;
+    return hs[a] > hs[b];
+  });
+  QB_CUDA_CHECK(cudaMemcpyAsync(perm, hp.data(), sizeof(int) * n,
+                                cudaMemcpyHostToDevice, st));
+  // sorted singular values
+  std::vector<double> ss(n);
+  for (int i = 0; i < n; ++i) ss[i] = hs[hp[i]];
+  if (S) QB_CUDA_CHECK(cudaMemcpyAsync(S, ss.data(), sizeof(double) * n,
+                                       cudaMemcpyHostToDevice, st));
+  // U_R, VH (VH rows: the first n rows of V only -- the rest is padding)
+  svd_gather_kernel<<<blocks, 256, 0, st>>>(W, V, npad, (int)n, (int)n, (int)n,
+                                            perm, sv, UR, VH ? VH : UR);
+  QB_LAUNCH_CHECK();
+  QB_CUDA_CHECK(cudaStreamSynchronize(st));  // host vectors go out of scope
+  if (U) {
+    rc = gemm_f64(Q1, n, 1, UR, n, 1, U, n, 1, m, n, n, 1.0, 0.0, st);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+}  // namespace qb
+
+extern "C" {
+
+int64_t qb_svd_workspace(int dtype, int64_t m, int64_t n) {
+  if (dtype != QB_F64) return -1;
+  qb::SvdGeom g;
+  const int64_t mm = std::max(m, n), nn = std::min(m, n);
+  if (!qb::svd_geometry(mm, nn, g)) return -2;
+  return g.total * 8;
+}
+
+int qb_svd(int dtype, int64_t m, int64_t n, const void *X, void *U, void *S,
+           void *VH, void *workspace, size_t workspace_bytes, int *sweeps_out,
+           void *stream) {
+  using namespace qb;
+  if (dtype != QB_F64) {
+    set_error("qb_svd: only f64 is implemented (got dtype %d)", dtype);
+    return -1;
+  }
+  if (m <= 0 || n <= 0) return 0;
+  const int64_t need = qb_svd_workspace(dtype, m, n);
+  if (need < 0) {
+    set_error("qb_svd: unsupported shape %lld x %lld", (long long)m, (long long)n);
+    return -2;
+  }
+  if (!workspace || (int64_t)workspace_bytes < need) {
+    set_error("qb_svd: workspace too small (need %lld bytes)", (long long)need);
+    return -8;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  double *ws = static_cast<double *>(workspace);
+  if (m >= n)
+    return svd_tall_f64(m, n, (const double *)X, (double *)U, (double *)S,
+                        (double *)VH, ws, sweeps_out, st);
+  // wide matrices: the host layer factors the transpose (a strided view
+  // materialised by qb_permute) and swaps the roles of U and VH.
+  (void)st; (void)ws;
+  set_error("qb_svd: m < n -- pass the transpose (m >= n required)");
+  return -2;
+}
+
+}  // extern "C"

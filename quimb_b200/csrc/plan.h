@@ -47,6 +47,8 @@ struct ContractParams {
   int64_t k_per_split;       // multiple of BK
   double *partial;           // [splitk][nbatch][M][N]
   int32_t tiles_m, tiles_n;
+  // C = alpha * A.B + beta * C   (real scalars; beta != 0 reads C)
+  double alpha, beta;
 };
 
 struct PairPlan {
@@ -110,7 +112,8 @@ inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 inline int plan_pair(const qb_tensor_t *A, const int32_t *la,
                      const qb_tensor_t *B, const int32_t *lb,
                      const qb_tensor_t *C, const int32_t *lc, int conjA,
-                     int conjB, PairPlan &plan, int force_cfg = -1) {
+                     int conjB, PairPlan &plan, int force_cfg = -1,
+                     int max_splitk = 64) {
   if (!A) return -1;
   if (!B) return -3;
   if (!C) return -5;
@@ -225,6 +228,7 @@ inline int plan_pair(const qb_tensor_t *A, const int32_t *la,
   for (int i = 0; i < p.k.n; ++i) { p.k.ext[i] = (int32_t)gk[i].ext; p.k.s0[i] = gk[i].a; p.k.s1[i] = gk[i].b; p.K *= gk[i].ext; }
   for (int i = 0; i < p.b.n; ++i) { p.b.ext[i] = (int32_t)gb[i].ext; p.b.s0[i] = gb[i].a; p.b.s1[i] = gb[i].b; p.bsC[i] = gb[i].c; p.nbatch *= gb[i].ext; }
   p.conjA = conjA; p.conjB = conjB;
+  p.alpha = 1.0; p.beta = 0.0;
   plan.dtype = A->dtype;
   plan.empty_out = zero_out;
   plan.zero_fill = zero_k && !zero_out;
@@ -309,7 +313,7 @@ inline int plan_pair(const qb_tensor_t *A, const int32_t *la,
     const int64_t tiles = cdiv(M, tc.bm) * cdiv(N, tc.bn) * p.nbatch;
     const int64_t kblocks = std::max<int64_t>(cdiv(Kh, tc.bk), 1);
     const int64_t slots = 148LL * kOcc[c];
-    for (int64_t sk = 1; sk <= 64; sk *= 2) {
+    for (int64_t sk = 1; sk <= max_splitk; sk *= 2) {
       if (sk > 1 && (kblocks / sk < 4)) break;
       const int64_t kb_per = cdiv(kblocks, sk);
       const int64_t nsplit = cdiv(kblocks, kb_per);

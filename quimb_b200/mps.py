@@ -1,0 +1,180 @@
+"""1D structured contractions on the device: the callers either side of the
+pairwise kernel for BASELINE config 2 (MPS norm / expectation) and for the
+DMRG environments.
+
+Mirrors (numerically, not structurally) quimb's
+``TensorNetwork1D.contract_structured`` / ``expec_TN_1D``
+(quimb/tensor/tn1d/core.py:55-95, 502-557) and ``TensorNetwork.norm``
+(quimb/tensor/tensor_core.py:4879-4918): the network is swept left to right
+carrying a (chi, chi) [or (chi, w, chi)] environment.  Each site costs
+4 d chi^3 flops in two launches of the contraction kernel; the bra is never
+materialised -- conjugation is a load flag of the kernel -- and site arrays
+are consumed in whatever layout they come in (strided views, no copies).
+
+Layouts: every function takes the index order of the site arrays as a string
+over {l, r, p} (quimb's default is 'lrp', tn1d/core.py:1801) and of MPO sites
+over {l, r, u, d} (quimb's 'lrud': u = ket-side 'k' index, d = bra-side 'b'
+index).  End sites may omit their dangling bond, as quimb's do.
+"""
+
+from . import ops
+from .array import Array
+from .contract import contract_pair
+
+# integer mode labels handed to the kernel
+L_, P_, R_, LB_, PB_, RB_, W_, WN_ = range(8)
+
+
+def site_lpr(x, shape, i, n):
+    """Free (l, p, r) view of site ``i`` of ``n`` given its layout string."""
+    x = ops.asarray(x)
+    lay = shape
+    if x.ndim == len(shape) - 1:
+        if i == 0 and "l" in lay:
+            lay = lay.replace("l", "")
+        elif i == n - 1 and "r" in lay:
+            lay = lay.replace("r", "")
+    if x.ndim != len(lay):
+        raise ValueError(f"site {i}: rank {x.ndim} does not fit layout {shape!r}")
+    t = x.t
+    for c in "lpr":
+        if c not in lay:
+            t = t.unsqueeze(-1)
+            lay = lay + c
+    return Array(t.permute(lay.index("l"), lay.index("p"), lay.index("r")), x.cj)
+
+
+def mpo_lrud(w, shape, i, n):
+    """Free (l, r, u, d) view of MPO site ``i`` of ``n``."""
+    w = ops.asarray(w)
+    lay = shape
+    if w.ndim == len(shape) - 1:
+        if i == 0 and "l" in lay:
+            lay = lay.replace("l", "")
+        elif i == n - 1 and "r" in lay:
+            lay = lay.replace("r", "")
+    if w.ndim != len(lay):
+        raise ValueError(f"MPO site {i}: rank {w.ndim} does not fit {shape!r}")
+    t = w.t
+    for c in "lrud":
+        if c not in lay:
+            t = t.unsqueeze(-1)
+            lay = lay + c
+    return Array(t.permute(*(lay.index(c) for c in "lrud")), w.cj)
+
+
+def norm_step(E, A):
+    """E'[b', b] = sum_{a', a, p} E[a', a] conj(A)[a', p, b'] A[a, p, b]"""
+    T = contract_pair(E.t, [LB_, L_], A.t, [L_, P_, R_], [LB_, P_, R_],
+                      conj_a=E.cj, conj_b=A.cj)
+    return Array(contract_pair(A.t, [LB_, P_, RB_], T, [LB_, P_, R_],
+                               [RB_, R_], conj_a=not A.cj))
+
+
+def _is_host(x):
+    import numpy as np
+    import torch
+    if isinstance(x, np.ndarray):
+        return True
+    return isinstance(x, torch.Tensor) and x.device.type == "cpu"
+
+
+def stream_sites(sites, copy_stream=None, depth=3):
+    """Iterate over site arrays, staging host-resident sites to the device
+    ``depth`` sites ahead on a side stream so the H2D copies overlap the
+    contraction of the previous sites (pinned host memory makes the copies
+    truly asynchronous)."""
+    import torch
+    if not any(_is_host(s) for s in sites):
+        yield from sites
+        return
+    dev = ops.default_device()
+    main = torch.cuda.current_stream(dev)
+    side = copy_stream or torch.cuda.Stream(device=dev)
+    side.wait_stream(main)
+    pending = []
+
+    def issue(s):
+        if not _is_host(s):
+            return (s, None)
+        t = s if isinstance(s, torch.Tensor) else torch.from_numpy(s)
+        with torch.cuda.stream(side):
+            d = t.to(dev, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(side)
+        return (d, ev)
+
+    it = iter(sites)
+    for s in it:
+        pending.append(issue(s))
+        if len(pending) >= depth:
+            break
+    while pending:
+        d, ev = pending.pop(0)
+        nxt = next(it, None)
+        if nxt is not None:
+            pending.append(issue(nxt))
+        if ev is not None:
+            main.wait_event(ev)
+            d.record_stream(main)
+        yield d
+
+
+def mps_norm2(sites, shape="lrp", copy_stream=None):
+    """<psi|psi> of an MPS given as device arrays, or as host arrays (numpy /
+    pinned torch tensors) that are streamed to the device while contracting;
+    returns a 0-d device Array."""
+    n = len(sites)
+    E = None
+    for i, s in enumerate(stream_sites(sites, copy_stream)):
+        A = site_lpr(s, shape, i, n)
+        if E is None:
+            E = ops.ones((A.shape[0], A.shape[0]), dtype=A.dtype, device=A.device)
+            if A.shape[0] != 1:
+                E = ops.eye(A.shape[0], dtype=A.dtype, device=A.device)
+        E = norm_step(E, A)
+    if E.shape != (1, 1):
+        return ops.trace(E)
+    return E.reshape(())
+
+
+def mps_norm(sites, shape="lrp"):
+    return ops.sqrt(ops.real(mps_norm2(sites, shape)))
+
+
+def env_left_step(E, A, W):
+    """E'[b', w', b] = sum E[a', w, a] A[a, p, b] W[w, w', p, q] conj(A)[a', q, b']
+
+    Order E.A -> .W -> .conj(A): 2 d w chi^3 + 2 w^2 d^2 chi^2 + 2 d w chi^3
+    flops (the MovingEnvironment update, quimb/tensor/tn1d/dmrg.py:383-405)."""
+    T = contract_pair(E.t, [LB_, W_, L_], A.t, [L_, P_, R_], [LB_, W_, P_, R_],
+                      conj_a=E.cj, conj_b=A.cj)
+    T = contract_pair(T, [LB_, W_, P_, R_], W.t, [W_, WN_, P_, PB_],
+                      [LB_, PB_, WN_, R_], conj_b=W.cj)
+    return Array(contract_pair(A.t, [LB_, PB_, RB_], T, [LB_, PB_, WN_, R_],
+                               [RB_, WN_, R_], conj_a=not A.cj))
+
+
+def env_right_step(E, A, W):
+    """E'[a', w, a] = sum A[a, p, b] E[b', w', b] W[w, w', p, q] conj(A)[a', q, b']"""
+    T = contract_pair(A.t, [L_, P_, R_], E.t, [RB_, WN_, R_], [L_, P_, WN_, RB_],
+                      conj_a=A.cj, conj_b=E.cj)
+    T = contract_pair(W.t, [W_, WN_, P_, PB_], T, [L_, P_, WN_, RB_],
+                      [W_, L_, PB_, RB_], conj_a=W.cj)
+    return Array(contract_pair(A.t, [LB_, PB_, RB_], T, [W_, L_, PB_, RB_],
+                               [LB_, W_, L_], conj_a=not A.cj))
+
+
+def mps_expec(sites, mpo, shape="lrp", mpo_shape="lrud"):
+    """<psi|H|psi> (quimb's expec_TN_1D(bra, mpo, ket)); 0-d Array."""
+    n = len(sites)
+    E = None
+    for i in range(n):
+        A = site_lpr(sites[i], shape, i, n)
+        W = mpo_lrud(mpo[i], mpo_shape, i, n)
+        if W.dtype != A.dtype:
+            W = W.astype(A.dtype)
+        if E is None:
+            E = ops.ones((1, 1, 1), dtype=A.dtype, device=A.device)
+        E = env_left_step(E, A, W)
+    return E.reshape(())

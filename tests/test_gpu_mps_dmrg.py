@@ -1,0 +1,130 @@
+"""GPU tier: MPS norm / expectation, device Lanczos and DMRG2 against the
+oracle and the reference-generated golden values."""
+
+import numpy as np
+import pytest
+
+import quimb_b200 as qb
+from oracle import dmrg_np as dm
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref_sites(data, prefix, L):
+    return [data[f"{prefix}__{i}"] for i in range(L)]
+
+
+def test_mps_norm_expec_match_reference_golden(golden_mps):
+    data, meta = golden_mps
+    sites = _ref_sites(data, "mps12", 12)          # quimb layout 'lrp'
+    n2 = qb.mps_norm2(sites, shape="lrp").item()
+    assert n2 == pytest.approx(meta["mps12_norm2"], rel=1e-12)
+    mpo = [np.asarray(data[f"heis6__{i}"]) for i in range(6)]
+    # 12-site Heisenberg MPO from the reference's 6-site tensors (bulk is uniform)
+    mpo12 = [mpo[0]] + [mpo[1]] * 10 + [mpo[5]]
+    e = qb.mps_expec(sites, mpo12, shape="lrp", mpo_shape="lrud").item()
+    assert e == pytest.approx(meta["mps12_expec_heis"], rel=1e-11)
+    csites = _ref_sites(data, "cmps8", 8)
+    n2c = qb.mps_norm2(csites, shape="lrp").item()
+    assert np.real(n2c) == pytest.approx(meta["cmps8_norm2"], rel=1e-12)
+    assert abs(np.imag(n2c)) < 1e-12 * abs(n2c)
+    mpo8 = [mpo[0]] + [mpo[1]] * 6 + [mpo[5]]
+    ec = qb.mps_expec(csites, mpo8, shape="lrp").item()
+    assert np.real(ec) == pytest.approx(meta["cmps8_expec_heis"], rel=1e-11)
+
+
+@pytest.mark.parametrize("L,chi", [(10, 16), (30, 64)])
+def test_mps_norm_vs_oracle(L, chi):
+    sites = dm.mps_rand(L, chi, seed=L)
+    ref = dm.mps_norm2(sites)
+    out = qb.mps_norm2(sites, shape="lpr").item()
+    assert out == pytest.approx(ref, rel=1e-12)
+    mpo = dm.mpo_heis(L)
+    # oracle MPO layout W[wl, wr, pu(bra), pd(ket)] -> 'lrdu'
+    e = qb.mps_expec(sites, mpo, shape="lpr", mpo_shape="lrdu").item()
+    assert e == pytest.approx(dm.mps_expec(sites, mpo), rel=1e-11)
+
+
+def test_env_steps_vs_oracle():
+    rng = np.random.default_rng(0)
+    E = rng.standard_normal((6, 5, 6)); A = rng.standard_normal((6, 2, 7))
+    W = rng.standard_normal((5, 4, 2, 2))
+    ref = dm.env_step_left(E, A, W)
+    Wq = np.transpose(W, (0, 1, 3, 2))             # -> (l, r, u=ket, d=bra)
+    out = qb.env_left_step(qb.asarray(E), qb.asarray(A), qb.asarray(Wq))
+    np.testing.assert_allclose(out.to_numpy(), ref, atol=1e-12)
+    E2 = rng.standard_normal((7, 4, 7))
+    ref = dm.env_step_right(E2, A, W)
+    out = qb.env_right_step(qb.asarray(E2), qb.asarray(A), qb.asarray(Wq))
+    np.testing.assert_allclose(out.to_numpy(), ref, atol=1e-12)
+
+
+def test_effective_hamiltonian_matvec_vs_oracle():
+    from quimb_b200.dmrg import EffHam2
+    rng = np.random.default_rng(1)
+    a, s, t, b, w = 9, 2, 2, 8, 5
+    L = rng.standard_normal((a, w, a)); R = rng.standard_normal((b, w, b))
+    W1 = rng.standard_normal((w, w, 2, 2)); W2 = rng.standard_normal((w, w, 2, 2))
+    x = rng.standard_normal(a * s * t * b)
+    ref = dm.EffHam2(L, W1, W2, R, (a, s, t, b))._matvec(x)
+    tq = lambda W: qb.asarray(np.transpose(W, (0, 1, 3, 2)))  # noqa: E731
+    H = EffHam2(qb.asarray(L), tq(W1), tq(W2), qb.asarray(R), (a, s, t, b))
+    out = H.matvec(qb.asarray(x))
+    np.testing.assert_allclose(out.to_numpy(), ref, rtol=1e-12, atol=1e-11)
+
+
+def test_lanczos_vs_dense():
+    rng = np.random.default_rng(2)
+    n = 600
+    M = rng.standard_normal((n, n)); M = 0.5 * (M + M.T)
+    Md = qb.asarray(M)
+    mv = lambda v: qb.tensordot(Md, v, axes=1)  # noqa: E731
+    v0 = qb.asarray(rng.standard_normal(n))
+    theta, x, info = qb.eigh_lanczos(mv, v0, ncv=20, tol=1e-10, return_info=True)
+    w = np.linalg.eigvalsh(M)
+    assert theta == pytest.approx(w[0], abs=1e-8)
+    xv = x.to_numpy()
+    assert np.linalg.norm(M @ xv - theta * xv) < 1e-6
+    assert abs(np.linalg.norm(xv) - 1) < 1e-12
+    thi, _ = qb.eigh_lanczos(mv, v0, which="LA", ncv=20, tol=1e-10)
+    assert thi == pytest.approx(w[-1], abs=1e-8)
+    # tiny problems: the Krylov space is the whole space
+    M4 = M[:4, :4]
+    th4, _ = qb.eigh_lanczos(lambda v: qb.tensordot(qb.asarray(M4), v, axes=1),
+                             qb.asarray(np.ones(4)), ncv=4, tol=1e-12)
+    assert th4 == pytest.approx(np.linalg.eigvalsh(M4)[0], abs=1e-10)
+
+
+def test_dmrg2_energies_match_reference_golden(golden_mps):
+    _, meta = golden_mps
+    run = meta["dmrg2_runs"][0]                      # L = 10, exact known
+    mpo = dm.mpo_heis(run["L"])
+    d = qb.DMRG2(mpo, run["bond_dims"], cutoffs=run["cutoffs"], mpo_shape="lrdu", seed=3)
+    d.solve(tol=run["tol"], max_sweeps=8)
+    assert d.energy == pytest.approx(run["exact"], abs=1e-7)
+    assert d.energy == pytest.approx(run["energies"][-1], abs=1e-6)
+    # state is normalised and right/left canonical pieces are isometries
+    n2 = qb.mps_norm2(d.state, shape="lpr").item()
+    assert n2 == pytest.approx(1.0, abs=1e-10)
+
+
+def test_dmrg2_L20_vs_reference_and_oracle(golden_mps):
+    _, meta = golden_mps
+    run = meta["dmrg2_runs"][1]
+    mpo = dm.mpo_heis(run["L"])
+    d = qb.DMRG2(mpo, run["bond_dims"], cutoffs=run["cutoffs"], mpo_shape="lrdu", seed=5)
+    d.solve(tol=run["tol"], max_sweeps=8)
+    assert d.energy == pytest.approx(run["energies"][-1], abs=20 * run["tol"])
+    o = dm.DMRG2(mpo, run["bond_dims"], cutoffs=run["cutoffs"], seed=5)
+    o.solve(tol=run["tol"], max_sweeps=8)
+    assert d.energy == pytest.approx(o.energy, abs=20 * run["tol"])
+    assert d.max_bond() <= run["bond_dims"][-1]
+
+
+def test_dmrg2_parity_mode_arpack_driver():
+    mpo = dm.mpo_heis(8)
+    d = qb.DMRG2(mpo, [8, 16], cutoffs=1e-10, mpo_shape="lrdu", seed=1)
+    d.opts["local_eig_backend"] = "SCIPY"
+    d.solve(tol=1e-8, max_sweeps=6)
+    H = dm.mpo_to_dense(mpo)
+    assert d.energy == pytest.approx(np.linalg.eigvalsh(H)[0], abs=1e-7)

@@ -1,0 +1,139 @@
+"""CPU tier: host logic of the product (planner, tree finder, option parsing)
+and the C-ABI surface.  No kernels are launched here."""
+
+import ctypes
+import itertools
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+
+import quimb_b200 as qb
+from quimb_b200 import _lib, split, tree
+from oracle import contract_np as cn
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "quimb_b200.h")).read()
+    names = set(re.findall(r"\b(qb_[a-z0-9_]+)\s*\(", header))
+    assert len(names) >= 20
+    missing = [n for n in sorted(names) if not hasattr(lib, n)]
+    assert not missing, missing
+    assert lib.qb_abi_version() == 1
+
+
+def _strides(shape):
+    st, acc = [], 1
+    for s in reversed(shape):
+        st.append(acc)
+        acc *= s
+    return list(reversed(st))
+
+
+@pytest.mark.parametrize("case", [
+    ("ab", "bc", "ac", dict(a=37, b=45, c=29)),
+    ("abcd", "cdef", "abef", dict(a=6, b=5, c=4, d=3, e=7, f=2)),
+    ("acbd", "dfce", "abef", dict(a=6, b=5, c=4, d=3, e=7, f=2)),
+    ("gab", "gbc", "gac", dict(g=3, a=4, b=5, c=6)),
+    ("abc", "abc", "", dict(a=3, b=4, c=5)),
+    ("ab", "cd", "abcd", dict(a=2, b=3, c=4, d=5)),
+    ("abe", "bc", "ac", dict(a=3, b=4, c=5, e=6)),
+])
+def test_planner_gemm_view(case):
+    ea, eb, ec, sz = case
+    L = {c: i for i, c in enumerate("abcdefgh")}
+    sa, sb, sc = ([sz[c] for c in e] for e in (ea, eb, ec))
+    plan = qb.plan_pair(sa, _strides(sa), [L[c] for c in ea], sb, _strides(sb),
+                        [L[c] for c in eb], sc, _strides(sc), [L[c] for c in ec])
+    batch = [c for c in ea if c in eb and c in ec]
+    m = [c for c in ea if c in ec and c not in eb]
+    n = [c for c in eb if c in ec and c not in ea]
+    k = [c for c in set(ea + eb) if c not in ec]
+    prod = lambda cs: int(np.prod([sz[c] for c in cs])) if cs else 1  # noqa: E731
+    assert plan["M"] == prod(m)
+    assert plan["N"] == prod(n)
+    assert plan["K"] == prod(k)
+    assert plan["batch"] == prod(batch)
+
+
+def test_planner_merges_contiguous_modes():
+    # (a b) and (c d) are jointly contiguous everywhere -> single modes
+    plan = qb.plan_pair([6, 5, 4, 3], [60, 12, 3, 1], [0, 1, 2, 3],
+                        [4, 3, 7, 2], [42, 14, 2, 1], [2, 3, 4, 5],
+                        [6, 5, 7, 2], [70, 14, 2, 1], [0, 1, 4, 5])
+    assert (plan["n_m"], plan["n_n"], plan["n_k"]) == (1, 1, 1)
+    assert plan["vecB"] == 1 and plan["vecC"] == 1
+
+
+def test_planner_errors():
+    with pytest.raises(ValueError):
+        qb.plan_pair([3, 4], [4, 1], [0, 1], [5, 6], [6, 1], [1, 2], [3, 6], [6, 1], [0, 2])
+    with pytest.raises(ValueError):  # output label in neither input
+        qb.plan_pair([3], [1], [0], [3], [1], [0], [2], [1], [7])
+
+
+def test_gen_output_inds_matches_reference_rule():
+    assert tree.gen_output_inds("abc" "cd" "ea") == ("b", "d", "e")
+    with pytest.raises(ValueError) as e:
+        tree.gen_output_inds(list("ab") + list("bc") + list("bd"))
+    meta = json.load(open(os.path.join(ROOT, "tests", "golden", "contract.json")))
+    assert str(e.value) == meta["_triple_index_error"]
+
+
+def test_tree_finder_cost_not_worse_than_oracle():
+    rng = np.random.default_rng(0)
+    for trial in range(20):
+        n = rng.integers(3, 7)
+        letters = "abcdefghij"
+        sizes = {c: int(rng.integers(2, 6)) for c in letters}
+        inputs = []
+        for _ in range(n):
+            r = rng.integers(1, 4)
+            inputs.append(tuple(rng.choice(list(letters), size=r, replace=False)))
+        flat = list(itertools.chain.from_iterable(inputs))
+        if any(flat.count(c) > 2 for c in set(flat)):
+            continue
+        out = cn.gen_output_inds(flat)
+        t = tree.find_tree(inputs, out, sizes, "optimal")
+        path = cn.find_path(inputs, out, sizes, "optimal")
+        fl, _ = cn.path_cost(inputs, out, sizes, path)
+        assert 2 * t.contraction_cost() <= fl + 1e-9
+
+
+def test_parse_split_opts_codes_match_reference():
+    meta = json.load(open(os.path.join(ROOT, "tests", "golden", "decomp.json")))
+    for c in meta["parse_split_opts"]:
+        kw = dict(c["kw"])
+        if kw.get("method", "auto") in ("auto", "svd", "qr", "lq"):
+            method, opts = split.parse_split_opts(**kw)
+            assert method == c["method"]
+            ref = dict(c["opts"])
+            for k, v in ref.items():
+                assert opts[k] == v, (kw, k)
+
+
+def test_svals_to_keep_c_matches_reference():
+    meta = json.load(open(os.path.join(ROOT, "tests", "golden", "decomp.json")))
+    s = np.array(meta["svals_to_keep"]["s"])
+    for cutoff, mode, expect in meta["svals_to_keep"]["cases"]:
+        n_keep, _, _ = split.svals_to_keep(s, cutoff, mode, -1, 0)
+        assert n_keep == expect
+    # renorm known answers (reference tests: 385 / 55 preserved)
+    s = np.arange(10, 0, -1.0)
+    n_keep, f, err = split.svals_to_keep(s, 1e-9, 3, 5, 2)
+    assert n_keep == 5 and np.isclose(np.sum((s[:5] * f) ** 2), 385.0)
+    assert np.isclose(err, np.sqrt(np.sum(s[5:] ** 2)))
+    n_keep, f, _ = split.svals_to_keep(s, 1e-9, 5, 5, 1)
+    assert np.isclose(np.sum(s[:5] * f), 55.0)
+
+
+def test_no_cpu_fallback():
+    import torch
+    a = torch.zeros(3, 3, dtype=torch.float64)
+    with pytest.raises(_lib.QuimbB200Error):
+        qb.contract_pair(a, [0, 1], a, [1, 2], [0, 2])

@@ -1,0 +1,154 @@
+"""CPU tier: the numpy oracle (oracle/) is pinned against golden vectors
+produced by the unmodified reference (oracle/make_golden.py) and against the
+known answers the reference's own tests hold for this path."""
+
+import numpy as np
+import pytest
+
+from oracle import contract_np as cn
+from oracle import decomp_np as dn
+from oracle import dmrg_np as dm
+
+
+def test_contract_matches_reference(golden_contract):
+    data, meta = golden_contract
+    for name, m in meta.items():
+        if name.startswith("_"):
+            continue
+        arrays = [data[f"{name}__in{k}"] for k in range(len(m["inds"]))]
+        inds = [tuple(i) for i in m["inds"]]
+        out, inds_out = cn.tensor_contract(arrays, inds, m["output_inds"])
+        # index bookkeeping: bit exact
+        assert list(inds_out) == m["result_inds"], name
+        ref = data[f"{name}__out"]
+        assert out.shape == ref.shape, name
+        np.testing.assert_allclose(out, ref, rtol=1e-12, atol=1e-12, err_msg=name)
+
+
+def test_triple_index_error(golden_contract):
+    _, meta = golden_contract
+    with pytest.raises(ValueError) as e:
+        cn.gen_output_inds(list("ab") + list("bc") + list("bd"))
+    assert str(e.value) == meta["_triple_index_error"]
+
+
+def test_output_inds_order_rule():
+    # tests/test_tensor/test_tensor_core.py:434-512 (TestTensorContract)
+    assert cn.gen_output_inds("abc" "cd" "ea") == ("b", "d", "e")
+    assert cn.gen_output_inds([0, 1, 2, 2, 3]) == (0, 1, 3)
+
+
+def test_svals_to_keep_known_answers(golden_decomp):
+    _, meta = golden_decomp
+    s = np.array(meta["svals_to_keep"]["s"])
+    for cutoff, mode, expect in meta["svals_to_keep"]["cases"]:
+        assert dn.number_svals_to_keep(s, cutoff, mode) == expect
+    # the reference's own test (test_decomp.py:52-57)
+    s = np.array([3.0, 2.0, 1.0, 0.1])
+    assert dn.number_svals_to_keep(s, 1.1, 1) == 2
+
+
+def test_renorm_known_answers():
+    # test_tensor_core.py:677-716: sum of squares 385 / sum 55 preserved
+    s = np.arange(10, 0, -1.0)
+    f2 = dn.svals_renorm_factor(s, 5, 2)
+    assert np.isclose(np.sum((s[:5] * f2) ** 2), 385.0)
+    f1 = dn.svals_renorm_factor(s, 5, 1)
+    assert np.isclose(np.sum(s[:5] * f1), 55.0)
+
+
+def test_svd_truncated_matches_reference(golden_decomp):
+    data, meta = golden_decomp
+    for c in meta["svd_cases"]:
+        x = data[f"mat__{c['mat']}"]
+        info = {}
+        left, s, right = dn.svd_truncated(
+            x, cutoff=c["cutoff"], cutoff_mode=c["cutoff_mode"],
+            max_bond=c["max_bond"], absorb=c["absorb"], renorm=c["renorm"],
+            info=info)
+        k = left.shape[1] if left is not None else right.shape[0]
+        assert k == c["n_keep"], c
+        assert info["error"] == pytest.approx(c["error"], rel=1e-9, abs=1e-12)
+        if c["key"] + "__s" in data:
+            np.testing.assert_allclose(s, data[c["key"] + "__s"], rtol=1e-10)
+        if c["key"] + "__rec" in data:
+            rec = left @ (np.diag(s) @ right if s is not None else right)
+            np.testing.assert_allclose(rec, data[c["key"] + "__rec"], atol=1e-10)
+
+
+def test_qr_stabilized_matches_reference(golden_decomp):
+    data, meta = golden_decomp
+    for c in meta["qr_cases"]:
+        x = data[f"mat__{c['mat']}"]
+        left, _, right = dn.qr_stabilized(x.copy(), absorb=c["absorb"])
+        for part, nm in ((left, "__left"), (right, "__right")):
+            key = c["key"] + nm
+            assert (part is not None) == (key in data), c
+            if part is not None:
+                np.testing.assert_allclose(part, data[key], atol=1e-11)
+
+
+def test_tensor_split_matches_reference(golden_decomp):
+    data, meta = golden_decomp
+    x = data["split__x"]
+    for c in meta["split_cases"]:
+        kw = dict(c["kw"])
+        left_inds = kw.pop("left_inds")
+        right_inds = kw.pop("right_inds", None)
+        out = dn.tensor_split(x, "abcd", left_inds, right_inds, **kw)
+        got = [o for o in out if o is not None]
+        assert len(got) == c["n_out"]
+        refs = [data[f"{c['key']}__{j}"] for j in range(c["n_out"])]
+        for g, r in zip(got, refs):
+            assert g.shape == r.shape
+        # factors are gauge dependent (signs); their product is not
+        def rebuild(parts):
+            if len(parts) == 3:
+                l, s, r = parts
+                return np.tensordot(l * s, r, axes=1)
+            return np.tensordot(parts[0], parts[1], axes=1)
+        np.testing.assert_allclose(rebuild(got), rebuild(refs), atol=1e-10)
+
+
+def test_heisenberg_mpo_matches_reference(golden_mps):
+    data, _ = golden_mps
+    H = dm.mpo_to_dense(dm.mpo_heis(6))
+    np.testing.assert_allclose(H, data["heis6__dense"], atol=1e-13)
+
+
+def _ref_mps_to_lpr(data, prefix, L):
+    """reference layout (l, r, p) [ends (r,p)/(l,p)] -> oracle layout (l,p,r)"""
+    sites = []
+    for i in range(L):
+        x = data[f"{prefix}__{i}"]
+        if i == 0:
+            x = x[None, :, :]            # (1, r, p)
+        elif i == L - 1:
+            x = x[:, None, :]            # (l, 1, p)
+        sites.append(np.transpose(x, (0, 2, 1)))
+    return sites
+
+
+def test_mps_norm_expec_match_reference(golden_mps):
+    data, meta = golden_mps
+    sites = _ref_mps_to_lpr(data, "mps12", 12)
+    n2 = dm.mps_norm2(sites)
+    assert n2 == pytest.approx(meta["mps12_norm2"], rel=1e-12)
+    e = dm.mps_expec(sites, dm.mpo_heis(12))
+    assert e == pytest.approx(meta["mps12_expec_heis"], rel=1e-11)
+    csites = _ref_mps_to_lpr(data, "cmps8", 8)
+    assert np.real(dm.mps_norm2(csites)) == pytest.approx(meta["cmps8_norm2"], rel=1e-12)
+    assert np.real(dm.mps_expec(csites, dm.mpo_heis(8))) == pytest.approx(
+        meta["cmps8_expec_heis"], rel=1e-11)
+
+
+def test_dmrg2_energies_match_reference(golden_mps):
+    _, meta = golden_mps
+    for run in meta["dmrg2_runs"][:2]:
+        d = dm.DMRG2(dm.mpo_heis(run["L"]), run["bond_dims"], cutoffs=run["cutoffs"], seed=7)
+        d.solve(tol=run["tol"], max_sweeps=8)
+        # converged energies agree with the reference run (different random
+        # start, loose inner tolerance -> compare at the solve tolerance)
+        assert d.energy == pytest.approx(run["energies"][-1], abs=20 * run["tol"])
+        if run["exact"] is not None:
+            assert d.energy == pytest.approx(run["exact"], abs=1e-6)
