@@ -326,16 +326,21 @@ __global__ void __launch_bounds__(WARPS_M *WARPS_N * 32)
     sgn_mask = neg ? 0x80000000u : 0u;
   }
 
+  const bool early = ((warp >> 2) & 1) == 0 || (NT <= 128);
 #pragma unroll 1
   for (int kb = 0; kb < nkb; ++kb) {
     cp_async_wait<STAGES - 2>();
     __syncthreads();  // stage kb landed; stage kb-1 free; next ktab visible
-    issue(kb + STAGES - 1);
+    // the two warps that share a scheduler (warp, warp+4) issue their
+    // gathers at different points of the k-block so that one of them always
+    // has DMMAs ready while the other does address arithmetic
+    if (early) issue(kb + STAGES - 1);
     fill_ktab(kb + STAGES);
     const double *tA = sA + (size_t)(kb % STAGES) * Cfg::A_ELEMS;
     const double *tB = sB + (size_t)(kb % STAGES) * Cfg::B_ELEMS;
 #pragma unroll
     for (int kk = 0; kk < BK; kk += 8) {
+      if (kk == 8 && !early) issue(kb + STAGES - 1);
       double af[MT][4], bf[NT8][2];
 #pragma unroll
       for (int i = 0; i < MT; ++i) {
