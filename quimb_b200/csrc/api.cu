@@ -1,6 +1,7 @@
 // extern "C" entry points declared in include/quimb_b200.h
 #include <stdarg.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include <vector>
 
@@ -68,6 +69,19 @@ static int check_device_dtype(int dt) {
 
 using namespace qb;
 
+// engine policy: explicit request, or QB_ENGINE=ozaki|dmma in the environment
+static bool want_ozaki(int engine, const PairPlan &plan) {
+  static const int env_engine = [] {
+    const char *e = getenv("QB_ENGINE");
+    if (e && !strcmp(e, "ozaki")) return (int)QB_ENGINE_OZAKI;
+    if (e && !strcmp(e, "dmma")) return (int)QB_ENGINE_DMMA;
+    return (int)QB_ENGINE_AUTO;
+  }();
+  if (engine == QB_ENGINE_AUTO) engine = env_engine;
+  return engine == QB_ENGINE_OZAKI && ozaki_eligible(plan);
+}
+
+
 extern "C" {
 
 int qb_abi_version(void) { return QB_ABI_VERSION; }
@@ -94,17 +108,18 @@ int64_t qb_contract_pair_workspace(const qb_tensor_t *A, const int32_t *la,
                                    const qb_tensor_t *B, const int32_t *lb,
                                    const qb_tensor_t *C, const int32_t *lc,
                                    int engine) {
-  (void)engine;
   PairPlan plan;
   int rc = plan_pair(A, la, B, lb, C, lc, 0, 0, plan);
   if (rc) return rc;
-  return plan_workspace_bytes(plan);
+  int64_t need = plan_workspace_bytes(plan);
+  if (want_ozaki(engine, plan)) need = std::max(need, ozaki_workspace_bytes(plan));
+  return need;
 }
 
 static int contract_pair_impl(const qb_tensor_t *A, const int32_t *la,
                               const qb_tensor_t *B, const int32_t *lb,
                               qb_tensor_t *C, const int32_t *lc, int conjA,
-                              int conjB, double alpha, double beta,
+                              int conjB, double alpha, double beta, int engine,
                               void *workspace, size_t workspace_bytes,
                               void *stream) {
   PairPlan plan;
@@ -124,6 +139,16 @@ static int contract_pair_impl(const qb_tensor_t *A, const int32_t *la,
     set_error("zero-extent contraction with beta not in {0, 1}");
     return -10;
   }
+  plan.p.alpha = alpha; plan.p.beta = beta;
+  if (want_ozaki(engine, plan)) {
+    int64_t need = ozaki_workspace_bytes(plan);
+    if (!workspace || (int64_t)workspace_bytes < need) {
+      set_error("workspace too small: need %lld bytes, got %lld",
+                (long long)need, (long long)workspace_bytes);
+      return -10;
+    }
+    return launch_contract_ozaki(plan, workspace, st);
+  }
   int64_t need = plan_workspace_bytes(plan);
   if (need > 0) {
     if (!workspace || (int64_t)workspace_bytes < need) {
@@ -133,7 +158,6 @@ static int contract_pair_impl(const qb_tensor_t *A, const int32_t *la,
     }
     plan.p.partial = static_cast<double *>(workspace);
   }
-  plan.p.alpha = alpha; plan.p.beta = beta;
   if (plan.dtype == QB_F64) return launch_contract_f64(plan, st);
   return launch_contract_c128(plan, st);
 }
@@ -142,8 +166,7 @@ int qb_contract_pair(const qb_tensor_t *A, const int32_t *la,
                      const qb_tensor_t *B, const int32_t *lb, qb_tensor_t *C,
                      const int32_t *lc, int conjA, int conjB, int engine,
                      void *workspace, size_t workspace_bytes, void *stream) {
-  (void)engine;
-  return contract_pair_impl(A, la, B, lb, C, lc, conjA, conjB, 1.0, 0.0,
+  return contract_pair_impl(A, la, B, lb, C, lc, conjA, conjB, 1.0, 0.0, engine,
                             workspace, workspace_bytes, stream);
 }
 
@@ -153,7 +176,7 @@ int qb_contract_pair_ab(const qb_tensor_t *A, const int32_t *la,
                         int conjB, double alpha, double beta, void *workspace,
                         size_t workspace_bytes, void *stream) {
   return contract_pair_impl(A, la, B, lb, C, lc, conjA, conjB, alpha, beta,
-                            workspace, workspace_bytes, stream);
+                            QB_ENGINE_AUTO, workspace, workspace_bytes, stream);
 }
 
 int qb_contract_batched(const qb_tensor_t *A0, const int32_t *la,

@@ -29,36 +29,6 @@
 
 namespace qb {
 
-// mixed-radix decode of a linear group index into two element offsets
-__device__ __forceinline__ void decode2(int64_t idx, const ModeGroup &g,
-                                        int64_t &o0, int64_t &o1) {
-  int64_t a = 0, b = 0;
-  if (idx <= 0xffffffffLL) {
-    uint32_t r = (uint32_t)idx;
-#pragma unroll 1
-    for (int i = 0; i < g.n; ++i) {
-      uint32_t e = (uint32_t)g.ext[i];
-      uint32_t q = r / e;
-      uint32_t d = r - q * e;
-      a += (int64_t)d * g.s0[i];
-      b += (int64_t)d * g.s1[i];
-      r = q;
-    }
-  } else {
-#pragma unroll 1
-    for (int i = 0; i < g.n; ++i) {
-      int64_t e = g.ext[i];
-      int64_t q = idx / e;
-      int64_t d = idx - q * e;
-      a += d * g.s0[i];
-      b += d * g.s1[i];
-      idx = q;
-    }
-  }
-  o0 = a;
-  o1 = b;
-}
-
 template <int BM, int BN, int BK, int WARPS_M, int WARPS_N, int STAGES>
 struct KernelCfg {
   static constexpr int NT = WARPS_M * WARPS_N * 32;

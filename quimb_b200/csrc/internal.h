@@ -9,6 +9,11 @@ int launch_contract_f64(const PairPlan &plan, cudaStream_t st);
 int launch_contract_c128(const PairPlan &plan, cudaStream_t st);
 int launch_fill_zero(const qb_tensor_t *C, cudaStream_t st);
 
+// tcgen05 int8 error-free-split engine (ozaki_tc.cu)
+bool ozaki_eligible(const PairPlan &plan);
+int64_t ozaki_workspace_bytes(const PairPlan &plan);
+int launch_contract_ozaki(const PairPlan &plan, void *workspace, cudaStream_t st);
+
 // C(MxN) = alpha * A(MxK) * B(KxN) + beta * C on strided fp64 matrices
 // (element strides; any of them may describe a transposed view).
 int gemm_f64(const double *A, int64_t a_rs, int64_t a_cs, const double *B,

@@ -181,3 +181,49 @@ def test_full_size_properties_chi1024():
     a = qb.tensordot(E1, A, axes=((1,), (0,)))
     b = qb.tensordot(A.transpose(2, 1, 0), E1.T, axes=((2,), (0,))).transpose(2, 1, 0)
     assert float(abs(a - b).max().item()) < 1e-10
+
+
+# ---- tcgen05 (int8 error-free split) engine -------------------------------
+OZ_CASES = [
+    ("ab,bc->ac", dict(a=128, b=128, c=64)),
+    ("ab,bc->ac", dict(a=1000, b=777, c=333)),
+    ("ba,bc->ac", dict(a=300, b=200, c=150)),
+    ("acbd,dfce->abef", dict(a=32, b=20, c=24, d=28, e=16, f=18)),
+    ("xwa,asbt->xwsbt", dict(x=64, w=5, a=256, s=2, b=64, t=2)),
+]
+
+
+@pytest.mark.parametrize("eq,sizes", OZ_CASES)
+def test_tcgen05_engine_matches_oracle(eq, sizes):
+    rng = np.random.default_rng(abs(hash(eq)) % 2**31)
+    lhs, rhs = eq.split("->")
+    ta, tb = lhs.split(",")
+    a = _rand(rng, [sizes[c] for c in ta], "float64")
+    b = _rand(rng, [sizes[c] for c in tb], "float64")
+    sym = {c: i for i, c in enumerate(dict.fromkeys(ta + tb + rhs))}
+    A, B = qb.asarray(a), qb.asarray(b)
+    n0 = qb.launch_count()
+    out = qb.contract_pair(A.t, [sym[c] for c in ta], B.t, [sym[c] for c in tb],
+                           [sym[c] for c in rhs], engine=2)
+    # rowmax + split for each operand, then the tcgen05 GEMM: 5 launches
+    assert qb.launch_count() - n0 == 5
+    ref = np.einsum(eq, a, b)
+    # fp64-level: error relative to max|row| max|col| sqrt(K)
+    assert np.max(np.abs(out.cpu().numpy() - ref)) <= 1e-12 * np.max(np.abs(ref))
+
+
+def test_tcgen05_engine_badly_scaled_and_accumulate():
+    rng = np.random.default_rng(8)
+    a = rng.standard_normal((256, 384)) * np.logspace(-9, 9, 256)[:, None]
+    b = rng.standard_normal((384, 192)) * np.logspace(-7, 7, 192)[None, :]
+    c0 = rng.standard_normal((256, 192))
+    C = qb.asarray(c0.copy())
+    qb.contract_pair(qb.asarray(a).t, [0, 1], qb.asarray(b).t, [1, 2], [0, 2],
+                     out=C.t, engine=2, alpha=1.0, beta=0.0)
+    ref = a @ b
+    scale = np.abs(a).max(1)[:, None] * np.abs(b).max(0)[None, :] * np.sqrt(384)
+    assert np.max(np.abs(C.to_numpy() - ref) / scale) < 1e-14
+    # small shapes silently use the exact DMMA engine
+    small = qb.contract_pair(qb.asarray(a[:8, :16]).t, [0, 1], qb.asarray(b[:16, :8]).t,
+                             [1, 2], [0, 2], engine=2)
+    np.testing.assert_allclose(small.cpu().numpy(), a[:8, :16] @ b[:16, :8], rtol=1e-12, atol=1e-6)
