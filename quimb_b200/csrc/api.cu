@@ -34,7 +34,8 @@ int sm_count() {
 int gemm_f64(const double *A, int64_t a_rs, int64_t a_cs, const double *B,
              int64_t b_rs, int64_t b_cs, double *C, int64_t c_rs, int64_t c_cs,
              int64_t M, int64_t N, int64_t K, double alpha, double beta,
-             cudaStream_t st) {
+             cudaStream_t st, double *splitk_ws, int64_t splitk_ws_elems,
+             int max_splitk) {
   if (M <= 0 || N <= 0) return 0;
   qb_tensor_t a, b, c;
   memset(&a, 0, sizeof(a)); memset(&b, 0, sizeof(b)); memset(&c, 0, sizeof(c));
@@ -46,8 +47,18 @@ int gemm_f64(const double *A, int64_t a_rs, int64_t a_cs, const double *B,
   c.shape[0] = M; c.shape[1] = N; c.stride[0] = c_rs; c.stride[1] = c_cs;
   const int32_t la[2] = {0, 1}, lb[2] = {1, 2}, lc[2] = {0, 2};
   PairPlan plan;
-  int rc = plan_pair(&a, la, &b, lb, &c, lc, 0, 0, plan, -1, /*max_splitk=*/1);
+  if (!splitk_ws) max_splitk = 1;
+  int rc = plan_pair(&a, la, &b, lb, &c, lc, 0, 0, plan, -1, max_splitk);
   if (rc) return rc;
+  if (plan.p.splitk > 1) {
+    if (plan_workspace_bytes(plan) > splitk_ws_elems * 8) {
+      // not enough scratch: redo the plan without split-K
+      rc = plan_pair(&a, la, &b, lb, &c, lc, 0, 0, plan, -1, 1);
+      if (rc) return rc;
+    } else {
+      plan.p.partial = splitk_ws;
+    }
+  }
   if (plan.zero_fill) {
     if (beta == 0.0) return launch_fill_zero(&c, st);
     return 0;

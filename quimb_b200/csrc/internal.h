@@ -19,6 +19,7 @@ int launch_contract_ozaki(const PairPlan &plan, void *workspace, cudaStream_t st
 int gemm_f64(const double *A, int64_t a_rs, int64_t a_cs, const double *B,
              int64_t b_rs, int64_t b_cs, double *C, int64_t c_rs, int64_t c_cs,
              int64_t M, int64_t N, int64_t K, double alpha, double beta,
-             cudaStream_t st);
+             cudaStream_t st, double *splitk_ws = nullptr,
+             int64_t splitk_ws_elems = 0, int max_splitk = 1);
 
 }  // namespace qb

@@ -21,6 +21,7 @@
 //                  summation order as the reference.
 #include <cooperative_groups.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <vector>
@@ -266,7 +267,7 @@ static int launch_panel(double *A, int64_t lda, int m, int nbw, double *V,
 
 struct QrGeom {
   int nb;
-  int64_t f_off, v_off, t_off, w_off, w2_off, total;  // in doubles
+  int64_t f_off, v_off, t_off, w_off, w2_off, sk_off, sk_elems, total;  // in doubles
 };
 
 static bool qr_geometry(int64_t m, int64_t n, QrGeom &g) {
@@ -283,6 +284,8 @@ static bool qr_geometry(int64_t m, int64_t n, QrGeom &g) {
   g.t_off = off; off += al(npan * g.nb * g.nb);    // T per panel
   g.w_off = off; off += al((int64_t)g.nb * std::max(n, k));
   g.w2_off = off; off += al((int64_t)g.nb * std::max(n, k));
+  g.sk_elems = al((int64_t)16 * g.nb * std::max(n, k));  // split-K partials
+  g.sk_off = off; off += g.sk_elems;
   g.total = off;
   return true;
 }
@@ -301,6 +304,8 @@ static int qr_f64(int64_t m, int64_t n, const double *X, double *Q, double *R,
   const int nb = g.nb;
   double *F = ws + g.f_off, *V = ws + g.v_off, *T = ws + g.t_off;
   double *W = ws + g.w_off, *W2 = ws + g.w2_off;
+  double *SK = ws + g.sk_off;
+  const int64_t SKN = g.sk_elems;
   QB_CUDA_CHECK(cudaMemcpyAsync(F, X, sizeof(double) * m * n,
                                 cudaMemcpyDeviceToDevice, st));
   int rc;
@@ -320,7 +325,7 @@ static int qr_f64(int64_t m, int64_t n, const double *X, double *Q, double *R,
     if (nt > 0) {
       double *A2 = F + j0 * n + j0 + nbw;
       // W = V^T A2            (nb x nt)
-      if ((rc = gemm_f64(Vp, 1, nb, A2, n, 1, W, nt, 1, nb, nt, mp, 1.0, 0.0, st))) return rc;
+      if ((rc = gemm_f64(Vp, 1, nb, A2, n, 1, W, nt, 1, nb, nt, mp, 1.0, 0.0, st, SK, SKN, 16))) return rc;
       // W2 = T^T W            (nb x nt)
       if ((rc = gemm_f64(Tp, 1, nb, W, nt, 1, W2, nt, 1, nb, nt, nb, 1.0, 0.0, st))) return rc;
       // A2 -= V W2
@@ -343,7 +348,7 @@ static int qr_f64(int64_t m, int64_t n, const double *X, double *Q, double *R,
       const int64_t nq = k - j0;
       double *Vp = V + pj * m * nb, *Tp = T + pj * nb * nb;
       double *Qs = Q + j0 * k + j0;
-      if ((rc = gemm_f64(Vp, 1, nb, Qs, k, 1, W, nq, 1, nb, nq, mp, 1.0, 0.0, st))) return rc;
+      if ((rc = gemm_f64(Vp, 1, nb, Qs, k, 1, W, nq, 1, nb, nq, mp, 1.0, 0.0, st, SK, SKN, 16))) return rc;
       if ((rc = gemm_f64(Tp, nb, 1, W, nq, 1, W2, nq, 1, nb, nq, nb, 1.0, 0.0, st))) return rc;
       if ((rc = gemm_f64(Vp, nb, 1, W2, nq, 1, Qs, k, 1, mp, nq, nb, -1.0, 1.0, st))) return rc;
     }
@@ -474,6 +479,7 @@ struct JacobiParams {
   int round;       // 0 .. nblk-2
   double tol;
   int *flag;       // set to 1 when any pair still needed rotating
+  int inner_max;   // max inner Jacobi sweeps per visit
 };
 
 __device__ __forceinline__ void rr_pair(int k, int round, int nblk, int &p, int &q) {
@@ -500,25 +506,41 @@ __device__ __forceinline__ void jac_load_chunk(double (*Xs)[JPITCH], const doubl
   }
 }
 
-__global__ void __launch_bounds__(256)
+constexpr int JSTG = 4;         // cp.async stages of the row-chunk stream
+constexpr int JCSZ = 2;         // CTAs (one cluster) per column-block pair
+
+// One round-robin round of the one-sided block Jacobi method.  A CLUSTER of
+// JCSZ CTAs owns one pair of column blocks (2 x 16 columns); the rows of W
+// and V are dealt round-robin (64-row chunks) to the CTAs of the cluster:
+//   1. partial Gram of the 32 columns by DMMA from a 4-stage cp.async stream,
+//      reduced over warps and then over the cluster through distributed
+//      shared memory (fixed order: deterministic);
+//   2. every CTA diagonalises the same 32 x 32 Gram by parallel-ordered
+//      cyclic Jacobi (two-sided rotations fused into one pass, 2 barriers
+//      per step), eigenvalues sorted descending;
+//   3. the rotation is applied by DMMA to this CTA's rows of W and of V.
+__global__ void __cluster_dims__(JCSZ, 1, 1) __launch_bounds__(256)
     jacobi_pair_kernel(const JacobiParams P) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
   extern __shared__ __align__(16) unsigned char jac_smem[];
   double(*Xs)[JCH][JPITCH] = reinterpret_cast<double(*)[JCH][JPITCH]>(jac_smem);
   __shared__ double G[JP][JP + 1];
+  __shared__ double Gpart[JP][JP];
   __shared__ __align__(16) double Jm[JP][JPITCH];
   __shared__ double rot[JB][2];
   __shared__ int rotpq[JB][2];
   __shared__ double redmax[8];
-  __shared__ int s_any;
   __shared__ int rank_s[JP];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
   int bp, bq;
-  rr_pair(blockIdx.x, P.round, P.nblk, bp, bq);
+  rr_pair(blockIdx.x / JCSZ, P.round, P.nblk, bp, bq);
   const int cp = bp * JB, cq = bq * JB;
 
-  // ---------------- phase 1: Gram matrix of the 32 columns -----------------
+  // ---------------- phase 1: partial Gram over this CTA's row chunks --------
   double acc[2][4][4];
 #pragma unroll
   for (int i = 0; i < 2; ++i)
@@ -526,38 +548,43 @@ __global__ void __launch_bounds__(256)
     for (int j = 0; j < 4; ++j)
 #pragma unroll
       for (int v = 0; v < 4; ++v) acc[i][j][v] = 0.0;
-  const int nch = (P.rows_w + JCH - 1) / JCH;
-  jac_load_chunk(Xs[0], P.W, P.ld, P.rows_w, 0, cp, cq, tid);
-  cp_async_commit();
-  for (int ch = 0; ch < nch; ++ch) {
-    if (ch + 1 < nch)
-      jac_load_chunk(Xs[(ch + 1) & 1], P.W, P.ld, P.rows_w, (ch + 1) * JCH, cp, cq, tid);
-    cp_async_commit();
-    cp_async_wait<1>();
-    __syncthreads();
-    const double(*X)[JPITCH] = Xs[ch & 1];
-    const int kb = warp * 8;  // this warp's 8 rows of the chunk
-    double af[2][4], bf[4][2];
+  {
+    const int nch_all = (P.rows_w + JCH - 1) / JCH;
+    const int nmine = (nch_all - rank + JCSZ - 1) / JCSZ;  // chunks rank, rank+JCSZ, ...
+    auto issue = [&](int i) {
+      if (i < nmine)
+        jac_load_chunk(Xs[i % JSTG], P.W, P.ld, P.rows_w, (rank + i * JCSZ) * JCH, cp, cq, tid);
+      cp_async_commit();
+    };
+    for (int s = 0; s < JSTG - 1; ++s) issue(s);
+    for (int i = 0; i < nmine; ++i) {
+      cp_async_wait<JSTG - 2>();
+      __syncthreads();
+      issue(i + JSTG - 1);
+      const double(*X)[JPITCH] = Xs[i % JSTG];
+      const int kb = warp * 8;
+      double af[2][4], bf[4][2];
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      af[i][0] = X[kb + t][i * 16 + g];
-      af[i][1] = X[kb + t][i * 16 + g + 8];
-      af[i][2] = X[kb + t + 4][i * 16 + g];
-      af[i][3] = X[kb + t + 4][i * 16 + g + 8];
+      for (int a = 0; a < 2; ++a) {
+        af[a][0] = X[kb + t][a * 16 + g];
+        af[a][1] = X[kb + t][a * 16 + g + 8];
+        af[a][2] = X[kb + t + 4][a * 16 + g];
+        af[a][3] = X[kb + t + 4][a * 16 + g + 8];
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        bf[j][0] = X[kb + t][j * 8 + g];
+        bf[j][1] = X[kb + t + 4][j * 8 + g];
+      }
+#pragma unroll
+      for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dmma_16x8x8(acc[a][j], af[a], bf[j]);
     }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      bf[j][0] = X[kb + t][j * 8 + g];
-      bf[j][1] = X[kb + t + 4][j * 8 + g];
-    }
-#pragma unroll
-    for (int i = 0; i < 2; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) dmma_16x8x8(acc[i][j], af[i], bf[j]);
+    cp_async_wait<0>();
     __syncthreads();
   }
-  cp_async_wait<0>();
-  // deterministic reduction over the 8 warps
+  // deterministic reduction over the 8 warps into Gpart
   for (int w = 0; w < 8; ++w) {
     if (warp == w) {
 #pragma unroll
@@ -568,54 +595,31 @@ __global__ void __launch_bounds__(256)
           for (int h = 0; h < 2; ++h) {
             const int r = i * 16 + g + h * 8, c = j * 8 + 2 * t;
             if (w == 0) {
-              G[r][c] = acc[i][j][2 * h];
-              G[r][c + 1] = acc[i][j][2 * h + 1];
+              Gpart[r][c] = acc[i][j][2 * h];
+              Gpart[r][c + 1] = acc[i][j][2 * h + 1];
             } else {
-              G[r][c] += acc[i][j][2 * h];
-              G[r][c + 1] += acc[i][j][2 * h + 1];
+              Gpart[r][c] += acc[i][j][2 * h];
+              Gpart[r][c + 1] += acc[i][j][2 * h + 1];
             }
           }
     }
     __syncthreads();
   }
-  // symmetrise (rounding) and measure the largest scaled off-diagonal
-  {
-    double mx = 0.0;
-    for (int idx = tid; idx < JP * JP; idx += 256) {
-      const int r = idx / JP, c = idx % JP;
-      if (r < c) {
-        const double v = 0.5 * (G[r][c] + G[c][r]);
-        const double d = G[r][r] * G[c][c];
-        if (d > 0.0) mx = fmax(mx, fabs(v) / sqrt(d));
-        else if (v != 0.0) mx = 1.0;
-      }
-    }
+  cluster.sync();
+  // full Gram = sum over the cluster (same order everywhere), symmetrised
+  for (int idx = tid; idx < JP * JP; idx += 256) {
+    const int r = idx / JP, c = idx % JP;
+    double s = 0.0;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    if (lane == 0) redmax[warp] = mx;
-    __syncthreads();
-    if (tid == 0) {
-      double m2 = 0.0;
-      for (int w = 0; w < 8; ++w) m2 = fmax(m2, redmax[w]);
-      s_any = (m2 > P.tol) ? 1 : 0;
-      if (s_any) atomicOr(P.flag, 1);
+    for (int q = 0; q < JCSZ; ++q) {
+      const double *gp = cluster.map_shared_rank(&Gpart[0][0], q);
+      s += 0.5 * (gp[r * JP + c] + gp[c * JP + r]);
     }
-    __syncthreads();
-    if (!s_any) return;  // this pair is already orthogonal
-    for (int idx = tid; idx < JP * JP; idx += 256) {
-      const int r = idx / JP, c = idx % JP;
-      if (r < c) {
-        const double v = 0.5 * (G[r][c] + G[c][r]);
-        G[r][c] = v; G[c][r] = v;
-      }
-      Jm[r][c] = (r == c) ? 1.0 : 0.0;
-    }
-    __syncthreads();
+    G[r][c] = s;
+    Jm[r][c] = (r == c) ? 1.0 : 0.0;
   }
-
-  // ---------------- phase 2: J^T G J = diag by cyclic Jacobi ----------------
-  for (int sweep = 0; sweep < 12; ++sweep) {
-    // convergence of the small problem
+  __syncthreads();
+  auto offmax = [&]() -> double {
     double mx = 0.0;
     for (int idx = tid; idx < JP * JP; idx += 256) {
       const int r = idx / JP, c = idx % JP;
@@ -633,44 +637,69 @@ __global__ void __launch_bounds__(256)
     double m2 = 0.0;
     for (int w = 0; w < 8; ++w) m2 = fmax(m2, redmax[w]);
     __syncthreads();
-    if (m2 <= 1e-16) break;
+    return m2;
+  };
+  const double off0 = offmax();
+  // all CTAs of the cluster take the same decision (same G)
+  if (off0 <= P.tol) {
+    cluster.sync();  // peers may still be reading our Gpart
+    return;
+  }
+  if (tid == 0 && rank == 0) atomicOr(P.flag, 1);
+
+  // ---------------- phase 2: J^T G J = diag by cyclic Jacobi ----------------
+  // inner sweeps: stop at round-off, or once this visit has reduced the
+  // pair's off-diagonal mass by 1e-4 (at most 3 sweeps): block Jacobi
+  // converges with inexact inner solves, and near convergence one sweep is
+  // enough to reach round-off (quadratic convergence)
+  for (int sweep = 0; sweep < P.inner_max; ++sweep) {
+    if (sweep > 0) {
+      const double off = offmax();
+      if (off <= 1e-15 || off <= 1e-4 * off0) break;
+    }
     for (int step = 0; step < JP - 1; ++step) {
       if (tid < JB) {
         int p, q;
         rr_pair(tid, step, JP, p, q);
         const double app = G[p][p], aqq = G[q][q], apq = G[p][q];
         double c = 1.0, s = 0.0;
-        if (apq != 0.0 && fabs(apq) > 1e-300) {
-          const double zeta = (aqq - app) / (2.0 * apq);
-          const double tt = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-          c = 1.0 / sqrt(1.0 + tt * tt);
+        if (fabs(apq) > 1e-300) {
+          // t = sgn(z) / (|z| + sqrt(1 + z^2)), z = (aqq - app) / (2 apq),
+          // rearranged to one sqrt + one division + one rsqrt
+          const double a = aqq - app, b = 2.0 * apq;
+          const double tt = copysign(fabs(b), a * b) / (fabs(a) + sqrt(a * a + b * b));
+          c = rsqrt(1.0 + tt * tt);
           s = c * tt;
         }
         rot[tid][0] = c; rot[tid][1] = s;
         rotpq[tid][0] = p; rotpq[tid][1] = q;
       }
       __syncthreads();
-      // columns: G <- G R, J <- J R   with R = [c s; -s c] on (p, q)
-      for (int idx = tid; idx < JB * JP; idx += 256) {
-        const int k = idx / JP, r = idx % JP;
-        const double c = rot[k][0], s = rot[k][1];
-        const int p = rotpq[k][0], q = rotpq[k][1];
-        const double gp = G[r][p], gq = G[r][q];
-        G[r][p] = c * gp - s * gq;
-        G[r][q] = s * gp + c * gq;
-        const double jp = Jm[r][p], jq = Jm[r][q];
-        Jm[r][p] = c * jp - s * jq;
-        Jm[r][q] = s * jp + c * jq;
-      }
-      __syncthreads();
-      // rows: G <- R^T G
-      for (int idx = tid; idx < JB * JP; idx += 256) {
-        const int k = idx / JP, r = idx % JP;
-        const double c = rot[k][0], s = rot[k][1];
-        const int p = rotpq[k][0], q = rotpq[k][1];
-        const double gp = G[p][r], gq = G[q][r];
-        G[p][r] = c * gp - s * gq;
-        G[q][r] = s * gp + c * gq;
+      {
+        // G <- R^T G R, one 2x2 block (pair k1 rows x pair k2 columns) per thread
+        const int k1 = tid >> 4, k2 = tid & 15;
+        const double c1 = rot[k1][0], s1 = rot[k1][1], c2 = rot[k2][0], s2 = rot[k2][1];
+        const int p1 = rotpq[k1][0], q1 = rotpq[k1][1], p2 = rotpq[k2][0], q2 = rotpq[k2][1];
+        const double gpp = G[p1][p2], gpq = G[p1][q2], gqp = G[q1][p2], gqq = G[q1][q2];
+        // columns first
+        const double a0 = c2 * gpp - s2 * gpq, a1 = s2 * gpp + c2 * gpq;
+        const double b0 = c2 * gqp - s2 * gqq, b1 = s2 * gqp + c2 * gqq;
+        // then rows
+        double n00 = c1 * a0 - s1 * b0, n01 = c1 * a1 - s1 * b1;
+        double n10 = s1 * a0 + c1 * b0, n11 = s1 * a1 + c1 * b1;
+        if (k1 == k2) { n01 = 0.0; n10 = 0.0; }  // the annihilated pair
+        G[p1][p2] = n00; G[p1][q2] = n01; G[q1][p2] = n10; G[q1][q2] = n11;
+        // J <- J R : 32 rows x 16 pairs = 2 items per thread
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+          const int idx = tid + 256 * it;
+          const int k = idx & 15, r = idx >> 4;  // 16 distinct column pairs per half-warp
+          const double c = rot[k][0], s = rot[k][1];
+          const int p = rotpq[k][0], q = rotpq[k][1];
+          const double jp = Jm[r][p], jq = Jm[r][q];
+          Jm[r][p] = c * jp - s * jq;
+          Jm[r][q] = s * jp + c * jq;
+        }
       }
       __syncthreads();
     }
@@ -686,81 +715,80 @@ __global__ void __launch_bounds__(256)
     rank_s[tid] = rk;
   }
   __syncthreads();
-  {
-    // permute the columns of J in place through G as scratch
-    for (int idx = tid; idx < JP * JP; idx += 256) {
-      const int r = idx / JP, c = idx % JP;
-      G[r][rank_s[c]] = Jm[r][c];
-    }
-    __syncthreads();
-    for (int idx = tid; idx < JP * JP; idx += 256) {
-      const int r = idx / JP, c = idx % JP;
-      Jm[r][c] = G[r][c];
-    }
-    __syncthreads();
+  for (int idx = tid; idx < JP * JP; idx += 256) {
+    const int r = idx / JP, c = idx % JP;
+    G[r][rank_s[c]] = Jm[r][c];
   }
+  __syncthreads();
+  for (int idx = tid; idx < JP * JP; idx += 256) {
+    const int r = idx / JP, c = idx % JP;
+    Jm[r][c] = G[r][c];
+  }
+  __syncthreads();
 
-  // ---------------- phase 3: apply J to the columns of W and V --------------
-  const int nchw = (P.rows_w + JCH - 1) / JCH;
-  const int nchv = (P.rows_v + JCH - 1) / JCH;
-  const int ntot = nchw + nchv;
-  auto chunk_src = [&](int ch, double *&M, int &rows, int &row0) {
-    if (ch < nchw) { M = P.W; rows = P.rows_w; row0 = ch * JCH; }
-    else { M = P.V; rows = P.rows_v; row0 = (ch - nchw) * JCH; }
-  };
+  // ---------------- phase 3: apply J to this CTA's rows of W and V ----------
   {
-    double *M; int rows, row0;
-    chunk_src(0, M, rows, row0);
-    jac_load_chunk(Xs[0], M, P.ld, rows, row0, cp, cq, tid);
-    cp_async_commit();
-  }
-  const int mt = warp & 3, nh = warp >> 2;  // 16 rows x 16 cols per warp
-  for (int ch = 0; ch < ntot; ++ch) {
-    double *M; int rows, row0;
-    if (ch + 1 < ntot) {
-      chunk_src(ch + 1, M, rows, row0);
-      jac_load_chunk(Xs[(ch + 1) & 1], M, P.ld, rows, row0, cp, cq, tid);
-    }
-    cp_async_commit();
-    cp_async_wait<1>();
-    __syncthreads();
-    chunk_src(ch, M, rows, row0);
-    const double(*X)[JPITCH] = Xs[ch & 1];
-    double c2[2][4];
-#pragma unroll
-    for (int j = 0; j < 2; ++j)
-#pragma unroll
-      for (int v = 0; v < 4; ++v) c2[j][v] = 0.0;
-#pragma unroll
-    for (int kk = 0; kk < JP; kk += 8) {
-      double af[4], bf[2][2];
-      af[0] = X[mt * 16 + g][kk + t];
-      af[1] = X[mt * 16 + g + 8][kk + t];
-      af[2] = X[mt * 16 + g][kk + t + 4];
-      af[3] = X[mt * 16 + g + 8][kk + t + 4];
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        bf[j][0] = Jm[kk + t][nh * 16 + j * 8 + g];
-        bf[j][1] = Jm[kk + t + 4][nh * 16 + j * 8 + g];
+    const int nchw = (P.rows_w + JCH - 1) / JCH, nchv = (P.rows_v + JCH - 1) / JCH;
+    const int ntot = nchw + nchv;
+    const int nmine = (ntot - rank + JCSZ - 1) / JCSZ;
+    auto chunk_src = [&](int i, double *&M, int &rows, int &row0) {
+      const int ch = rank + i * JCSZ;
+      if (ch < nchw) { M = P.W; rows = P.rows_w; row0 = ch * JCH; }
+      else { M = P.V; rows = P.rows_v; row0 = (ch - nchw) * JCH; }
+    };
+    auto issue = [&](int i) {
+      if (i < nmine) {
+        double *M; int rows, row0;
+        chunk_src(i, M, rows, row0);
+        jac_load_chunk(Xs[i % JSTG], M, P.ld, rows, row0, cp, cq, tid);
       }
+      cp_async_commit();
+    };
+    for (int s = 0; s < JSTG - 1; ++s) issue(s);
+    const int mt = warp & 3, nh = warp >> 2;  // 16 rows x 16 cols per warp
+    for (int i = 0; i < nmine; ++i) {
+      cp_async_wait<JSTG - 2>();
+      __syncthreads();
+      issue(i + JSTG - 1);
+      double *M; int rows, row0;
+      chunk_src(i, M, rows, row0);
+      const double(*X)[JPITCH] = Xs[i % JSTG];
+      double c2[2][4];
 #pragma unroll
-      for (int j = 0; j < 2; ++j) dmma_16x8x8(c2[j], af, bf[j]);
-    }
+      for (int j = 0; j < 2; ++j)
 #pragma unroll
-    for (int j = 0; j < 2; ++j)
+        for (int v = 0; v < 4; ++v) c2[j][v] = 0.0;
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int r = row0 + mt * 16 + g + h * 8;
-        const int c = nh * 16 + j * 8 + 2 * t;  // column within the pair
-        if (r < rows) {
-          const int gc = (c < JB) ? (cp + c) : (cq + c - JB);
-          *reinterpret_cast<double2 *>(M + (int64_t)r * P.ld + gc) =
-              make_double2(c2[j][2 * h], c2[j][2 * h + 1]);
+      for (int kk = 0; kk < JP; kk += 8) {
+        double af[4], bf[2][2];
+        af[0] = X[mt * 16 + g][kk + t];
+        af[1] = X[mt * 16 + g + 8][kk + t];
+        af[2] = X[mt * 16 + g][kk + t + 4];
+        af[3] = X[mt * 16 + g + 8][kk + t + 4];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          bf[j][0] = Jm[kk + t][nh * 16 + j * 8 + g];
+          bf[j][1] = Jm[kk + t + 4][nh * 16 + j * 8 + g];
         }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) dmma_16x8x8(c2[j], af, bf[j]);
       }
-    __syncthreads();
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int r = row0 + mt * 16 + g + h * 8;
+          const int c = nh * 16 + j * 8 + 2 * t;  // column within the pair
+          if (r < rows) {
+            const int gc = (c < JB) ? (cp + c) : (cq + c - JB);
+            *reinterpret_cast<double2 *>(M + (int64_t)r * P.ld + gc) =
+                make_double2(c2[j][2 * h], c2[j][2 * h + 1]);
+          }
+        }
+    }
+    cp_async_wait<0>();
   }
-  cp_async_wait<0>();
+  cluster.sync();  // nobody exits while peers may read its shared memory
 }
 
 // column norms of W (rows x ld, first ncols columns)
@@ -801,13 +829,16 @@ __global__ void __launch_bounds__(256)
       const int64_t r = i / nk;
       const int k = (int)(i - r * nk);
       const int c = perm[k];
-      const double sv = s[c];
-      UR[i] = (sv > 0.0) ? W[r * ld + c] / sv : 0.0;
+      // W = R^T was orthogonalised: R = Z S Y^T with Z the accumulated
+      // rotations (-> U_R) and Y the normalised columns of W (-> V)
+      UR[i] = V[r * ld + c];
     } else {
       const int64_t j = i - tot_u;
       const int k = (int)(j / rows_v);
       const int64_t r = j - (int64_t)k * rows_v;
-      VH[j] = V[r * ld + perm[k]];
+      const int c = perm[k];
+      const double sv = s[c];
+      VH[j] = (sv > 0.0) ? W[r * ld + c] / sv : 0.0;
     }
   }
 }
@@ -821,8 +852,9 @@ __global__ void pad_copy_kernel(const double *__restrict__ src, int64_t rows,
        i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / ld_dst, c = i - r * ld_dst;
     double v = 0.0;
-    if (identity) v = (r == c) ? 1.0 : 0.0;
-    else if (r < rows && c < cols) v = src[r * ld_src + c];
+    if (identity == 1) v = (r == c) ? 1.0 : 0.0;
+    else if (r < rows && c < cols)
+      v = (identity == 2) ? src[c * ld_src + r] : src[r * ld_src + c];  // 2: transposed
     dst[i] = v;
   }
 }
@@ -870,11 +902,11 @@ static int svd_tall_f64(int64_t m, int64_t n, const double *X, double *U,
   int rc = qr_f64(m, n, X, Q1, R, /*stabilized=*/0, ws + g.qr_off, st);
   if (rc) return rc;
   const int64_t npad = g.npad;
-  pad_copy_kernel<<<blocks, 256, 0, st>>>(R, n, n, n, W, npad, n, 0);
+  pad_copy_kernel<<<blocks, 256, 0, st>>>(R, n, n, n, W, npad, n, 2);  // W = R^T
   QB_LAUNCH_CHECK();
   pad_copy_kernel<<<blocks, 256, 0, st>>>(nullptr, 0, 0, 0, V, npad, npad, 1);
   QB_LAUNCH_CHECK();
-  constexpr int kJacSmem = 2 * JCH * JPITCH * 8;
+  constexpr int kJacSmem = JSTG * JCH * JPITCH * 8;
   static bool attr_set = false;
   if (!attr_set) {
     QB_CUDA_CHECK(cudaFuncSetAttribute(jacobi_pair_kernel,
@@ -887,13 +919,21 @@ static int svd_tall_f64(int64_t m, int64_t n, const double *X, double *U,
   P.nblk = (int)(npad / JB);
   P.tol = 1e-15 * sqrt((double)n) * 8.0;
   P.flag = flag;
+  {
+    static const int inner = [] { const char *e = getenv("QB_JAC_INNER"); return e ? atoi(e) : 1; }();
+    P.inner_max = inner;
+  }
   int sweeps = 0;
-  const int max_sweeps = 40;
+  const int max_sweeps = 60;
+  const int inner0 = P.inner_max;
   for (; sweeps < max_sweeps; ++sweeps) {
+    // one inner sweep per visit is fastest; fall back to fuller inner solves
+    // if the outer iteration is unusually slow
+    P.inner_max = (sweeps < 25) ? inner0 : std::max(inner0, 4);
     QB_CUDA_CHECK(cudaMemsetAsync(flag, 0, sizeof(int), st));
     for (int r = 0; r < P.nblk - 1; ++r) {
       P.round = r;
-      jacobi_pair_kernel<<<P.nblk / 2, 256, kJacSmem, st>>>(P);
+      jacobi_pair_kernel<<<(P.nblk / 2) * JCSZ, 256, kJacSmem, st>>>(P);
       QB_LAUNCH_CHECK();
     }
     int h = 0;
