@@ -168,6 +168,16 @@ int qb_scale(int dtype, int64_t n, const double alpha[2],
 int qb_dot(int dtype, int64_t n, const void *x, const void *y, void *out,
            void *workspace, void *stream);
 int64_t qb_dot_workspace(int64_t n);
+/* Krylov block algebra (one pass over V each; f64): V is m x n row-major with
+ * leading dimension ldv, m <= 16.
+ *   qb_multi_dot :  out[j] = <V[j], w>            (device out, deterministic)
+ *   qb_multi_axpy:  w += alpha * sum_j h[j] V[j]  (h on the device)
+ * Together: one classical Gram-Schmidt pass of the Lanczos vector w. */
+int qb_multi_dot(int dtype, int m, int64_t n, const void *V, int64_t ldv,
+                 const void *w, void *out, void *workspace, void *stream);
+int64_t qb_multi_dot_workspace(void);
+int qb_multi_axpy(int dtype, int m, int64_t n, const void *V, int64_t ldv,
+                  const void *h, double alpha, void *w, void *stream);
 /* x (rows x cols, row-major contiguous) *= d[col]^p  (side=1) or d[row]^p
  * (side=0); p in {1, 0.5}; d is real (f32 for F32/C64, f64 otherwise) */
 int qb_scale_diag(int dtype, int64_t rows, int64_t cols, void *x,

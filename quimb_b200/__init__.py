@@ -19,7 +19,8 @@ from .array import Array
 from .ops import *  # noqa: F401,F403  (the autoray-visible function surface)
 from .ops import (abs, all, any, max, min, sum)  # noqa: F401,A004
 from . import linalg  # noqa: F401
-from .contract import contract_pair, plan_pair  # noqa: F401
+from .contract import contract_batched, contract_pair, plan_pair  # noqa: F401
+from . import dist  # noqa: F401
 from .tree import (ContractExpression, Tree, array_contract,  # noqa: F401
                    find_tree, gen_output_inds)
 from .mps import (env_left_step, env_right_step, mps_expec, mps_norm,  # noqa: F401

@@ -92,6 +92,9 @@ def load(build_if_missing=True):
     sig("qb_dot", ci, [ci, i64, vp, vp, vp, vp, vp])
     sig("qb_dot_workspace", i64, [i64])
     sig("qb_scale_diag", ci, [ci, i64, i64, vp, vp, ci, ci, vp])
+    sig("qb_multi_dot", ci, [ci, ci, i64, vp, i64, vp, vp, vp, vp])
+    sig("qb_multi_dot_workspace", i64, [])
+    sig("qb_multi_axpy", ci, [ci, ci, i64, vp, i64, vp, ctypes.c_double, vp, vp])
     for name, res, args in (
         ("qb_qr_stab", ci, [ci, i64, i64, vp, vp, vp, ci, vp, ctypes.c_size_t, vp]),
         ("qb_qr_workspace", i64, [ci, i64, i64]),

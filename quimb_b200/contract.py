@@ -98,3 +98,51 @@ def plan_pair(a_shape, a_strides, la, b_shape, b_strides, lb, c_shape,
     keys = ("M", "N", "K", "batch", "n_m", "n_n", "n_k", "n_b", "cfg",
             "splitk", "vecA", "vecB", "vecC", "thrA", "thrB", "degenerate")
     return dict(zip(keys, list(out)))
+
+
+def contract_batched(a_list, la, b_list, lb, lc, conj_a=False, conj_b=False):
+    """Many independent contractions of identical signature in ONE launch
+    (the small same-shape intermediates of MPS / PEPS / circuit sweeps).
+
+    ``a_list[i]``, ``b_list[i]`` must share shape, strides and dtype across
+    ``i``; returns the list of outputs (views of one allocation)."""
+    if len(a_list) != len(b_list) or not a_list:
+        raise ValueError("contract_batched: need equally many a and b operands")
+    a0, b0 = a_list[0], b_list[0]
+    for a, b in zip(a_list, b_list):
+        _lib.require_cuda(a, "a")
+        _lib.require_cuda(b, "b")
+        if (a.shape != a0.shape or a.stride() != a0.stride() or a.dtype != a0.dtype
+                or b.shape != b0.shape or b.stride() != b0.stride() or b.dtype != a0.dtype):
+            raise ValueError("contract_batched: operands must share shape, "
+                             "strides and dtype")
+    lib = _lib.load()
+    ext = {}
+    for t, ls in ((a0, la), (b0, lb)):
+        for l, s in zip(ls, t.shape):
+            ext[l] = s
+    shape = [ext[l] for l in lc]
+    n = len(a_list)
+    out = torch.empty([n] + shape, dtype=a0.dtype, device=a0.device)
+    # representative descriptors carry the weakest pointer alignment
+    def rep_ptr(ts):
+        p = 0
+        for t in ts:
+            p |= t.data_ptr()
+        low = p & 15
+        return ts[0].data_ptr() if low == 0 else (ts[0].data_ptr() | low)
+    da = _lib.desc(a0, rep_ptr(a_list))
+    db = _lib.desc(b0, rep_ptr(b_list))
+    dc = _lib.desc(out[0])
+    ptrs = torch.tensor([[t.data_ptr() for t in a_list],
+                         [t.data_ptr() for t in b_list],
+                         [out[i].data_ptr() for i in range(n)]],
+                        dtype=torch.int64).to(a0.device)
+    rc = lib.qb_contract_batched(da, _lib.labels(la), db, _lib.labels(lb), dc,
+                                 _lib.labels(lc), ptrs[0].data_ptr(),
+                                 ptrs[1].data_ptr(), ptrs[2].data_ptr(), n,
+                                 int(bool(conj_a)), int(bool(conj_b)),
+                                 _lib.stream_ptr())
+    _lib.check(rc, "qb_contract_batched")
+    ptrs.record_stream(torch.cuda.current_stream())
+    return [out[i] for i in range(n)]

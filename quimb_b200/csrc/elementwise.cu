@@ -451,3 +451,106 @@ int qb_scale_diag(int dtype, int64_t rows, int64_t cols, void *x,
 }
 
 }  // extern "C"
+
+// ------------------------------------------------- Lanczos block algebra ----
+// h[j] = <V[j], w>  for j < m  (V is m x n row-major, real fp64), one pass
+// over V and w; deterministic two-stage reduction.
+namespace qb {
+constexpr int MD_MAX = 16;
+constexpr int MD_BLOCKS = 592;
+
+__global__ void __launch_bounds__(256)
+    multi_dot_stage1(int m, int64_t n, const double *__restrict__ V, int64_t ldv,
+                     const double *__restrict__ w, double *__restrict__ part) {
+  double acc[MD_MAX];
+#pragma unroll
+  for (int j = 0; j < MD_MAX; ++j) acc[j] = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const double wi = w[i];
+#pragma unroll
+    for (int j = 0; j < MD_MAX; ++j)
+      if (j < m) acc[j] += V[(int64_t)j * ldv + i] * wi;
+  }
+  __shared__ double sh[8][MD_MAX];
+#pragma unroll
+  for (int j = 0; j < MD_MAX; ++j) {
+    double v = (j < m) ? warp_sum(acc[j]) : 0.0;
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5][j] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < m) {
+    double s = 0.0;
+    for (int wv = 0; wv < 8; ++wv) s += sh[wv][threadIdx.x];
+    part[(int64_t)blockIdx.x * MD_MAX + threadIdx.x] = s;
+  }
+}
+__global__ void __launch_bounds__(256)
+    multi_dot_stage2(int m, int nparts, const double *__restrict__ part,
+                     double *__restrict__ out) {
+  __shared__ double sh[256];
+  for (int j = 0; j < m; ++j) {
+    double a = 0.0;
+    for (int i = threadIdx.x; i < nparts; i += 256) a += part[(int64_t)i * MD_MAX + j];
+    sh[threadIdx.x] = a;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+      if (threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) out[j] = sh[0];
+    __syncthreads();
+  }
+}
+// w[i] += alpha * sum_j h[j] * V[j][i]   (h on the device)
+__global__ void __launch_bounds__(256)
+    multi_axpy_kernel(int m, int64_t n, const double *__restrict__ V, int64_t ldv,
+                      const double *__restrict__ h, double alpha, double *__restrict__ w) {
+  double hj[MD_MAX];
+#pragma unroll
+  for (int j = 0; j < MD_MAX; ++j) hj[j] = (j < m) ? alpha * h[j] : 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    double s = w[i];
+#pragma unroll
+    for (int j = 0; j < MD_MAX; ++j)
+      if (j < m) s += hj[j] * V[(int64_t)j * ldv + i];
+    w[i] = s;
+  }
+}
+}  // namespace qb
+
+extern "C" {
+
+int64_t qb_multi_dot_workspace(void) { return (int64_t)qb::MD_BLOCKS * qb::MD_MAX * 8; }
+
+int qb_multi_dot(int dtype, int m, int64_t n, const void *V, int64_t ldv,
+                 const void *w, void *out, void *workspace, void *stream) {
+  using namespace qb;
+  if (dtype != QB_F64) { set_error("qb_multi_dot: f64 only"); return -1; }
+  if (m < 1 || m > MD_MAX) { set_error("qb_multi_dot: 1 <= m <= %d", MD_MAX); return -2; }
+  if (!workspace) { set_error("qb_multi_dot: workspace required"); return -8; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  multi_dot_stage1<<<MD_BLOCKS, 256, 0, st>>>(m, n, (const double *)V, ldv,
+                                              (const double *)w, (double *)workspace);
+  QB_LAUNCH_CHECK();
+  multi_dot_stage2<<<1, 256, 0, st>>>(m, MD_BLOCKS, (const double *)workspace, (double *)out);
+  QB_LAUNCH_CHECK();
+  return 0;
+}
+
+int qb_multi_axpy(int dtype, int m, int64_t n, const void *V, int64_t ldv,
+                  const void *h, double alpha, void *w, void *stream) {
+  using namespace qb;
+  if (dtype != QB_F64) { set_error("qb_multi_axpy: f64 only"); return -1; }
+  if (m < 1 || m > MD_MAX) { set_error("qb_multi_axpy: 1 <= m <= %d", MD_MAX); return -2; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int64_t b = (n + 255) / 256;
+  if (b > (int64_t)sm_count() * 8) b = (int64_t)sm_count() * 8;
+  multi_axpy_kernel<<<(unsigned)b, 256, 0, st>>>(m, n, (const double *)V, ldv,
+                                                 (const double *)h, alpha, (double *)w);
+  QB_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,101 @@
+"""Multi-GPU sharding of the contraction path.
+
+One process per GPU (torchrun); ``torch.distributed`` (NCCL over NVLink on
+the GPUs, gloo in the CPU tests) is plumbing only.  What shards naturally on
+this path are *independent units with a single exchange at the end*:
+
+  * slices of a contraction tree: cotengra fixes the values of a few indices,
+    every assignment is a complete independent contraction and the results
+    are summed (quimb/tensor/tensor_core.py:255-259).  Units are dealt
+    round-robin to the ranks, summed locally on the device and combined by
+    ONE all-reduce of the (small) output -- no collective on the data path;
+  * independent networks (many MPS norms / amplitudes): pure replicas.
+
+The DMRG chain itself is sequential (each environment depends on the
+previous one, dmrg.py:297-301); it is not sharded in round 1.
+"""
+
+import itertools
+
+import torch
+import torch.distributed as dist
+
+
+def world():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def shard_units(n_units, rank=None, world_size=None):
+    """Round-robin assignment of ``n_units`` independent units."""
+    if rank is None or world_size is None:
+        rank, world_size = world()
+    return list(range(rank, n_units, world_size))
+
+
+def all_reduce_sum(t):
+    """In-place sum over ranks of a torch tensor (no-op without a group)."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t
+
+
+def slice_assignments(sliced_inds, size_dict):
+    """All value assignments of the sliced indices, in a fixed order."""
+    ranges = [range(size_dict[ix]) for ix in sliced_inds]
+    return list(itertools.product(*ranges))
+
+
+def contract_sliced(arrays, inputs, output, sliced_inds, optimize="auto",
+                    contract_fn=None, rank=None, world_size=None, reduce=True):
+    """Slice-parallel contraction: sum over all assignments of ``sliced_inds``
+    of the contraction with those indices fixed; assignments are sharded over
+    the ranks and combined with one all-reduce.
+
+    ``contract_fn(arrays, inputs, output, optimize)`` defaults to the device
+    tree executor; the CPU tests inject a stand-in to exercise the sharding
+    and the collective without a GPU.
+    """
+    if contract_fn is None:
+        from .tree import array_contract as contract_fn
+    inputs = [tuple(t) for t in inputs]
+    sliced = tuple(sliced_inds)
+    if any(ix in output for ix in sliced):
+        raise ValueError("cannot slice an output index")
+    size_dict = {}
+    for t, x in zip(inputs, arrays):
+        for ix, d in zip(t, x.shape):
+            size_dict[ix] = int(d)
+    units = slice_assignments(sliced, size_dict)
+    mine = shard_units(len(units), rank, world_size)
+    red_inputs = [tuple(ix for ix in t if ix not in sliced) for t in inputs]
+    total = None
+    for u in mine:
+        vals = dict(zip(sliced, units[u]))
+        sub = []
+        for t, x in zip(inputs, arrays):
+            idx = tuple(vals[ix] if ix in vals else slice(None) for ix in t)
+            sub.append(x[idx])
+        part = contract_fn(sub, red_inputs, tuple(output), optimize)
+        total = part if total is None else total + part
+    if not reduce:
+        return total, mine
+    return _finish(total, arrays, inputs, output, size_dict), mine
+
+
+def _finish(total, arrays, inputs, output, size_dict):
+    from .array import Array
+    t = total.t if isinstance(total, Array) else total
+    if t is None:
+        # this rank had no unit: contribute zeros of the output shape
+        ref = arrays[0]
+        rt = ref.t if isinstance(ref, Array) else ref
+        shape = [size_dict[ix] for ix in output]
+        t = torch.zeros(shape, dtype=rt.dtype if isinstance(rt, torch.Tensor) else torch.float64,
+                        device=rt.device if isinstance(rt, torch.Tensor) else "cpu")
+    elif not isinstance(t, torch.Tensor):
+        t = torch.as_tensor(t)
+    t = t.contiguous()
+    all_reduce_sum(t)
+    return t

@@ -48,7 +48,8 @@ def get_default_opts():
         "bond_compress_method": "svd",
         "bond_compress_cutoff_mode": "sum2",
         "local_eig_tol": 1e-3,
-        "local_eig_ncv": 4,
+        "local_eig_ncv": 4,          # ARPACK's basis size in parity mode
+        "device_eig_ncv": 16,        # max basis size of the device Lanczos
         "local_eig_backend": None,   # None: device Lanczos; 'SCIPY': parity mode
         "local_eig_maxiter": None,
     }
@@ -66,6 +67,12 @@ class EffHam2:
         self.L, self.W1, self.W2, self.R = Lenv, W1, W2, Renv
         self.dims = tuple(dims)  # (a, s, t, b)
         self.nmatvec = 0
+        # W12[w, s, t, w2, s', t'] = sum_w1 W1[w, w1, s, s'] W2[w1, w2, t, t']:
+        # the two bandwidth-bound MPO steps become one pass over the
+        # (chi, w, d, d, chi) intermediate
+        self.W12 = contract_pair(W1.t, [W_, W1_, S_, SB_], W2.t, [W1_, W2_, T_, TB_],
+                                 [W_, S_, T_, W2_, SB_, TB_], conj_a=W1.cj,
+                                 conj_b=W2.cj)
 
     def matvec(self, v):
         self.nmatvec += 1
@@ -73,14 +80,9 @@ class EffHam2:
         # T1[a', w, s, t, b] = L[a', w, a] x[a, s, t, b]
         T = contract_pair(self.L.t, [LB_, W_, L_], x.t, [L_, S_, T_, R_],
                           [LB_, W_, S_, T_, R_], conj_a=self.L.cj, conj_b=x.cj)
-        # T2[a', t, b, w1, s'] = T1 W1[w, w1, s, s']
-        T = contract_pair(T, [LB_, W_, S_, T_, R_], self.W1.t,
-                          [W_, W1_, S_, SB_], [LB_, SB_, W1_, T_, R_],
-                          conj_b=self.W1.cj)
-        # T3[a', s', t', w2, b] = T2 W2[w1, w2, t, t']
-        T = contract_pair(T, [LB_, SB_, W1_, T_, R_], self.W2.t,
-                          [W1_, W2_, T_, TB_], [LB_, SB_, TB_, W2_, R_],
-                          conj_b=self.W2.cj)
+        # T3[a', s', t', w2, b] = T1[a', w, s, t, b] W12[w, s, t, w2, s', t']
+        T = contract_pair(T, [LB_, W_, S_, T_, R_], self.W12,
+                          [W_, S_, T_, W2_, SB_, TB_], [LB_, SB_, TB_, W2_, R_])
         # y[a', s', t', b'] = T3 R[b', w2, b]
         y = contract_pair(T, [LB_, SB_, TB_, W2_, R_], self.R.t,
                           [RB_, W2_, R_], [LB_, SB_, TB_, RB_], conj_b=self.R.cj)
@@ -200,12 +202,12 @@ class DMRG2:
                                            ncv=self.opts["local_eig_ncv"],
                                            tol=self.opts["local_eig_tol"])
         n = v0.size
-        ncv = self.opts["local_eig_ncv"]
+        ncv = self.opts["device_eig_ncv"]
         tol = self.opts["local_eig_tol"]
         if n < 800:
             # the reference diagonalises small effective Hamiltonians densely
-            # (dmrg.py:690); here: a Krylov space as large as the problem
-            ncv, tol = min(n, 32), 1e-12
+            # (dmrg.py:690); here: the largest Krylov space, tight tolerance
+            ncv, tol = min(n, 16), 1e-12
         return eigh_lanczos(Heff, v0, which=self.which, ncv=ncv, tol=tol,
                             maxiter=self.opts["local_eig_maxiter"],
                             return_info=True)

@@ -7,31 +7,60 @@ and every iteration calls back into ``TNLinearOperator._matvec``.  With a
 device matvec that would cross PCIe twice per iteration, so the whole Krylov
 process lives on the device here:
 
-  * restarted Lanczos with a small basis (``ncv``, like ARPACK's), full
-    re-orthogonalisation by classical Gram-Schmidt applied twice, written as
-    two skinny contractions ``h = V w`` / ``w -= V^T h`` on the pairwise
-    kernel (alpha/beta form);
+  * restarted Lanczos (thick restart with the Ritz vector, whose image H x is
+    known, so a restart costs no matvec), full re-orthogonalisation by
+    classical Gram-Schmidt applied twice, each pass = two fused HBM-bound
+    kernels (``qb_multi_dot`` : h = V w,  ``qb_multi_axpy`` : w -= V^T h);
   * the images ``W_j = H v_j`` are kept, so the projected matrix
-    ``V H V^T`` is one contraction, the Ritz vector's image ``H x`` comes for
-    free and every restart saves one matvec;
+    ``V H V^T`` is one skinny contraction;
   * two small device->host reads per restart cycle (the ncv x ncv projected
     matrix, then the true residual norm |H x - theta x|); the tiny dense
     eigenproblem is host control logic, as in ARPACK.
 
 Convergence test as in ARPACK's dsaupd: ``resid <= tol * max(eps^(2/3),
-|theta|)``.  ``parity mode`` (scipy ARPACK driving the device matvec through
-host copies) is available as ``eigh_arpack_host_driver`` for validation.
+|theta|)``.  The basis size ``ncv`` is a free parameter of the device solver:
+ARPACK's 4 is memory-frugal for host vectors; on a 180 GB device a basis of
+8-16 vectors (32 MiB each at chi = 1024) needs far fewer matvecs.
+``eigh_arpack_host_driver`` is the parity mode (scipy ARPACK on the host
+driving the device matvec).
 """
+
+import ctypes
 
 import numpy as np
 import torch
 
-from . import ops
+from . import _lib, ops
 from .array import Array
 from .contract import contract_pair
 from .linalg import norm as _norm
 
 _J, _N = 0, 1
+_MD_WS = {}
+
+
+def _md_ws(dev):
+    ws = _MD_WS.get(dev.index)
+    if ws is None:
+        ws = torch.empty(_lib.load().qb_multi_dot_workspace(), dtype=torch.uint8,
+                         device=dev)
+        _MD_WS[dev.index] = ws
+    return ws
+
+
+def _orthogonalise(V, j, w, h):
+    """Two classical Gram-Schmidt passes of w against V[0..j] (in place)."""
+    lib = _lib.load()
+    m, n = j + 1, w.numel()
+    st = _lib.stream_ptr()
+    ws = _md_ws(w.device).data_ptr()
+    for _ in range(2):
+        rc = lib.qb_multi_dot(_lib.QB_F64, m, n, V.data_ptr(), V.stride(0),
+                              w.data_ptr(), h.data_ptr(), ws, st)
+        _lib.check(rc, "qb_multi_dot")
+        rc = lib.qb_multi_axpy(_lib.QB_F64, m, n, V.data_ptr(), V.stride(0),
+                               h.data_ptr(), -1.0, w.data_ptr(), st)
+        _lib.check(rc, "qb_multi_axpy")
 
 
 def eigh_lanczos(matvec, v0, which="SA", ncv=4, tol=1e-3, maxiter=None,
@@ -44,21 +73,24 @@ def eigh_lanczos(matvec, v0, which="SA", ncv=4, tol=1e-3, maxiter=None,
         Device matvec on flat contiguous vectors.
     v0 : Array
         Start vector (any shape, flattened).
+    ncv : int
+        Krylov basis size between restarts (2 <= ncv <= 16).
     Returns ``(theta: float, x: Array[n])`` (+ info dict).
     """
     v0 = ops.materialize(ops.asarray(v0)).reshape(-1)
     n = v0.size
     dt = v0.t.dtype
-    if dt.is_complex:
-        raise NotImplementedError("eigh_lanczos: complex operators are not "
-                                  "implemented yet (no fallback)")
+    if dt != torch.float64:
+        raise NotImplementedError(f"eigh_lanczos: dtype {dt} is not implemented "
+                                  "yet (float64 only; no fallback)")
     dev = v0.t.device
-    m = max(2, min(int(ncv), n))
+    m = max(2, min(int(ncv), n, 16))
     if maxiter is None:
-        maxiter = max(10 * n, 300) if n < 30 else 300
+        maxiter = 1000
     V = torch.zeros((m, n), dtype=dt, device=dev)
     W = torch.empty((m, n), dtype=dt, device=dev)
     w = torch.empty((n,), dtype=dt, device=dev)
+    h = torch.empty((16,), dtype=dt, device=dev)
     eps23 = np.finfo(np.float64).eps ** (2.0 / 3.0)
     sign = 1.0 if which in ("SA", "SR") else -1.0
 
@@ -70,33 +102,42 @@ def eigh_lanczos(matvec, v0, which="SA", ncv=4, tol=1e-3, maxiter=None,
     theta, resid = None, None
     info = {"restarts": 0, "converged": False}
     x = Array(V[0])
+    mmax = m
     for cycle in range(maxiter):
-        bnorm = None
+        # adaptive basis: a short first cycle (an already good v0 converges
+        # in ~3 matvecs, like ARPACK's ncv=4), longer ones for hard problems
+        m = min(mmax, 4 << min(cycle, 4))
         for j in range(m):
             if not (j == 0 and have_w0):
                 Wj = matvec(Array(V[j]))
                 nmv += 1
                 W[j].copy_(ops.materialize(Wj).t.reshape(-1))
-            w.copy_(W[j])
-            Vj = V[: j + 1]
-            for _ in range(2):  # CGS2
-                h = contract_pair(Vj, [_J, _N], w, [_N], [_J])
-                contract_pair(Vj, [_J, _N], h, [_J], [_N], out=w, alpha=-1.0,
-                              beta=1.0)
-            bnorm = _norm(Array(w))
             if j + 1 < m:
+                w.copy_(W[j])
+                _orthogonalise(V, j, w, h)
+                bnorm = _norm(Array(w))
                 V[j + 1].copy_(w)
                 ops.scale_(Array(V[j + 1]), 1.0, div_by=bnorm)
         # projected matrix (m x m): host read #1 of the cycle
-        Hm = contract_pair(V, [_J, _N], W, [2, _N], [_J, 2])
+        Hm = contract_pair(V[:m], [_J, _N], W[:m], [2, _N], [_J, 2])
         Hh = Hm.cpu().numpy()
         Hh = 0.5 * (Hh + Hh.T)
         evals, evecs = np.linalg.eigh(sign * Hh)
         theta = sign * evals[0]
         y = evecs[:, 0]
-        yd = torch.as_tensor(y, dtype=dt).to(dev)
-        xnew = contract_pair(V, [_J, _N], yd, [_J], [_N])
-        hx = contract_pair(W, [_J, _N], yd, [_J], [_N])
+        yd = torch.zeros(16, dtype=dt)
+        yd[:m] = torch.as_tensor(y, dtype=dt)
+        yd = yd.to(dev)
+        lib = _lib.load()
+        xnew = torch.zeros((n,), dtype=dt, device=dev)
+        hx = torch.zeros((n,), dtype=dt, device=dev)
+        st = _lib.stream_ptr()
+        _lib.check(lib.qb_multi_axpy(_lib.QB_F64, m, n, V.data_ptr(), V.stride(0),
+                                     yd.data_ptr(), 1.0, xnew.data_ptr(), st),
+                   "qb_multi_axpy")
+        _lib.check(lib.qb_multi_axpy(_lib.QB_F64, m, n, W.data_ptr(), W.stride(0),
+                                     yd.data_ptr(), 1.0, hx.data_ptr(), st),
+                   "qb_multi_axpy")
         # true residual |H x - theta x| (robust to Krylov breakdown):
         # host read #2
         w.copy_(hx)
@@ -118,7 +159,7 @@ def eigh_lanczos(matvec, v0, which="SA", ncv=4, tol=1e-3, maxiter=None,
     # normalise the Ritz vector
     xn = _norm(x)
     x = ops.scale_(ops.materialize(x, force=True), 1.0, div_by=xn)
-    info.update(nmatvec=nmv, resid=resid, theta=theta)
+    info.update(nmatvec=nmv, resid=resid, theta=theta, ncv=mmax)
     if return_info:
         return float(theta), x, info
     return float(theta), x

@@ -227,3 +227,19 @@ def test_tcgen05_engine_badly_scaled_and_accumulate():
     small = qb.contract_pair(qb.asarray(a[:8, :16]).t, [0, 1], qb.asarray(b[:16, :8]).t,
                              [1, 2], [0, 2], engine=2)
     np.testing.assert_allclose(small.cpu().numpy(), a[:8, :16] @ b[:16, :8], rtol=1e-12, atol=1e-6)
+
+
+def test_batched_small_contractions_one_launch():
+    rng = np.random.default_rng(12)
+    n = 37
+    As = [rng.standard_normal((6, 5, 4)) for _ in range(n)]
+    Bs = [rng.standard_normal((4, 5, 7)) for _ in range(n)]
+    ta = [qb.asarray(a).t for a in As]
+    tb = [qb.asarray(b).t for b in Bs]
+    n0 = qb.launch_count()
+    outs = qb.contract_batched(ta, [0, 1, 2], tb, [2, 1, 3], [3, 0])
+    assert qb.launch_count() - n0 == 1
+    for a, b, o in zip(As, Bs, outs):
+        np.testing.assert_allclose(o.cpu().numpy(), np.einsum("abc,cbd->da", a, b), atol=1e-12)
+    with pytest.raises(ValueError):
+        qb.contract_batched(ta, [0, 1, 2], tb[:-1], [2, 1, 3], [3, 0])

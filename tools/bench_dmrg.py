@@ -1,0 +1,94 @@
+"""DMRG2 sweep benchmark (BASELINE configs[2]: Heisenberg chain, chi=1024,
+fp64, two-site SVD).  Not the driver's bench.py contract (that is configs[1]);
+this produces the 'DMRG sweep time' half of the BASELINE metric.
+
+  python tools/bench_dmrg.py [--L 100] [--chi 1024] [--cpu-L 24] [--no-cpu]
+
+GPU: one full `sweep_right(canonize=True, max_bond=chi, cutoff=0)` of
+quimb_b200.DMRG2 on a random MPS (device Lanczos ncv=4 tol=1e-3, Jacobi SVD).
+CPU: the numpy/scipy oracle (the reference's algorithm: ARPACK + LAPACK) on a
+shorter chain that still reaches chi in the middle; both are reported per
+two-site update at full chi so they can be compared like for like.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--L", type=int, default=100)
+    ap.add_argument("--chi", type=int, default=1024)
+    ap.add_argument("--cpu-L", type=int, default=24)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    import torch
+    import quimb_b200 as qb
+    from oracle import dmrg_np as dm
+
+    out = {"L": args.L, "chi": args.chi, "dtype": "f64"}
+    mpo = dm.mpo_heis(args.L)
+    d = qb.DMRG2(mpo, args.chi, cutoffs=0.0, mpo_shape="lrdu", seed=2)
+    torch.cuda.synchronize()
+    site_t = []
+    orig = d._update_local_state_2site
+
+    def timed(i, direction, **kw):
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        r = orig(i, direction, **kw)
+        torch.cuda.synchronize(); site_t.append((i, time.perf_counter() - t0, d.nmatvecs[-1],
+                                                 d._k[i].shape[2]))
+        return r
+    d._update_local_state_2site = timed
+    n0 = qb.launch_count()
+    t0 = time.perf_counter()
+    e = d.sweep_right(canonize=True, max_bond=args.chi, cutoff=0.0, cutoff_mode="sum2")
+    torch.cuda.synchronize()
+    t_sweep = time.perf_counter() - t0
+    full = [t for (i, t, nmv, k) in site_t if k == args.chi]
+    out["gpu"] = {
+        "sweep_s": t_sweep, "energy": e, "launches": qb.launch_count() - n0,
+        "sites": len(site_t), "sites_at_full_chi": len(full),
+        "s_per_site_full_chi": float(np.median(full)) if full else None,
+        "matvecs_per_site": float(np.mean([nmv for (_, _, nmv, _) in site_t])),
+        "update_s_total": float(sum(t for (_, t, _, _) in site_t)),
+    }
+    print(json.dumps(out), flush=True)
+    if not args.no_cpu:
+        Lc = args.cpu_L
+        o = dm.DMRG2(dm.mpo_heis(Lc), args.chi, cutoffs=0.0, seed=2)
+        ts = []
+        orig_o = o._update_2site
+
+        def timed_o(i, direction, max_bond, cutoff):
+            t0 = time.perf_counter()
+            r = orig_o(i, direction, max_bond, cutoff)
+            ts.append((i, time.perf_counter() - t0, o.nmatvecs[-1], o.k[i].shape[2]))
+            return r
+        o._update_2site = timed_o
+        t0 = time.perf_counter()
+        eo = o.sweep("R", canonize=True, max_bond=args.chi, cutoff=0.0)
+        t_cpu = time.perf_counter() - t0
+        fullc = [t for (i, t, nmv, k) in ts if k == args.chi]
+        out["cpu"] = {
+            "L": Lc, "sweep_s": t_cpu, "energy": eo, "cores": os.cpu_count(),
+            "sites_at_full_chi": len(fullc),
+            "s_per_site_full_chi": float(np.median(fullc)) if fullc else None,
+            "matvecs_per_site": float(np.mean([nmv for (_, _, nmv, _) in ts])),
+            "kind": "port (numpy tensordot + scipy ARPACK + LAPACK gesdd)",
+        }
+        if full and fullc:
+            out["speedup_per_site_full_chi"] = out["cpu"]["s_per_site_full_chi"] / out["gpu"]["s_per_site_full_chi"]
+            out["cpu_sweep_extrapolated_s"] = out["cpu"]["s_per_site_full_chi"] * len(site_t)
+    print(json.dumps(out), flush=True)
+    os.makedirs("gpurun_out", exist_ok=True)
+    json.dump(out, open("gpurun_out/bench_dmrg.json", "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()
