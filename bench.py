@@ -107,6 +107,13 @@ def cpu_reference_steps(steps, warmup, target_seconds=12.0):
     """The reference's CPU path (numpy/OpenBLAS tensordot chain) on a bounded
     sample of the same workload: `nsites` bulk chi=1024 sites per step."""
     from oracle import dmrg_np as dm
+    # use every host thread the BLAS will take (torchrun exports
+    # OMP_NUM_THREADS=1, which would otherwise pin the baseline to one core)
+    try:
+        import threadpoolctl
+        threadpoolctl.threadpool_limits(limits=os.cpu_count())
+    except Exception:
+        pass
     rng = np.random.default_rng(0)
     A = rng.standard_normal((CHI, PHYS, CHI))
     A /= np.linalg.norm(A) ** 0.5

@@ -50,11 +50,13 @@ int gemm_f64(const double *A, int64_t a_rs, int64_t a_cs, const double *B,
   if (!splitk_ws) max_splitk = 1;
   int rc = plan_pair(&a, la, &b, lb, &c, lc, 0, 0, plan, -1, max_splitk);
   if (rc) return rc;
+  plan.streamk = 0;  // internal GEMMs use classic launches (small scratch)
   if (plan.p.splitk > 1) {
     if (plan_workspace_bytes(plan) > splitk_ws_elems * 8) {
       // not enough scratch: redo the plan without split-K
       rc = plan_pair(&a, la, &b, lb, &c, lc, 0, 0, plan, -1, 1);
       if (rc) return rc;
+      plan.streamk = 0;
     } else {
       plan.p.partial = splitk_ws;
     }
@@ -212,6 +214,7 @@ int qb_contract_batched(const qb_tensor_t *A0, const int32_t *la,
     return -2;
   }
   // pointer-array batch: no split-K (tiles x count is the parallelism)
+  plan.streamk = 0;
   plan.p.splitk = 1;
   plan.p.k_per_split = cdiv(plan.p.K, 16) * 16;
   plan.p.dA = dA; plan.p.dB = dB; plan.p.dC = dC;

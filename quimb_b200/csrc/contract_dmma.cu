@@ -134,10 +134,20 @@ __device__ __forceinline__ double flip_sign(double v, unsigned mask_hi) {
   return __hiloint2double(__double2hiint(v) ^ (int)mask_hi, __double2loint(v));
 }
 
+// stream-K bookkeeping of one tile segment
+struct SkSeg {
+  int mode;        // 0: classic tile, 1: tail (write partial), 2: head (sum peers)
+  int bid;         // this CTA (partial slot)
+  int peer0, peer1;  // head: CTAs [peer0, peer1) hold the rest of the tile
+  double *part;    // [grid][BM*BN] partial accumulators
+  int *flags;      // [grid]
+};
+
 template <int BM, int BN, int BK, int WARPS_M, int WARPS_N, int STAGES,
           bool CPLX>
-__global__ void __launch_bounds__(WARPS_M *WARPS_N * 32)
-    contract_f64_kernel(const __grid_constant__ ContractParams p) {
+__device__ __forceinline__ void contract_tile(const ContractParams &p, int pid,
+                                              int64_t zb, int ks, int64_t kbeg,
+                                              int64_t kend, const SkSeg sk) {
   using Cfg = KernelCfg<BM, BN, BK, WARPS_M, WARPS_N, STAGES>;
   constexpr int NT = Cfg::NT;
   constexpr int MT = Cfg::MT, NT8 = Cfg::NT8;
@@ -169,7 +179,6 @@ __global__ void __launch_bounds__(WARPS_M *WARPS_N * 32)
     // grouped rasterisation: walk 8 m-tiles down before moving along n so
     // that concurrently resident CTAs share B panels in L2
     const int G = 8;
-    int pid = blockIdx.x;
     int width = G * p.tiles_n;
     int group = pid / width;
     int first_m = group * G;
@@ -178,8 +187,6 @@ __global__ void __launch_bounds__(WARPS_M *WARPS_N * 32)
     tm = first_m + rem % gsz;
     tn = rem / gsz;
   }
-  const int64_t zb = blockIdx.y;   // batch
-  const int ks = blockIdx.z;       // k-split
   const int64_t m0 = (int64_t)tm * BM, n0 = (int64_t)tn * BN;
 
   const double *A = static_cast<const double *>(p.A);
@@ -226,8 +233,6 @@ __global__ void __launch_bounds__(WARPS_M *WARPS_N * 32)
     else offBn[i] = ob;
     offCn[i] = oc;
   }
-  const int64_t kbeg = (int64_t)ks * p.k_per_split;  // in real-k units
-  const int64_t kend = min(Kh, kbeg + p.k_per_split);
   const int nkb = (int)((kend - kbeg + BK - 1) / BK);
 
   auto fill_ktab = [&](int kb) {
@@ -340,6 +345,39 @@ __global__ void __launch_bounds__(WARPS_M *WARPS_N * 32)
   }
   cp_async_wait<0>();
 
+  // ---- stream-K: tail segments park their accumulators, heads collect ----
+  if (sk.mode == 1) {
+    double *dst = sk.part + (size_t)sk.bid * (BM * BN);
+#pragma unroll
+    for (int i = 0; i < MT; ++i)
+#pragma unroll
+      for (int j = 0; j < NT8; ++j)
+#pragma unroll
+        for (int v = 0; v < 4; ++v)
+          __stcg(&dst[((i * NT8 + j) * 4 + v) * NT + tid], acc[i][j][v]);
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) atomicExch(&sk.flags[sk.bid], 1);
+    return;
+  }
+  if (sk.mode == 2) {
+    for (int c = sk.peer0; c < sk.peer1; ++c) {
+      if (tid == 0) {
+        while (atomicAdd(&sk.flags[c], 0) == 0) __nanosleep(100);
+      }
+      __syncthreads();
+      __threadfence();
+      const double *src = sk.part + (size_t)c * (BM * BN);
+#pragma unroll
+      for (int i = 0; i < MT; ++i)
+#pragma unroll
+        for (int j = 0; j < NT8; ++j)
+#pragma unroll
+          for (int v = 0; v < 4; ++v)
+            acc[i][j][v] += __ldcg(&src[((i * NT8 + j) * 4 + v) * NT + tid]);
+    }
+  }
+
   // ---- epilogue ----------------------------------------------------------
   if (p.splitk > 1) {
     // canonical [split][batch][M][Nh] partial buffer
@@ -395,6 +433,58 @@ __global__ void __launch_bounds__(WARPS_M *WARPS_N * 32)
         }
       }
     }
+}
+
+template <int BM, int BN, int BK, int WARPS_M, int WARPS_N, int STAGES,
+          bool CPLX>
+__global__ void __launch_bounds__(WARPS_M *WARPS_N * 32)
+    contract_f64_kernel(const __grid_constant__ ContractParams p) {
+  const int64_t Kh = CPLX ? 2 * p.K : p.K;
+  const int ks = blockIdx.z;
+  const int64_t kbeg = (int64_t)ks * p.k_per_split;  // in real-k units
+  const int64_t kend = min(Kh, kbeg + p.k_per_split);
+  SkSeg sk{0, 0, 0, 0, nullptr, nullptr};
+  contract_tile<BM, BN, BK, WARPS_M, WARPS_N, STAGES, CPLX>(p, blockIdx.x, blockIdx.y, ks,
+                                                           kbeg, kend, sk);
+}
+
+// Stream-K: one persistent CTA per SM; the (tile, k-block) iteration space is
+// cut into gridDim.x equal contiguous ranges, so every SM gets the same number
+// of k-blocks whatever the tile count (no wave quantisation).  A range that
+// starts inside a tile is a TAIL: its accumulators go to a per-CTA slot of the
+// workspace; the CTA whose range holds the first k-block of that tile (the
+// HEAD, processed last in its range, i.e. long after the tails were written)
+// adds them in a fixed order and runs the normal epilogue.
+template <int BM, int BN, int BK, int WARPS_M, int WARPS_N, int STAGES,
+          bool CPLX>
+__global__ void __launch_bounds__(WARPS_M *WARPS_N * 32)
+    contract_f64_streamk_kernel(const __grid_constant__ ContractParams p) {
+  const int64_t Kh = CPLX ? 2 * p.K : p.K;
+  const int64_t nkbT = (Kh + BK - 1) / BK;
+  const int64_t tiles = (int64_t)p.tiles_m * p.tiles_n;
+  const int64_t total = tiles * nkbT;
+  const int G = gridDim.x, bid = blockIdx.x;
+  const int64_t u0 = total * bid / G, u1 = total * (bid + 1) / G;
+  double *part = p.partial;
+  int *flags = reinterpret_cast<int *>(p.partial + (size_t)G * (BM * BN));
+  for (int64_t u = u0; u < u1;) {
+    const int64_t tile = u / nkbT, kb0 = u - tile * nkbT;
+    const int64_t kb1 = min(nkbT, kb0 + (u1 - u));
+    SkSeg sk{0, bid, 0, 0, part, flags};
+    if (kb0 > 0) sk.mode = 1;
+    else if (kb1 < nkbT) {
+      // peers: CTAs after this one whose range starts inside this tile
+      sk.mode = 2;
+      sk.peer0 = bid + 1;
+      int c = bid + 1;
+      while (c < G && total * c / G < (tile + 1) * nkbT) ++c;
+      sk.peer1 = c;
+    }
+    contract_tile<BM, BN, BK, WARPS_M, WARPS_N, STAGES, CPLX>(
+        p, (int)tile, 0, 0, kb0 * BK, min(Kh, kb1 * BK), sk);
+    u += kb1 - kb0;
+    __syncthreads();  // shared memory is reused by the next segment
+  }
 }
 
 // deterministic split-K reduction + strided scatter into C
@@ -455,8 +545,27 @@ static int launch_cfg(const ContractParams &p, cudaStream_t st) {
 }
 
 template <bool CPLX>
+static int launch_streamk(const PairPlan &plan, cudaStream_t st) {
+  using Cfg = KernelCfg<128, 128, 16, 2, 4, 4>;
+  auto kern = contract_f64_streamk_kernel<128, 128, 16, 2, 4, 4, CPLX>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    QB_CUDA_CHECK(cudaFuncSetAttribute(
+        kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+    attr_set = true;
+  }
+  const int G = plan.streamk;
+  int *flags = reinterpret_cast<int *>(plan.p.partial + (size_t)G * (128 * 128));
+  QB_CUDA_CHECK(cudaMemsetAsync(flags, 0, sizeof(int) * G, st));
+  kern<<<G, Cfg::NT, Cfg::SMEM, st>>>(plan.p);
+  QB_LAUNCH_CHECK();
+  return 0;
+}
+
+template <bool CPLX>
 static int launch_contract_t(const PairPlan &plan, cudaStream_t st) {
   const ContractParams &p = plan.p;
+  if (plan.streamk > 0 && p.partial) return launch_streamk<CPLX>(plan, st);
   int rc;
   switch (plan.cfg) {
     case 0: rc = launch_cfg<128, 128, 16, 2, 4, 4, CPLX>(p, st); break;

@@ -8,6 +8,7 @@
 // reproduced bit-exactly because C is addressed through its own strides.
 #pragma once
 #include <stdint.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <vector>
@@ -55,6 +56,7 @@ struct PairPlan {
   ContractParams p;
   int dtype;
   int cfg;           // tile configuration id
+  int streamk;       // >0: persistent stream-K launch with this many CTAs
   bool empty_out;    // output has zero elements
   bool zero_fill;    // contracted extent is zero -> C = 0
   int64_t out_elems;
@@ -342,10 +344,31 @@ inline int plan_pair(const qb_tensor_t *A, const int32_t *la,
   p.tiles_n = (int32_t)cdiv(N, tc.bn);
   p.splitk = best_split;
   p.k_per_split = best_kper;
+  // stream-K (large tile only): when the tile count leaves SMs idle in the
+  // last wave, cut the (tile, k-block) space into one equal range per SM
+  plan.streamk = 0;
+  {
+    static const int sk_env = [] {
+      const char *e = getenv("QB_STREAMK");
+      return e ? atoi(e) : 1;
+    }();
+    const int G = 148;
+    const int64_t tiles = (int64_t)p.tiles_m * p.tiles_n;
+    const int64_t kblocks = cdiv(Kh, tc.bk);
+    const double eff = (double)(tiles * p.splitk) / (double)(cdiv(tiles * p.splitk, G) * G);
+    if (sk_env && cfg == 0 && p.nbatch == 1 && tiles >= 32 && tiles * kblocks >= 8LL * G &&
+        (eff < 0.93 || p.splitk > 1)) {
+      plan.streamk = G;
+      p.splitk = 1;
+      p.k_per_split = kblocks * tc.bk;
+    }
+  }
   return 0;
 }
 
 inline int64_t plan_workspace_bytes(const PairPlan &plan) {
+  if (plan.streamk > 0)
+    return (int64_t)plan.streamk * (128 * 128 * 8 + 64);  // partial tiles + flags
   if (plan.p.splitk <= 1) return 0;
   return (int64_t)plan.p.splitk * plan.p.nbatch * plan.p.M * plan.p.N * 8 *
          (dtype_is_complex(plan.dtype) ? 2 : 1);
