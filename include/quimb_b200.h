@@ -183,6 +183,12 @@ int qb_multi_axpy(int dtype, int m, int64_t n, const void *V, int64_t ldv,
 int qb_scale_diag(int dtype, int64_t rows, int64_t cols, void *x,
                   const void *d, int side, int sqrt_d, void *stream);
 
+/* contiguous precision conversion f32<->f64, c64<->c128 (n elements).  f32 /
+ * c64 operands are widened (exactly) for the fp64 engines and the result is
+ * rounded once. */
+int qb_convert(int src_dtype, int dst_dtype, int64_t n, const void *src,
+               void *dst, void *stream);
+
 /* ---- decompositions ---------------------------------------------------- */
 /*
  * Stabilised thin QR of a row-major contiguous m x n matrix X (m >= n):

@@ -26,6 +26,27 @@ def _workspace(nbytes, device):
     return buf
 
 
+_WIDE = {torch.float32: torch.float64, torch.complex64: torch.complex128}
+
+
+def convert(t, dtype):
+    """Contiguous copy of ``t`` in another precision through ``qb_convert``
+    (strided inputs are first materialised by the permute kernel)."""
+    _lib.require_cuda(t)
+    if t.dtype == dtype:
+        return t
+    if not t.is_contiguous():
+        src = torch.empty(t.shape, dtype=t.dtype, device=t.device)
+        rc = _lib.load().qb_permute(_lib.desc(t), _lib.desc(src), 0, _lib.stream_ptr())
+        _lib.check(rc, "qb_permute")
+        t = src
+    out = torch.empty(t.shape, dtype=dtype, device=t.device)
+    rc = _lib.load().qb_convert(_lib.qb_dtype(t.dtype), _lib.qb_dtype(dtype), t.numel(),
+                                t.data_ptr(), out.data_ptr(), _lib.stream_ptr())
+    _lib.check(rc, "qb_convert")
+    return out
+
+
 def contract_pair(a, la, b, lb, lc, conj_a=False, conj_b=False, out=None,
                   engine=0, alpha=1.0, beta=0.0):
     """``out[lc] = sum op(a)[la] * op(b)[lb]`` with integer mode labels.
@@ -47,6 +68,19 @@ def contract_pair(a, la, b, lb, lc, conj_a=False, conj_b=False, out=None,
         raise TypeError(f"dtype mismatch: {a.dtype} vs {b.dtype}")
     if len(la) != a.dim() or len(lb) != b.dim():
         raise ValueError("label count does not match operand rank")
+    if a.dtype in _WIDE:
+        # single precision: widen exactly, contract in fp64, round once
+        wide = _WIDE[a.dtype]
+        wout = None if out is None else convert(out, wide)
+        res = contract_pair(convert(a, wide), la, convert(b, wide), lb, lc, conj_a,
+                            conj_b, wout, engine, alpha, beta)
+        narrow = convert(res, a.dtype)
+        if out is not None:
+            rc = _lib.load().qb_permute(_lib.desc(narrow), _lib.desc(out), 0,
+                                        _lib.stream_ptr())
+            _lib.check(rc, "qb_permute")
+            return out
+        return narrow
     lib = _lib.load()
     ext = {}
     for t, ls in ((a, la), (b, lb)):

@@ -19,6 +19,7 @@ SOURCES = [
     "linalg.cu",
     "ozaki_tc.cu",
     "microbench.cu",
+    "convert.cu",
 ]
 HEADERS = ["common.cuh", "plan.h", "../../include/quimb_b200.h"]
 LIB = os.path.join(HERE, "libquimb_b200.so")

@@ -24,6 +24,24 @@ def _workspace(nbytes, device):
     return buf
 
 
+def _narrow(fn):
+    """float32 input: widen exactly, factor in fp64, round the factors once
+    (dtype is preserved end to end, as the reference does)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(x, *args, **kwargs):
+        x = ops.asarray(x)
+        if x.t.dtype != torch.float32:
+            return fn(x, *args, **kwargs)
+        from .contract import convert
+        wide = Array(convert(ops.materialize(x).t, torch.float64))
+        outs = fn(wide, *args, **kwargs)
+        return tuple(Array(convert(o.t, torch.float32)) if isinstance(o, Array) else o
+                     for o in outs)
+    return wrapped
+
+
 def _as_matrix(x):
     x = ops.materialize(ops.asarray(x))
     if x.ndim != 2:
@@ -37,6 +55,7 @@ def _as_matrix(x):
     return x
 
 
+@_narrow
 def qr(x, stabilized=False, want_q=True, want_r=True):
     """Thin QR of a 2-d device array: Q (m, k), R (k, n), k = min(m, n).
     ``stabilized`` makes diag(R) >= 0 (quimb's qr_stabilized convention)."""
@@ -66,6 +85,7 @@ def qr(x, stabilized=False, want_q=True, want_r=True):
     return (Array(Q) if want_q else None), (Array(R) if want_r else None)
 
 
+@_narrow
 def svd(x, full_matrices=False, return_sweeps=False):
     """Thin SVD: U (m, k), s (k,) descending, VH (k, n)."""
     if full_matrices:
@@ -109,9 +129,11 @@ def eigh(x):
     """Small dense symmetric eigenproblems (Lanczos tridiagonals, DMRG's
     dense-Heff branch for prod(dims) < 800) are host-side control logic in
     the reference too (dmrg.py:690); they are solved on the host."""
+    if x.shape[0] > 64:
+        raise NotImplementedError(
+            "quimb_b200.linalg.eigh: only the tiny projected (Krylov) problems "
+            "are solved here; for operators use eigh_lanczos (no dense device "
+            "eigh yet, and no CPU fallback)")
     a = ops.to_numpy(x)
-    if a.shape[0] > 4096:
-        raise NotImplementedError("quimb_b200.linalg.eigh: large dense eigh "
-                                  "is not on the hot path; use eigh_lanczos")
     w, v = np.linalg.eigh(a)
     return ops.asarray(w), ops.asarray(v)

@@ -243,3 +243,21 @@ def test_batched_small_contractions_one_launch():
         np.testing.assert_allclose(o.cpu().numpy(), np.einsum("abc,cbd->da", a, b), atol=1e-12)
     with pytest.raises(ValueError):
         qb.contract_batched(ta, [0, 1, 2], tb[:-1], [2, 1, 3], [3, 0])
+
+
+@pytest.mark.parametrize("dtype,tol", [("float32", 2e-6), ("complex64", 2e-6)])
+def test_single_precision_dtype_preserved(dtype, tol):
+    """f32 / c64 in -> same dtype out (reference: test_dmrg.py:290-300 dtype
+    preservation), values at fp32 accuracy of the fp32 numpy result."""
+    rng = np.random.default_rng(3)
+    a = _rand(rng, (24, 18, 10), dtype); b = _rand(rng, (10, 18, 7), dtype)
+    out = qb.einsum("abc,cbd->ad", qb.asarray(a), qb.asarray(b))
+    assert out.dtype == np.dtype(dtype)
+    ref = np.einsum("abc,cbd->ad", a.astype(np.result_type(dtype, np.float64)),
+                    b.astype(np.result_type(dtype, np.float64)))
+    assert np.max(np.abs(out.to_numpy() - ref)) <= tol * np.max(np.abs(ref))
+    # views + conj
+    out2 = qb.tensordot(qb.asarray(a).transpose(2, 1, 0).conj(), qb.asarray(b), axes=((0, 1), (0, 1)))
+    ref2 = np.tensordot(a.transpose(2, 1, 0).conj(), b, axes=((0, 1), (0, 1)))
+    assert out2.dtype == np.dtype(dtype)
+    assert np.max(np.abs(out2.to_numpy() - ref2)) <= 10 * tol * np.max(np.abs(ref2))

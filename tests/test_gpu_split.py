@@ -156,3 +156,16 @@ def test_dmrg_size_split_properties():
     sref = np.linalg.svd(x, compute_uv=False)
     assert info["error"] == pytest.approx(np.sqrt(np.sum(sref[chi:] ** 2)), rel=1e-10)
     assert np.linalg.norm(l @ r - x) == pytest.approx(info["error"], rel=1e-9)
+
+
+def test_float32_split_preserves_dtype():
+    rng = np.random.default_rng(4)
+    x = rng.standard_normal((40, 24)).astype(np.float32)
+    left, _, right = qb.svd_truncated(qb.asarray(x), cutoff=0.0, max_bond=10, absorb=0)
+    assert left.dtype == np.float32 and right.dtype == np.float32
+    s = np.linalg.svd(x.astype(np.float64), compute_uv=False)
+    err = np.linalg.norm(left.to_numpy().astype(np.float64) @ right.to_numpy().astype(np.float64) - x)
+    assert err == pytest.approx(np.sqrt(np.sum(s[10:] ** 2)), rel=1e-4)
+    Q, _, R = qb.qr_stabilized(qb.asarray(x))
+    assert Q.dtype == np.float32
+    np.testing.assert_allclose(Q.to_numpy() @ R.to_numpy(), x, atol=1e-5)
