@@ -312,10 +312,26 @@ def main():
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
+    # DRAM traffic per launch of the dominant kernel from the committed ncu
+    # --set full capture (profiles/): mean of dram read + write over its launches
+    traffic = None
+    try:
+        rd = wr = None
+        for ln in open(os.path.join(ROOT, "profiles", "r01_contract_kernel_ncu_full.txt")):
+            if ln.startswith("dram__bytes_read.sum [Mbyte]"):
+                rd = [float(x) * 1e6 for x in ln.split(":", 1)[1].split("|")]
+            if ln.startswith("dram__bytes_write.sum [Kbyte]"):
+                wr = [float(x) * 1e3 for x in ln.split(":", 1)[1].split("|")]
+        if rd and wr:
+            traffic = float(np.mean(rd) + np.mean(wr))
+    except Exception:
+        pass
     roofline = {
         "bound": "tensor", "achieved": achieved, "peak": tf.value, "unit": "TFLOP/s",
-        "frac": achieved / tf.value if tf.value else None, "traffic": None,
-        "kernel": "contract_f64_kernel<128,128,16> (DMMA fp64)",
+        "frac": achieved / tf.value if tf.value else None, "traffic": traffic,
+        "traffic_source": "profiles/r01_contract_kernel_ncu_full.txt (bytes per launch; "
+                          "algorithmic 33.5e6)",
+        "kernel": "contract_f64_streamk_kernel<128,128,16> (DMMA fp64, persistent stream-K)",
         "peak_source": "fp64 DMMA issue-rate microbenchmark measured live on this GPU "
                        "(tcgen05 has no f64 kind; MEASURED_PEAKS.json holds bf16 only)",
         "flops_per_launch": k_fl, "ms_per_launch": k_ms,
