@@ -70,6 +70,10 @@ def contract_sliced(arrays, inputs, output, sliced_inds, optimize="auto",
     units = slice_assignments(sliced, size_dict)
     mine = shard_units(len(units), rank, world_size)
     red_inputs = [tuple(ix for ix in t if ix not in sliced) for t in inputs]
+    if contract_fn.__module__.endswith("tree") and isinstance(optimize, (str, type(None))):
+        # every slice has the same structure: find the tree once
+        from .tree import find_tree
+        optimize = find_tree(red_inputs, tuple(output), size_dict, optimize)
     total = None
     for u in mine:
         vals = dict(zip(sliced, units[u]))

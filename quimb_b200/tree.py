@@ -109,29 +109,60 @@ def linear_to_ssa(path, n):
 
 # ---------------------------------------------------------------- finders ---
 def _greedy_ssa(inputs, output, size_dict):
-    """Greedy: repeatedly contract the pair (sharing an index if any exists)
-    that minimises size(result) - size(a) - size(b)."""
+    """Greedy: repeatedly contract the pair sharing an index that minimises
+    size(result) - size(a) - size(b) (opt_einsum's heuristic); disconnected
+    components are joined by outer products at the end.  Candidates are
+    generated from an index -> tensors map, so the cost per step is
+    proportional to the number of neighbouring pairs, not all pairs."""
     inds = {i: tuple(t) for i, t in enumerate(inputs)}
+    where = {}
+    for i, t in inds.items():
+        for ix in set(t):
+            where.setdefault(ix, set()).add(i)
+    out_set = set(output)
     sz = lambda t: math.prod(size_dict[ix] for ix in t)  # noqa: E731
+
+    def result(a, b):
+        sa, sb = set(inds[a]), set(inds[b])
+        keep = []
+        for ix in dict.fromkeys(inds[a] + inds[b]):
+            # needed later if it is an output or lives on a third tensor
+            if ix in out_set or (where[ix] - {a, b}):
+                keep.append(ix)
+        return tuple(keep), sa | sb
+
     ssa, nxt = [], len(inputs)
     while len(inds) > 1:
-        keys = list(inds)
+        cands = set()
+        for ix, ts in where.items():
+            if len(ts) >= 2:
+                tl = sorted(ts)
+                for x in range(len(tl)):
+                    for y in range(x + 1, len(tl)):
+                        cands.add((tl[x], tl[y]))
         best = None
-        for a, b in itertools.combinations(keys, 2):
-            sa, sb = set(inds[a]), set(inds[b])
-            need = set(output)
-            for c in keys:
-                if c != a and c != b:
-                    need.update(inds[c])
-            res = tuple(ix for ix in dict.fromkeys(inds[a] + inds[b]) if ix in need)
-            key = (0 if sa & sb else 1, sz(res) - sz(inds[a]) - sz(inds[b]),
-                   math.prod(size_dict[ix] for ix in sa | sb))
-            if best is None or key < best[0]:
-                best = (key, a, b, res)
+        if cands:
+            for a, b in cands:
+                res, union = result(a, b)
+                key = (sz(res) - sz(inds[a]) - sz(inds[b]),
+                       math.prod(size_dict[ix] for ix in union), a, b)
+                if best is None or key < best[0]:
+                    best = (key, a, b, res)
+        else:
+            # no shared indices left: outer product of the two smallest
+            ks = sorted(inds, key=lambda k: (sz(inds[k]), k))[:2]
+            a, b = ks
+            res, _ = result(a, b)
+            best = (None, a, b, res)
         _, a, b, res = best
         ssa.append((a, b))
-        del inds[a], inds[b]
+        for k in (a, b):
+            for ix in set(inds[k]):
+                where[ix].discard(k)
+            del inds[k]
         inds[nxt] = res
+        for ix in set(res):
+            where.setdefault(ix, set()).add(nxt)
         nxt += 1
     return ssa
 
