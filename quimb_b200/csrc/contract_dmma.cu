@@ -546,8 +546,8 @@ static int launch_cfg(const ContractParams &p, cudaStream_t st) {
 
 template <bool CPLX>
 static int launch_streamk(const PairPlan &plan, cudaStream_t st) {
-  using Cfg = KernelCfg<128, 128, 16, 2, 4, 4>;
-  auto kern = contract_f64_streamk_kernel<128, 128, 16, 2, 4, 4, CPLX>;
+  using Cfg = KernelCfg<128, 128, 16, 4, 4, 4>;
+  auto kern = contract_f64_streamk_kernel<128, 128, 16, 4, 4, 4, CPLX>;
   static bool attr_set = false;
   if (!attr_set) {
     QB_CUDA_CHECK(cudaFuncSetAttribute(
@@ -568,7 +568,7 @@ static int launch_contract_t(const PairPlan &plan, cudaStream_t st) {
   if (plan.streamk > 0 && p.partial) return launch_streamk<CPLX>(plan, st);
   int rc;
   switch (plan.cfg) {
-    case 0: rc = launch_cfg<128, 128, 16, 2, 4, 4, CPLX>(p, st); break;
+    case 0: rc = launch_cfg<128, 128, 16, 4, 4, 4, CPLX>(p, st); break;
     case 1: rc = launch_cfg<64, 64, 16, 2, 2, 4, CPLX>(p, st); break;
     case 2: rc = launch_cfg<128, 32, 16, 4, 1, 4, CPLX>(p, st); break;
     case 3: rc = launch_cfg<32, 128, 16, 1, 4, 4, CPLX>(p, st); break;
