@@ -88,26 +88,49 @@ def find_path(inputs, output, size_dict, optimize="auto"):
 
 
 def _path_greedy(inputs, output, size_dict):
-    terms = [tuple(t) for t in inputs]
+    """opt_einsum-style greedy: among pairs sharing an index take the one
+    minimising size(out) - size(a) - size(b); outer products only when no
+    connected pair is left.  Candidate pairs come from an index -> terms map."""
+    terms = {i: tuple(t) for i, t in enumerate(inputs)}
+    order = list(range(len(inputs)))          # current positions (linear path)
+    where = {}
+    for i, t in terms.items():
+        for ix in set(t):
+            where.setdefault(ix, set()).add(i)
+    out_set = set(output)
+    nxt = len(inputs)
     path = []
     while len(terms) > 1:
+        cands = set()
+        for ix, ts in where.items():
+            if len(ts) >= 2:
+                tl = sorted(ts)
+                for x in range(len(tl)):
+                    for y in range(x + 1, len(tl)):
+                        cands.add((tl[x], tl[y]))
+        if not cands:
+            ks = sorted(terms, key=lambda k: (_size(terms[k], size_dict), k))[:2]
+            cands = {(min(ks), max(ks))}
         best = None
-        for i, j in itertools.combinations(range(len(terms)), 2):
-            shared = set(terms[i]) & set(terms[j])
-            need = _needed_elsewhere(terms, (i, j), output)
-            res = _pair_result(terms[i], terms[j], need)
-            score = (
-                _size(res, size_dict)
-                - _size(terms[i], size_dict)
-                - _size(terms[j], size_dict)
-            )
-            # never prefer outer products over real contractions
-            key = (0 if shared else 1, score, _flops(terms[i], terms[j], size_dict))
+        for i, j in cands:
+            res = tuple(ix for ix in dict.fromkeys(terms[i] + terms[j])
+                        if ix in out_set or (where[ix] - {i, j}))
+            key = (_size(res, size_dict) - _size(terms[i], size_dict) - _size(terms[j], size_dict),
+                   _flops(terms[i], terms[j], size_dict), i, j)
             if best is None or key < best[0]:
                 best = (key, i, j, res)
         _, i, j, res = best
-        path.append((i, j))
-        terms = [t for k, t in enumerate(terms) if k not in (i, j)] + [res]
+        pi, pj = order.index(i), order.index(j)
+        path.append((min(pi, pj), max(pi, pj)))
+        order = [k for k in order if k not in (i, j)] + [nxt]
+        for k in (i, j):
+            for ix in set(terms[k]):
+                where[ix].discard(k)
+            del terms[k]
+        terms[nxt] = res
+        for ix in set(res):
+            where.setdefault(ix, set()).add(nxt)
+        nxt += 1
     return path
 
 

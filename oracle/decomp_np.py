@@ -307,3 +307,45 @@ def tensor_split(x, inds, left_inds, right_inds=None, method="auto",
     if right is not None:
         right = right.reshape(-1, *rdims)
     return left, s, right
+
+
+# ---- bond canonisation / compression (array level) -------------------------
+def tensor_canonize_bond(a, a_inds, b, b_inds, absorb="right"):
+    """tensor_core.py:671-824: QR ``a`` over the bond it shares with ``b`` and
+    absorb R into ``b`` (absorb='right'); LQ of ``b`` for absorb='left'.
+    Index orders of both outputs are those of the inputs."""
+    a_inds, b_inds = tuple(a_inds), tuple(b_inds)
+    (bond,) = [ix for ix in a_inds if ix in b_inds]
+    if absorb == "left":
+        nb, na = tensor_canonize_bond(b, b_inds, a, a_inds, "right")
+        return na, nb
+    lix = tuple(ix for ix in a_inds if ix != bond)
+    q, _, r = tensor_split(a, a_inds, lix, (bond,), method="qr")
+    # q: (*lix, k), r: (k, bond)
+    new_a = np.transpose(q, [(lix + (bond,)).index(ix) for ix in a_inds])
+    nb = np.tensordot(r, b, axes=(1, b_inds.index(bond)))      # (k, rest of b...)
+    rest = tuple(ix for ix in b_inds if ix != bond)
+    new_b = np.transpose(nb, [((bond,) + rest).index(ix) for ix in b_inds])
+    return new_a, new_b
+
+
+def tensor_compress_bond(a, a_inds, b, b_inds, max_bond=None, cutoff=1e-10,
+                         cutoff_mode="rel", absorb="both", renorm=None, info=None):
+    """tensor_core.py:864-1094, ``reduced=True`` branch: QR(a) / LQ(b), SVD of
+    the reduced core Ra Rb with truncation, factors folded back.  Output index
+    orders equal the input ones."""
+    a_inds, b_inds = tuple(a_inds), tuple(b_inds)
+    (bond,) = [ix for ix in a_inds if ix in b_inds]
+    lix = tuple(ix for ix in a_inds if ix != bond)
+    rix = tuple(ix for ix in b_inds if ix != bond)
+    qa, _, ra = tensor_split(a, a_inds, lix, (bond,), method="qr")            # (*lix,k1),(k1,bond)
+    lb, _, qb = tensor_split(b, b_inds, (bond,), rix, method="lq")            # (bond,k2),(k2,*rix)
+    core = ra @ lb                                                            # (k1, k2)
+    opts = parse_truncation_opts(max_bond, cutoff, cutoff_mode, renorm)
+    _, ab = parse_method_absorb("svd", absorb, True)
+    cl, s, cr = svd_truncated(core, absorb=ab, info=info, **opts)            # (k1,k),(k,k2)
+    na = np.tensordot(qa, cl, axes=(qa.ndim - 1, 0))                          # (*lix, k)
+    nb = np.tensordot(cr, qb, axes=(1, 0))                                    # (k, *rix)
+    new_a = np.transpose(na, [(lix + (bond,)).index(ix) for ix in a_inds])
+    new_b = np.transpose(nb, [((bond,) + rix).index(ix) for ix in b_inds])
+    return new_a, new_b

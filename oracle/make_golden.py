@@ -173,6 +173,24 @@ def decomp_cases():
                             "kw": {k: (list(v) if k.endswith("inds") else v)
                                    for k, v in kw.items()}})
     meta["split_cases"] = split_cases
+    # bond canonisation / compression through the Tensor interface
+    ta = qtn.Tensor(rng.standard_normal((6, 12, 5)), inds=("a", "x", "b"))
+    tb = qtn.Tensor(rng.standard_normal((4, 12, 3)), inds=("c", "x", "d"))
+    store["bond__a"], store["bond__b"] = ta.data.copy(), tb.data.copy()
+    ca, cb = ta.copy(), tb.copy()
+    qtn.tensor_canonize_bond(ca, cb, absorb="right")
+    store["bond__canon_a"], store["bond__canon_b"] = np.asarray(ca.data), np.asarray(cb.data)
+    meta["bond_canon_inds"] = [list(ca.inds), list(cb.inds)]
+    bond_cases = []
+    for kw in [dict(max_bond=5, cutoff=0.0, absorb="both"), dict(max_bond=None, cutoff=1e-1, absorb="right"),
+               dict(max_bond=7, cutoff=1e-10, absorb="left")]:
+        xa, xb = ta.copy(), tb.copy()
+        qtn.tensor_compress_bond(xa, xb, **kw)
+        key = f"bond__cmp{len(bond_cases)}"
+        store[key + "_a"], store[key + "_b"] = np.asarray(xa.data), np.asarray(xb.data)
+        bond_cases.append({"key": key, "kw": kw, "inds": [list(xa.inds), list(xb.inds)],
+                           "bond": int(xa.ind_size("x"))})
+    meta["bond_cases"] = bond_cases
     # parse_split_opts codes
     meta["parse_split_opts"] = []
     for kw in [dict(), dict(method="svd", absorb="left", max_bond=7, cutoff=1e-3, cutoff_mode="sum2"),

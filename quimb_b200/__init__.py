@@ -21,12 +21,12 @@ from .ops import (abs, all, any, max, min, sum)  # noqa: F401,A004
 from . import linalg  # noqa: F401
 from .contract import contract_batched, contract_pair, plan_pair  # noqa: F401
 from . import dist  # noqa: F401
-from .tree import (ContractExpression, Tree, array_contract,  # noqa: F401
-                   find_tree, gen_output_inds)
+from .tree import (ContractExpression, GraphedContraction, Tree,  # noqa: F401
+                   array_contract, find_tree, gen_output_inds)
 from .mps import (env_left_step, env_right_step, mps_expec, mps_norm,  # noqa: F401
                   mps_norm2)
 from .split import (array_split, qr_stabilized, svd_truncated,  # noqa: F401
-                    tensor_split)
+                    tensor_canonize_bond, tensor_compress_bond, tensor_split)
 from .lanczos import eigh_lanczos  # noqa: F401
 from .dmrg import DMRG2  # noqa: F401
 from .integration import register_with_quimb  # noqa: F401

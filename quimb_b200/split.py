@@ -236,3 +236,66 @@ def tensor_split(x, inds, left_inds, right_inds=None, method="auto",
     if right is not None:
         out.append(right.reshape(-1, *rdims))
     return tuple(out)
+
+
+def _out_perm(have, want):
+    return [have.index(ix) for ix in want]
+
+
+def tensor_canonize_bond(a, a_inds, b, b_inds, absorb="right"):
+    """Array-level ``tensor_canonize_bond`` (tensor_core.py:671-824): QR ``a``
+    over the bond shared with ``b``, absorb R into ``b`` (or the LQ mirror for
+    ``absorb='left'``).  Outputs keep the index order of the inputs; the
+    absorption is one launch of the contraction kernel writing straight into
+    that order."""
+    from .contract import contract_pair
+    a, b = ops.asarray(a), ops.asarray(b)
+    a_inds, b_inds = tuple(a_inds), tuple(b_inds)
+    shared = [ix for ix in a_inds if ix in b_inds]
+    if len(shared) != 1:
+        raise ValueError("The tensors specified don't share an bond.")
+    if absorb == "left":
+        nb, na = tensor_canonize_bond(b, b_inds, a, a_inds, "right")
+        return na, nb
+    bond = shared[0]
+    lix = tuple(ix for ix in a_inds if ix != bond)
+    q, r = tensor_split(a, a_inds, lix, (bond,), method="qr")
+    new_a = q.transpose(*_out_perm(lix + (bond,), a_inds))
+    lab = {ix: i for i, ix in enumerate(dict.fromkeys(a_inds + b_inds))}
+    K = len(lab)  # label of the new bond
+    lb = [lab[ix] for ix in b_inds]
+    out = [K if ix == bond else lab[ix] for ix in b_inds]
+    new_b = Array(contract_pair(r.t, [K, lab[bond]], b.t, lb, out, conj_a=r.cj, conj_b=b.cj))
+    return new_a, new_b
+
+
+def tensor_compress_bond(a, a_inds, b, b_inds, max_bond=None, cutoff=1e-10,
+                         cutoff_mode="rel", absorb="both", renorm=None, info=None):
+    """Array-level ``tensor_compress_bond`` (tensor_core.py:864-1094, the
+    default ``reduced=True`` pipeline): QR(a), LQ(b), truncated SVD of the
+    reduced core, factors folded back with two contractions.  Outputs keep the
+    index order of the inputs."""
+    from .contract import contract_pair
+    a, b = ops.asarray(a), ops.asarray(b)
+    a_inds, b_inds = tuple(a_inds), tuple(b_inds)
+    shared = [ix for ix in a_inds if ix in b_inds]
+    if len(shared) != 1:
+        raise ValueError("The tensors specified don't share an bond. "
+                         "To create one automatically, set `create_bond=True`.")
+    bond = shared[0]
+    lix = tuple(ix for ix in a_inds if ix != bond)
+    rix = tuple(ix for ix in b_inds if ix != bond)
+    qa, ra = tensor_split(a, a_inds, lix, (bond,), method="qr")      # (*lix,k1), (k1,bond)
+    lb_, qb = tensor_split(b, b_inds, (bond,), rix, method="lq")     # (bond,k2), (k2,*rix)
+    core = ops.tensordot(ra, lb_, axes=((1,), (0,)))                 # (k1, k2)
+    _, opts = parse_split_opts("svd", absorb, max_bond, cutoff, cutoff_mode, renorm)
+    cl, _, cr = svd_truncated(core, info=info, **opts)               # (k1,k), (k,k2)
+    lab = {ix: i for i, ix in enumerate(dict.fromkeys(a_inds + b_inds))}
+    K1, K2, KB = len(lab), len(lab) + 1, lab[bond]
+    la = [lab[ix] for ix in lix] + [K1]
+    new_a = Array(contract_pair(qa.t, la, cl.t, [K1, KB], [lab[ix] for ix in a_inds],
+                                conj_a=qa.cj, conj_b=cl.cj))
+    lq = [K2] + [lab[ix] for ix in rix]
+    new_b = Array(contract_pair(cr.t, [KB, K2], qb.t, lq, [lab[ix] for ix in b_inds],
+                                conj_a=cr.cj, conj_b=qb.cj))
+    return new_a, new_b

@@ -320,3 +320,42 @@ class ContractExpression:
         for i, a in zip(self.var_pos, arrays):
             full[i] = a
         return execute(self.tree, full)
+
+
+class GraphedContraction:
+    """A whole contraction tree captured ONCE into a CUDA graph and replayed.
+
+    Trees over many small tensors (circuit amplitudes, PEPS/MPS sweeps) are
+    launch- and host-bound: hundreds of kernels of a few microseconds each.
+    quimb/cotengra cache the *expression* per geometry
+    (tests/test_tensor/test_contract.py:155-175); here the cached object is
+    the captured launch sequence itself, so a repeat contraction with new
+    input values costs one graph launch.  Input arrays are copied into static
+    device buffers; the output buffer is reused (clone it to keep it).
+    """
+
+    def __init__(self, inputs, output, example_arrays, optimize="auto"):
+        import torch
+        arrays = [ops.materialize(ops.asarray(a), force=True) for a in example_arrays]
+        self.inputs = [tuple(t) for t in inputs]
+        self.output = tuple(output)
+        self.tree = find_tree(self.inputs, self.output, _sizes(self.inputs, arrays),
+                              optimize)
+        self.static_in = arrays
+        execute(self.tree, self.static_in)          # warm-up: attributes, workspaces
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = execute(self.tree, self.static_in)
+        self.n_nodes = len(self.tree.steps)
+
+    def __call__(self, *arrays):
+        if len(arrays) != len(self.static_in):
+            raise ValueError("wrong number of arrays")
+        for s, a in zip(self.static_in, arrays):
+            a = ops.asarray(a)
+            if a.shape != s.shape:
+                raise ValueError("shape mismatch with the captured contraction")
+            s.t.copy_(a.resolve())
+        self.graph.replay()
+        return self.out

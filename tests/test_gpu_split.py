@@ -169,3 +169,19 @@ def test_float32_split_preserves_dtype():
     Q, _, R = qb.qr_stabilized(qb.asarray(x))
     assert Q.dtype == np.float32
     np.testing.assert_allclose(Q.to_numpy() @ R.to_numpy(), x, atol=1e-5)
+
+
+def test_bond_canonize_compress_match_reference(golden_decomp):
+    data, meta = golden_decomp
+    a, b = data["bond__a"], data["bond__b"]
+    na, nb = qb.tensor_canonize_bond(qb.asarray(a), "axb", qb.asarray(b), "cxd")
+    np.testing.assert_allclose(_np(na), data["bond__canon_a"], atol=1e-11)   # unique (QR)
+    np.testing.assert_allclose(_np(nb), data["bond__canon_b"], atol=1e-11)
+    for c in meta["bond_cases"]:
+        xa, xb = qb.tensor_compress_bond(qb.asarray(a), "axb", qb.asarray(b), "cxd", **c["kw"])
+        ra, rb = data[c["key"] + "_a"], data[c["key"] + "_b"]
+        assert xa.shape == ra.shape and xb.shape == rb.shape     # bond position and size: exact
+        np.testing.assert_allclose(np.einsum("axb,cxd->abcd", _np(xa), _np(xb)),
+                                   np.einsum("axb,cxd->abcd", ra, rb), atol=1e-10)
+    with pytest.raises(ValueError):
+        qb.tensor_compress_bond(qb.asarray(a), "axb", qb.asarray(b), "cyd")

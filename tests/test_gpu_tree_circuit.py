@@ -38,3 +38,16 @@ def test_sliced_contraction_sums_to_the_same_amplitude():
                                           rank=0, world_size=1)
     assert len(mine) == 4
     assert abs(complex(total.item()) - amp) <= 1e-10
+
+
+def test_cuda_graph_replay_of_a_tree():
+    arrays, inputs, output, amp = random_circuit_amplitude(8, 6, 3)
+    g = qb.GraphedContraction(inputs, output, arrays, optimize="greedy")
+    v1 = complex(g(*arrays).item())
+    assert abs(v1 - amp) <= 1e-10
+    # new input values (different output bitstring), same structure: one replay
+    arrays2, _, _, amp2 = random_circuit_amplitude(8, 6, 3, bits=[1, 0, 1, 1, 0, 0, 1, 0])
+    n0 = qb.launch_count()
+    v2 = complex(g(*arrays2).item())
+    assert qb.launch_count() == n0          # no host-side launches: graph replay
+    assert abs(v2 - amp2) <= 1e-10

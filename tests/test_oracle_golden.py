@@ -152,3 +152,18 @@ def test_dmrg2_energies_match_reference(golden_mps):
         assert d.energy == pytest.approx(run["energies"][-1], abs=20 * run["tol"])
         if run["exact"] is not None:
             assert d.energy == pytest.approx(run["exact"], abs=1e-6)
+
+
+def test_bond_canonize_compress_match_reference(golden_decomp):
+    data, meta = golden_decomp
+    a, b = data["bond__a"], data["bond__b"]
+    na, nb = dn.tensor_canonize_bond(a, "axb", b, "cxd")
+    assert meta["bond_canon_inds"] == [list("axb"), list("cxd")]
+    np.testing.assert_allclose(na, data["bond__canon_a"], atol=1e-12)
+    np.testing.assert_allclose(nb, data["bond__canon_b"], atol=1e-12)
+    for c in meta["bond_cases"]:
+        xa, xb = dn.tensor_compress_bond(a, "axb", b, "cxd", **c["kw"])
+        ra, rb = data[c["key"] + "_a"], data[c["key"] + "_b"]
+        assert xa.shape == ra.shape and xb.shape == rb.shape and xa.shape[1] == c["bond"]
+        np.testing.assert_allclose(np.einsum("axb,cxd->abcd", xa, xb),
+                                   np.einsum("axb,cxd->abcd", ra, rb), atol=1e-11)
