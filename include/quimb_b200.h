@@ -189,6 +189,13 @@ int qb_scale_diag(int dtype, int64_t rows, int64_t cols, void *x,
 int qb_convert(int src_dtype, int dst_dtype, int64_t n, const void *src,
                void *dst, void *stream);
 
+/* complex128 <-> interleaved real embedding E[2i+a, 2j+b] (row-major
+ * 2m x 2n): complex QR / SVD run on the real kernels through it.
+ * qb_extract_complex: out[i, c] = E[2i, c*col_step] + 1j E[2i+1, c*col_step]. */
+int qb_embed_complex(int64_t m, int64_t n, const void *z, void *E, void *stream);
+int qb_extract_complex(int64_t m, int64_t ncols, int64_t col_step, const void *E,
+                       int64_t ld, void *out, void *stream);
+
 /* ---- decompositions ---------------------------------------------------- */
 /*
  * Stabilised thin QR of a row-major contiguous m x n matrix X (m >= n):

@@ -93,6 +93,8 @@ def load(build_if_missing=True):
     sig("qb_dot_workspace", i64, [i64])
     sig("qb_scale_diag", ci, [ci, i64, i64, vp, vp, ci, ci, vp])
     sig("qb_convert", ci, [ci, ci, i64, vp, vp, vp])
+    sig("qb_embed_complex", ci, [i64, i64, vp, vp, vp])
+    sig("qb_extract_complex", ci, [i64, i64, i64, vp, i64, vp, vp])
     sig("qb_multi_dot", ci, [ci, ci, i64, vp, i64, vp, vp, vp, vp])
     sig("qb_multi_dot_workspace", i64, [])
     sig("qb_multi_axpy", ci, [ci, ci, i64, vp, i64, vp, ctypes.c_double, vp, vp])

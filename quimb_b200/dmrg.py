@@ -104,12 +104,12 @@ class DMRG2:
     """Two-site DMRG for an open-boundary MPO, on the device."""
 
     def __init__(self, ham, bond_dims, cutoffs=1e-8, which="SA", p0=None,
-                 mpo_shape="lrud", mps_shape="lpr", seed=None):
+                 mpo_shape="lrud", mps_shape="lpr", seed=None, dtype=None):
         self.L = len(ham)
         n = self.L
         self.which = which
         self.ham = [mpo_lrud(w, mpo_shape, i, n) for i, w in enumerate(ham)]
-        dt = self.ham[0].dtype
+        dt = np.dtype(dtype) if dtype is not None else self.ham[0].dtype
         self.phys_dim = self.ham[0].shape[2]
         self._set_bond_dim_seq(bond_dims)
         self._set_cutoff_seq(cutoffs)
@@ -118,7 +118,9 @@ class DMRG2:
             mps_shape = "lpr"
         self._k = [ops.materialize(site_lpr(a, mps_shape, i, n), force=True)
                    for i, a in enumerate(p0)]
-        if self._k[0].dtype != dt:
+        if self._k[0].dtype != self.ham[0].dtype:
+            # the network runs in the dtype of the state (quimb preserves the
+            # dtype end to end: test_dmrg.py:290-300)
             self.ham = [w.astype(self._k[0].dtype) for w in self.ham]
         # quimb's DMRG starts from a normalised state (MPS_rand_state
         # normalises; a user p0 is used as given)
@@ -336,6 +338,8 @@ def _rand_mps(n, bond_dim, d, dtype, seed):
     for i in range(n):
         shape = (bonds[i], d, bonds[i + 1])
         x = rng.standard_normal(shape)
+        if np.dtype(dtype).kind == "c":
+            x = (x + 1j * rng.standard_normal(shape)) / np.sqrt(2)
         nd = sum(1 for q in shape if q > 1) or 1
         x = x / np.linalg.norm(x) ** (1.5 / nd)
         sites.append(ops.asarray(x.astype(np.dtype(dtype))))

@@ -78,6 +78,21 @@ def eigh_lanczos(matvec, v0, which="SA", ncv=4, tol=1e-3, maxiter=None,
     Returns ``(theta: float, x: Array[n])`` (+ info dict).
     """
     v0 = ops.materialize(ops.asarray(v0)).reshape(-1)
+    if v0.t.dtype == torch.complex128:
+        # A Hermitian operator on C^n is a real symmetric operator on R^2n
+        # (complex storage viewed as interleaved reals); each eigenvalue is
+        # doubled and every real eigenvector is the image of a complex one,
+        # so the real Krylov machinery applies unchanged.
+        def mv_real(vr):
+            vc = Array(torch.view_as_complex(vr.t.reshape(-1, 2)))
+            out = ops.materialize(matvec(vc)).t.reshape(-1)
+            return Array(torch.view_as_real(out).reshape(-1))
+
+        vr0 = Array(torch.view_as_real(v0.t).reshape(-1))
+        theta, xr, info = eigh_lanczos(mv_real, vr0, which=which, ncv=ncv, tol=tol,
+                                       maxiter=maxiter, return_info=True)
+        x = Array(torch.view_as_complex(xr.t.reshape(-1, 2)))
+        return (theta, x, info) if return_info else (theta, x)
     n = v0.size
     dt = v0.t.dtype
     if dt != torch.float64:

@@ -2,9 +2,23 @@
 like="quimb_b200")`` resolves to.  SVD and QR run on the dedicated CUDA
 kernels (``csrc/linalg.cu``: cluster-resident Householder panels, one-sided
 block Jacobi); nothing here falls back to a CPU or library factorization.
+
+dtypes: float64 natively.  float32 / complex64 are widened exactly, factored
+in double precision and rounded once.  complex128 runs on the same real
+kernels through the interleaved real embedding
+``E[2i+a, 2j+b] = [[re, -im], [im, re]]``:
+
+* the stabilised real QR of E *is* the embedding of the stabilised complex QR
+  (QR with positive diagonal is unique), so Q and R are read off its even
+  columns;
+* every real singular vector of E is the image of a complex singular vector
+  of x, each singular value appears twice; one vector per pair is kept (for
+  clusters of equal singular values a small complex Gram matrix decides which
+  candidates are independent and re-orthonormalises them).
 """
 
 import ctypes
+import functools
 
 import numpy as np
 import torch
@@ -24,21 +38,32 @@ def _workspace(nbytes, device):
     return buf
 
 
+_WIDE = {torch.float32: torch.float64, torch.complex64: torch.complex128}
+
+
 def _narrow(fn):
-    """float32 input: widen exactly, factor in fp64, round the factors once
-    (dtype is preserved end to end, as the reference does)."""
-    import functools
+    """float32 / complex64 input: widen exactly, factor in double precision,
+    round the factors once (dtype is preserved end to end, as the reference
+    does)."""
 
     @functools.wraps(fn)
     def wrapped(x, *args, **kwargs):
         x = ops.asarray(x)
-        if x.t.dtype != torch.float32:
+        if x.t.dtype not in _WIDE:
             return fn(x, *args, **kwargs)
         from .contract import convert
-        wide = Array(convert(ops.materialize(x).t, torch.float64))
+        src = x.t.dtype
+        real_src = torch.float32
+        wide = Array(convert(ops.materialize(x).t, _WIDE[src]))
         outs = fn(wide, *args, **kwargs)
-        return tuple(Array(convert(o.t, torch.float32)) if isinstance(o, Array) else o
-                     for o in outs)
+        res = []
+        for o in outs:
+            if isinstance(o, Array):
+                t = ops.materialize(o).t
+                res.append(Array(convert(t, src if t.dtype.is_complex else real_src)))
+            else:
+                res.append(o)
+        return tuple(res)
     return wrapped
 
 
@@ -47,21 +72,43 @@ def _as_matrix(x):
     if x.ndim != 2:
         raise ValueError("quimb_b200.linalg: only 2-d arrays are supported "
                          f"(got shape {x.shape})")
-    if x.t.dtype != torch.float64:
-        raise TypeError(
-            f"quimb_b200.linalg: dtype {x.dtype} is not implemented yet "
-            "(float64 only); no fallback exists")
+    if x.t.dtype not in (torch.float64, torch.complex128):
+        raise TypeError(f"quimb_b200.linalg: dtype {x.dtype} is not supported")
     _lib.require_cuda(x.t)
     return x
+
+
+def _embed(x):
+    """complex (m, n) -> real (2m, 2n) interleaved embedding (one kernel)."""
+    m, n = x.shape
+    E = torch.empty((2 * m, 2 * n), dtype=torch.float64, device=x.t.device)
+    rc = _lib.load().qb_embed_complex(m, n, x.t.data_ptr(), E.data_ptr(), _lib.stream_ptr())
+    _lib.check(rc, "qb_embed_complex")
+    return E
+
+
+def _extract(E, m, ncols, col_step):
+    """complex (m, ncols) with out[i,c] = E[2i, c*step] + 1j E[2i+1, c*step]."""
+    out = torch.empty((m, ncols), dtype=torch.complex128, device=E.device)
+    rc = _lib.load().qb_extract_complex(m, ncols, col_step, E.data_ptr(), E.stride(0),
+                                        out.data_ptr(), _lib.stream_ptr())
+    _lib.check(rc, "qb_extract_complex")
+    return out
 
 
 @_narrow
 def qr(x, stabilized=False, want_q=True, want_r=True):
     """Thin QR of a 2-d device array: Q (m, k), R (k, n), k = min(m, n).
-    ``stabilized`` makes diag(R) >= 0 (quimb's qr_stabilized convention)."""
+    ``stabilized`` makes diag(R) >= 0 (quimb's qr_stabilized convention);
+    complex input is always returned stabilised (diag(R) real, >= 0)."""
     x = _as_matrix(x)
     m, n = x.shape
     k = min(m, n)
+    if x.t.dtype == torch.complex128:
+        Qe, Re = qr(Array(_embed(x)), stabilized=True, want_q=want_q, want_r=want_r)
+        Q = Array(_extract(Qe.t, m, k, 2)) if want_q else None
+        R = Array(_extract(Re.t, k, n, 2)) if want_r else None
+        return Q, R
     lib = _lib.load()
     dev = x.t.device
     if m < n:
@@ -85,13 +132,58 @@ def qr(x, stabilized=False, want_q=True, want_r=True):
     return (Array(Q) if want_q else None), (Array(R) if want_r else None)
 
 
+def _select_complex_pairs(s_host, gram_fn):
+    """Choose one real singular vector per complex singular vector.
+
+    ``s_host``: the 2k sorted singular values of the embedding.  Returns
+    (indices, blocks) where ``blocks`` lists (start, [local picks], T) for
+    clusters of more than one complex vector that need the small
+    re-orthonormalising transform T (k_c x k_c, complex, host)."""
+    n2 = len(s_host)
+    smax = s_host[0] if n2 and s_host[0] > 0 else 1.0
+    sel, blocks = [], []
+    i = 0
+    while i < n2:
+        j = i + 1
+        while j < n2 and abs(s_host[j] - s_host[i]) <= 1e-10 * smax:
+            j += 1
+        if (j - i) % 2:
+            j = min(j + 1, n2)  # pairs are never split
+        size = j - i
+        d = size // 2
+        if d <= 1:
+            sel.append(i)
+        else:
+            G = gram_fn(i, j)  # complex Gram of the candidates, host (size x size)
+            chosen = []
+            for c in range(size):
+                if len(chosen) == d:
+                    break
+                if chosen:
+                    gs = G[np.ix_(chosen, [c])]
+                    GS = G[np.ix_(chosen, chosen)]
+                    res = (G[c, c] - (gs.conj().T @ np.linalg.solve(GS, gs))[0, 0]).real
+                else:
+                    res = G[c, c].real
+                if res > 0.25:
+                    chosen.append(c)
+            Gs = G[np.ix_(chosen, chosen)]
+            T = np.linalg.inv(np.linalg.cholesky(Gs)).conj().T
+            blocks.append((len(sel), len(chosen), T))
+            sel.extend(i + c for c in chosen)
+        i = j
+    return sel, blocks
+
+
 @_narrow
 def svd(x, full_matrices=False, return_sweeps=False):
-    """Thin SVD: U (m, k), s (k,) descending, VH (k, n)."""
+    """Thin SVD: U (m, k), s (k,) real descending, VH (k, n)."""
     if full_matrices:
         raise NotImplementedError("quimb_b200.linalg.svd: thin SVD only")
     x = _as_matrix(x)
     m, n = x.shape
+    if x.t.dtype == torch.complex128:
+        return _svd_complex(x, return_sweeps)
     if m < n:
         xt = ops.materialize(Array(x.t.t()))
         out = svd(xt, return_sweeps=return_sweeps)
@@ -114,6 +206,37 @@ def svd(x, full_matrices=False, return_sweeps=False):
     _lib.check(rc, "qb_svd")
     out = (Array(U), Array(S), Array(VH))
     return out + (sweeps.value,) if return_sweeps else out
+
+
+def _svd_complex(x, return_sweeps):
+    m, n = x.shape
+    k = min(m, n)
+    out = svd(Array(_embed(x)), return_sweeps=True)
+    Ue, se, VHe, sweeps = out                       # (2m,2k) (2k,) (2k,2n)
+    s_host = se.t.cpu().numpy()
+    Uc = _extract(ops.materialize(Ue).t, m, 2 * k, 1)           # (m, 2k) complex
+    # row j of VHe viewed as complex is v_j^T; VH rows are conj(v_j)
+    Vrows = torch.view_as_complex(ops.materialize(VHe).t.reshape(2 * k, n, 2))
+
+    def gram(i, j):
+        Z = Array(Uc[:, i:j])
+        return ops.tensordot(Z.conj(), Z, axes=((0,), (0,))).to_numpy()
+
+    sel, blocks = _select_complex_pairs(s_host, gram)
+    idx = torch.as_tensor(sel, dtype=torch.int64, device=x.t.device)
+    U = Uc.index_select(1, idx).contiguous()                    # (m, k)
+    VH = Array(Vrows.index_select(0, idx).contiguous()).conj()  # (k, n), lazy conj
+    VH = ops.materialize(VH).t
+    S = se.t.index_select(0, idx).contiguous()
+    for start, size, T in blocks:
+        Td = ops.asarray(np.ascontiguousarray(T))
+        Ub = Array(U[:, start:start + size])
+        U[:, start:start + size] = ops.tensordot(Ub, Td, axes=((1,), (0,))).t
+        Vb = Array(VH[start:start + size, :])
+        VH[start:start + size, :] = ops.tensordot(Td.conj().transpose(1, 0), Vb,
+                                                  axes=((1,), (0,))).t
+    res = (Array(U), Array(S), Array(VH))
+    return res + (sweeps,) if return_sweeps else res
 
 
 def norm(x, ord=None):

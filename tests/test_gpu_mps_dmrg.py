@@ -128,3 +128,27 @@ def test_dmrg2_parity_mode_arpack_driver():
     d.solve(tol=1e-8, max_sweeps=6)
     H = dm.mpo_to_dense(mpo)
     assert d.energy == pytest.approx(np.linalg.eigvalsh(H)[0], abs=1e-7)
+
+
+def test_dmrg2_complex128_dtype_preserved():
+    """dtype preservation (reference: test_dmrg.py:290-300): a complex state
+    stays complex, the energy is the real ground-state energy."""
+    mpo = dm.mpo_heis(8)
+    d = qb.DMRG2(mpo, [8, 16], cutoffs=1e-10, mpo_shape="lrdu", seed=4, dtype="complex128")
+    d.solve(tol=1e-8, max_sweeps=6)
+    assert all(a.dtype == np.complex128 for a in d.state)
+    e0 = np.linalg.eigvalsh(dm.mpo_to_dense(mpo))[0]
+    assert d.energy == pytest.approx(e0, abs=1e-7)
+
+
+def test_lanczos_complex_hermitian():
+    rng = np.random.default_rng(7)
+    n = 300
+    M = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n)); M = 0.5 * (M + M.conj().T)
+    Md = qb.asarray(M)
+    theta, x = qb.eigh_lanczos(lambda v: qb.tensordot(Md, v, axes=1),
+                               qb.asarray(rng.standard_normal(n) + 1j * rng.standard_normal(n)),
+                               ncv=16, tol=1e-10)
+    assert theta == pytest.approx(np.linalg.eigvalsh(M)[0], abs=1e-8)
+    xv = x.to_numpy()
+    assert np.linalg.norm(M @ xv - theta * xv) < 1e-6

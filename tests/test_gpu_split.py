@@ -20,10 +20,6 @@ def test_qr_matches_reference_golden(golden_decomp):
     data, meta = golden_decomp
     for c in meta["qr_cases"]:
         x = data[f"mat__{c['mat']}"]
-        if np.iscomplexobj(x):
-            with pytest.raises(TypeError):
-                qb.qr_stabilized(qb.asarray(x), absorb=c["absorb"])
-            continue
         left, _, right = qb.qr_stabilized(qb.asarray(x), absorb=c["absorb"])
         for part, nm in ((left, "__left"), (right, "__right")):
             key = c["key"] + nm
@@ -92,8 +88,6 @@ def test_svd_truncated_matches_reference_golden(golden_decomp):
     data, meta = golden_decomp
     for c in meta["svd_cases"]:
         x = data[f"mat__{c['mat']}"]
-        if np.iscomplexobj(x):
-            continue
         info = {"error": None}
         left, s, right = qb.svd_truncated(
             qb.asarray(x), cutoff=c["cutoff"], cutoff_mode=c["cutoff_mode"],
@@ -185,3 +179,47 @@ def test_bond_canonize_compress_match_reference(golden_decomp):
                                    np.einsum("axb,cxd->abcd", ra, rb), atol=1e-10)
     with pytest.raises(ValueError):
         qb.tensor_compress_bond(qb.asarray(a), "axb", qb.asarray(b), "cyd")
+
+
+@pytest.mark.parametrize("m,n", [(12, 14), (40, 24), (64, 64)])
+def test_complex_svd_qr_via_real_embedding(m, n):
+    rng = np.random.default_rng(m + n)
+    x = rng.standard_normal((m, n)) + 1j * rng.standard_normal((m, n))
+    U, s, VH = qb.linalg.svd(qb.asarray(x))
+    u, sv, vh = _np(U), _np(s), _np(VH)
+    k = min(m, n)
+    assert u.shape == (m, k) and vh.shape == (k, n) and sv.dtype == np.float64
+    np.testing.assert_allclose(sv, np.linalg.svd(x, compute_uv=False), rtol=1e-11)
+    np.testing.assert_allclose((u * sv) @ vh, x, atol=1e-11)
+    np.testing.assert_allclose(u.conj().T @ u, np.eye(k), atol=1e-11)
+    np.testing.assert_allclose(vh @ vh.conj().T, np.eye(k), atol=1e-11)
+    Q, R = qb.linalg.qr(qb.asarray(x), stabilized=True)
+    q, r = _np(Q), _np(R)
+    np.testing.assert_allclose(q @ r, x, atol=1e-11)
+    np.testing.assert_allclose(q.conj().T @ q, np.eye(k), atol=1e-12)
+    assert np.abs(np.diag(r).imag).max() < 1e-13 and (np.diag(r).real >= 0).all()
+    lo, _, ro = dn.qr_stabilized(x.copy())
+    np.testing.assert_allclose(q, lo, atol=1e-10)
+
+
+def test_complex_svd_degenerate_singular_values():
+    rng = np.random.default_rng(5)
+    q1, _ = np.linalg.qr(rng.standard_normal((16, 16)) + 1j * rng.standard_normal((16, 16)))
+    q2, _ = np.linalg.qr(rng.standard_normal((16, 16)) + 1j * rng.standard_normal((16, 16)))
+    s = np.array([3.0] * 4 + [1.0] * 6 + [0.5] * 6)
+    x = (q1 * s) @ q2
+    U, sv, VH = qb.linalg.svd(qb.asarray(x))
+    u, svn, vh = _np(U), _np(sv), _np(VH)
+    np.testing.assert_allclose(svn, s, atol=1e-12)
+    np.testing.assert_allclose((u * svn) @ vh, x, atol=1e-11)
+    np.testing.assert_allclose(u.conj().T @ u, np.eye(16), atol=1e-11)
+
+
+def test_complex64_split_preserves_dtype():
+    rng = np.random.default_rng(6)
+    x = (rng.standard_normal((30, 20)) + 1j * rng.standard_normal((30, 20))).astype(np.complex64)
+    left, _, right = qb.svd_truncated(qb.asarray(x), cutoff=0.0, max_bond=8, absorb=0)
+    assert left.dtype == np.complex64 and right.dtype == np.complex64
+    sref = np.linalg.svd(x.astype(np.complex128), compute_uv=False)
+    err = np.linalg.norm(left.to_numpy().astype(np.complex128) @ right.to_numpy().astype(np.complex128) - x)
+    assert err == pytest.approx(np.sqrt(np.sum(sref[8:] ** 2)), rel=1e-4)
