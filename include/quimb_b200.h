@@ -86,7 +86,13 @@ enum {
 enum {
   QB_ENGINE_AUTO = 0, /* heuristic                                    */
   QB_ENGINE_DMMA = 1, /* native fp64 tensor-core path (DMMA)          */
-  QB_ENGINE_OZAKI = 2 /* tcgen05 int8 error-free-split path (fp64)    */
+  QB_ENGINE_OZAKI = 2, /* tcgen05 int8 error-free-split path (fp64)    */
+  /* OR-able flag: the caller guarantees that bytes [0, 1024) of `workspace`
+   * (the stream-K flag words) were zero before its first use and are written
+   * by this library only -- which always leaves them zero again -- so the
+   * per-launch clear of those words is skipped (saves one memset node per
+   * contraction; matters for back-to-back launches and CUDA graphs). */
+  QB_ENGINE_WS_ZEROED = 0x100
 };
 
 /* ---- library ---------------------------------------------------------- */
@@ -230,6 +236,13 @@ int qb_svals_to_keep(const double *s, int64_t n, double cutoff,
 /* ---- device queries / microbenchmarks ---------------------------------- */
 /* sustained DMMA (fp64 tensor core) rate of the current device in TFLOP/s */
 int qb_measure_dmma_peak(double *tflops, void *stream);
+/* tuning hook: with QB_TRACE=1 in the environment the contraction kernels stamp
+ * %globaltimer at their phase boundaries (entry, tables, prologue issued,
+ * first tile landed, main loop done, stream-K fix-up done, stores issued) into
+ * a device buffer laid out [cta][4 segments][8 phases]; this copies the first
+ * `count` uint64 entries to `host_out`, clears the buffer and returns 0
+ * (1 if tracing is off). */
+int qb_debug_trace_read(unsigned long long *host_out, int64_t count);
 
 #ifdef __cplusplus
 }

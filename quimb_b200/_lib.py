@@ -12,6 +12,8 @@ import torch
 
 QB_MAX_RANK = 32
 QB_F32, QB_F64, QB_C64, QB_C128 = 0, 1, 2, 3
+QB_ENGINE_AUTO, QB_ENGINE_DMMA, QB_ENGINE_OZAKI = 0, 1, 2
+QB_ENGINE_WS_ZEROED = 0x100
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libquimb_b200.so")
@@ -107,6 +109,7 @@ def load(build_if_missing=True):
         ("qb_svals_to_keep", ci, [dblp, i64, ctypes.c_double, ci, i64, ci,
                                   P(i64), dblp, dblp]),
         ("qb_measure_dmma_peak", ci, [dblp, vp]),
+        ("qb_debug_trace_read", ci, [vp, i64]),
     ):
         if hasattr(lib, name):
             sig(name, res, args)

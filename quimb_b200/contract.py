@@ -16,11 +16,13 @@ _WS = {}
 
 
 def _workspace(nbytes, device):
-    """Grow-only per-(device, stream) scratch buffer."""
+    """Grow-only per-(device, stream) scratch buffer.  Allocated zeroed and
+    handed to nothing but the contraction entry points, which keep its 1 KiB
+    header (stream-K flag words) zero -- the QB_ENGINE_WS_ZEROED contract."""
     key = (device.index, torch.cuda.current_stream(device).cuda_stream)
     buf = _WS.get(key)
     if buf is None or buf.numel() < nbytes:
-        buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8,
+        buf = torch.zeros(max(int(nbytes), 1 << 20), dtype=torch.uint8,
                           device=device)
         _WS[key] = buf
     return buf
@@ -107,8 +109,8 @@ def contract_pair(a, la, b, lb, lc, conj_a=False, conj_b=False, out=None,
         ws_ptr, ws_n = ctypes.c_void_p(ws.data_ptr()), ws.numel()
     if alpha == 1.0 and beta == 0.0:
         rc = lib.qb_contract_pair(da, pla, db, plb, dc, plc, int(bool(conj_a)),
-                                  int(bool(conj_b)), engine, ws_ptr, ws_n,
-                                  _lib.stream_ptr())
+                                  int(bool(conj_b)), engine | _lib.QB_ENGINE_WS_ZEROED,
+                                  ws_ptr, ws_n, _lib.stream_ptr())
     else:
         rc = lib.qb_contract_pair_ab(da, pla, db, plb, dc, plc,
                                      int(bool(conj_a)), int(bool(conj_b)),

@@ -52,7 +52,7 @@ int gemm_f64(const double *A, int64_t a_rs, int64_t a_cs, const double *B,
   if (rc) return rc;
   plan.streamk = 0;  // internal GEMMs use classic launches (small scratch)
   if (plan.p.splitk > 1) {
-    if (plan_workspace_bytes(plan) > splitk_ws_elems * 8) {
+    if (plan_scratch_bytes(plan) > splitk_ws_elems * 8) {
       // not enough scratch: redo the plan without split-K
       rc = plan_pair(&a, la, &b, lb, &c, lc, 0, 0, plan, -1, 1);
       if (rc) return rc;
@@ -125,8 +125,23 @@ int64_t qb_contract_pair_workspace(const qb_tensor_t *A, const int32_t *la,
   int rc = plan_pair(A, la, B, lb, C, lc, 0, 0, plan);
   if (rc) return rc;
   int64_t need = plan_workspace_bytes(plan);
-  if (want_ozaki(engine, plan)) need = std::max(need, ozaki_workspace_bytes(plan));
+  if (want_ozaki(engine & 0xff, plan))
+    need = std::max(need, ozaki_workspace_bytes(plan) + kWsHeaderBytes);
   return need;
+}
+
+// QB_TRACE=1: device buffer the kernels stamp their phase times into
+static constexpr int64_t kTraceEntries = 1 << 20;
+static unsigned long long *trace_buffer() {
+  static unsigned long long *buf = [] () -> unsigned long long * {
+    const char *e = getenv("QB_TRACE");
+    if (!e || atoi(e) == 0) return nullptr;
+    unsigned long long *b = nullptr;
+    if (cudaMalloc(&b, kTraceEntries * 8) != cudaSuccess) return nullptr;
+    cudaMemset(b, 0, kTraceEntries * 8);
+    return b;
+  }();
+  return buf;
 }
 
 static int contract_pair_impl(const qb_tensor_t *A, const int32_t *la,
@@ -141,6 +156,8 @@ static int contract_pair_impl(const qb_tensor_t *A, const int32_t *la,
     const char *e = getenv("QB_FORCE_CFG");
     return e ? atoi(e) : -1;
   }();
+  const bool ws_zeroed = (engine & QB_ENGINE_WS_ZEROED) != 0;
+  engine &= 0xff;
   int rc = plan_pair(A, la, B, lb, C, lc, conjA, conjB, plan, force_cfg);
   if (rc) return rc;
   if ((rc = check_device_dtype(plan.dtype))) return rc;
@@ -153,14 +170,18 @@ static int contract_pair_impl(const qb_tensor_t *A, const int32_t *la,
     return -10;
   }
   plan.p.alpha = alpha; plan.p.beta = beta;
+  if (unsigned long long *tb = trace_buffer()) {
+    static unsigned trace_launch = 0;  // 16 rotating slots of 8192 stamps
+    plan.p.trace = tb + (size_t)(trace_launch++ % 16) * 8192;
+  }
   if (want_ozaki(engine, plan)) {
-    int64_t need = ozaki_workspace_bytes(plan);
+    int64_t need = ozaki_workspace_bytes(plan) + kWsHeaderBytes;
     if (!workspace || (int64_t)workspace_bytes < need) {
       set_error("workspace too small: need %lld bytes, got %lld",
                 (long long)need, (long long)workspace_bytes);
       return -10;
     }
-    return launch_contract_ozaki(plan, workspace, st);
+    return launch_contract_ozaki(plan, static_cast<char *>(workspace) + kWsHeaderBytes, st);
   }
   int64_t need = plan_workspace_bytes(plan);
   if (need > 0) {
@@ -169,7 +190,10 @@ static int contract_pair_impl(const qb_tensor_t *A, const int32_t *la,
                 (long long)need, (long long)workspace_bytes);
       return -10;
     }
-    plan.p.partial = static_cast<double *>(workspace);
+    // header = stream-K flag words, scratch behind it
+    plan.p.flags = static_cast<int *>(workspace);
+    plan.p.partial = reinterpret_cast<double *>(static_cast<char *>(workspace) + kWsHeaderBytes);
+    plan.flags_clean = ws_zeroed;
   }
   if (plan.dtype == QB_F64) return launch_contract_f64(plan, st);
   return launch_contract_c128(plan, st);
@@ -216,7 +240,8 @@ int qb_contract_batched(const qb_tensor_t *A0, const int32_t *la,
   // pointer-array batch: no split-K (tiles x count is the parallelism)
   plan.streamk = 0;
   plan.p.splitk = 1;
-  plan.p.k_per_split = cdiv(plan.p.K, 16) * 16;
+  // whole (real-unit) contracted extent in one pass
+  plan.p.k_per_split = cdiv(plan.p.K * (plan.dtype == QB_C128 ? 2 : 1), 32) * 32;
   plan.p.dA = dA; plan.p.dB = dB; plan.p.dC = dC;
   int64_t done = 0;
   while (done < count) {
@@ -232,3 +257,14 @@ int qb_contract_batched(const qb_tensor_t *A0, const int32_t *la,
 }
 
 }  // extern "C"
+
+extern "C" int qb_debug_trace_read(unsigned long long *host_out, int64_t count) {
+  unsigned long long *buf = trace_buffer();
+  if (!buf) return 1;
+  if (count > kTraceEntries) count = kTraceEntries;
+  cudaDeviceSynchronize();
+  if (cudaMemcpy(host_out, buf, count * 8, cudaMemcpyDeviceToHost) != cudaSuccess) return 2;
+  cudaMemset(buf, 0, kTraceEntries * 8);
+  return 0;
+}
+

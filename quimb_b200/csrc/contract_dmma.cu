@@ -52,14 +52,15 @@ struct KernelCfg {
 };
 
 // gather one ROWS x BK tile of 8-byte elements into shared memory
-template <int ROWS, int BK, int NT>
+template <int ROWS, int BK, int NT, int KM = -1>
 __device__ __forceinline__ void load_tile(
     double *__restrict__ sm, const double *__restrict__ gbase,
     const int64_t *__restrict__ row_off, const int64_t *__restrict__ k_off,
     int vec, int thr, int tid) {
   // vec: 0 scalar, 1 pairs along rows, 2 pairs along k.  thr: 1 walk k.
   // smem layout: vec==1 or (vec==0 && thr==0) -> [k][row]; else [row][k]
-  const bool kmajor = (vec == 2) || (vec == 0 && thr == 1);
+  // KM >= 0: the layout is a compile-time constant (specialised kernels)
+  const bool kmajor = KM >= 0 ? (KM == 1) : ((vec == 2) || (vec == 0 && thr == 1));
   const int s_row = kmajor ? (BK + 4) : 1;
   const int s_k = kmajor ? 1 : (ROWS + 4);
   if (vec == 0) {
@@ -134,6 +135,18 @@ __device__ __forceinline__ double flip_sign(double v, unsigned mask_hi) {
   return __hiloint2double(__double2hiint(v) ^ (int)mask_hi, __double2loint(v));
 }
 
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// tuning: stamp phase `ph` of segment `seg` of this CTA (8 phases x 4 segments)
+#define QB_TRACE(ph)                                                        \
+  do {                                                                      \
+    if (p.trace && threadIdx.x == 0 && sk.seg < 4)                          \
+      p.trace[((size_t)sk.bid * 4 + sk.seg) * 8 + (ph)] = global_ns();      \
+  } while (0)
+
 // stream-K bookkeeping of one tile segment
 struct SkSeg {
   int mode;        // 0: classic tile, 1: tail (write partial), 2: head (sum peers)
@@ -141,10 +154,11 @@ struct SkSeg {
   int peer0, peer1;  // head: CTAs [peer0, peer1) hold the rest of the tile
   double *part;    // [grid][BM*BN] partial accumulators
   int *flags;      // [grid]
+  int seg;         // ordinal of this segment within the CTA (trace only)
 };
 
 template <int BM, int BN, int BK, int WARPS_M, int WARPS_N, int STAGES,
-          bool CPLX>
+          bool CPLX, int LA = -1, int LB = -1, int DBG = 0>
 __device__ __forceinline__ void contract_tile(const ContractParams &p, int pid,
                                               int64_t zb, int ks, int64_t kbeg,
                                               int64_t kend, const SkSeg sk) {
@@ -163,6 +177,12 @@ __device__ __forceinline__ void contract_tile(const ContractParams &p, int pid,
   int64_t *ktabA = offCn + BN;      // [2][BK]
   int64_t *ktabB = ktabA + 2 * BK;  // [2][BK]
 
+  QB_TRACE(0);
+  // let the next kernel of the stream become resident as SMs free up ...
+  asm volatile("griddepcontrol.launch_dependents;");
+  // ... and do not touch global memory before the previous one has finished
+  // (pointer-array batches read their arrays right away)
+  if (p.dA) asm volatile("griddepcontrol.wait;" ::: "memory");
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
@@ -255,22 +275,24 @@ __device__ __forceinline__ void contract_tile(const ContractParams &p, int pid,
   auto issue = [&](int kb) {
     if (kb < nkb) {
       const int st = kb % STAGES;
-      load_tile<BM, BK, NT>(sA + (size_t)st * Cfg::A_ELEMS, A, offAm,
-                            ktabA + (kb & 1) * BK, CPLX ? 2 : p.vecA, p.thrA, tid);
+      load_tile<BM, BK, NT, LA>(sA + (size_t)st * Cfg::A_ELEMS, A, offAm,
+                                ktabA + (kb & 1) * BK, CPLX ? 2 : p.vecA, p.thrA, tid);
       if (CPLX)
         load_tile_cplx<NCB, KCB, Cfg::BC_PITCH, NT>(
             sB + (size_t)st * Cfg::B_ELEMS, B, offBn, ktabB + (kb & 1) * BK,
             p.thrB, tid);
       else
-        load_tile<BN, BK, NT>(sB + (size_t)st * Cfg::B_ELEMS, B, offBn,
-                              ktabB + (kb & 1) * BK, p.vecB, p.thrB, tid);
+        load_tile<BN, BK, NT, LB>(sB + (size_t)st * Cfg::B_ELEMS, B, offBn,
+                                  ktabB + (kb & 1) * BK, p.vecB, p.thrB, tid);
     }
     cp_async_commit();
   };
 
   // prologue: tables for block 0, then STAGES-1 loads in flight
   fill_ktab(0);
+  if (!p.dA) asm volatile("griddepcontrol.wait;" ::: "memory");
   __syncthreads();
+  QB_TRACE(1);
 #pragma unroll 1
   for (int s = 0; s < STAGES - 1; ++s) {
     issue(s);
@@ -278,6 +300,7 @@ __device__ __forceinline__ void contract_tile(const ContractParams &p, int pid,
     __syncthreads();
   }
 
+  QB_TRACE(2);
   double acc[MT][NT8][4];
 #pragma unroll
   for (int i = 0; i < MT; ++i)
@@ -287,8 +310,8 @@ __device__ __forceinline__ void contract_tile(const ContractParams &p, int pid,
       for (int v = 0; v < 4; ++v) acc[i][j][v] = 0.0;
 
   const int vecA = CPLX ? 2 : p.vecA;
-  const bool a_kmajor = (vecA == 2) || (vecA == 0 && p.thrA == 1);
-  const bool b_kmajor = (p.vecB == 2) || (p.vecB == 0 && p.thrB == 1);
+  const bool a_kmajor = LA >= 0 ? (LA == 1) : ((vecA == 2) || (vecA == 0 && p.thrA == 1));
+  const bool b_kmajor = LB >= 0 ? (LB == 1) : ((p.vecB == 2) || (p.vecB == 0 && p.thrB == 1));
   const int sAm = a_kmajor ? (BK + 4) : 1, sAk = a_kmajor ? 1 : (BM + 4);
   const int sBn = b_kmajor ? (BK + 4) : 1, sBk = b_kmajor ? 1 : (BN + 4);
   // complex B expansion: per-thread component and sign (a = t&1, c = g&1)
@@ -302,21 +325,28 @@ __device__ __forceinline__ void contract_tile(const ContractParams &p, int pid,
   }
 
   const bool early = ((warp >> 2) & 1) == 0 || (NT <= 128);
+  // DBG (tuning builds only, QB_DBG): 1 no tile loads, 2 no barriers,
+  // 4 fragments read once -- results are garbage, only the timing is used
+  constexpr int dbg = DBG;
+  double af[MT][4], bf[NT8][2];
 #pragma unroll 1
   for (int kb = 0; kb < nkb; ++kb) {
-    cp_async_wait<STAGES - 2>();
-    __syncthreads();  // stage kb landed; stage kb-1 free; next ktab visible
+    if (!(dbg & 2)) {
+      cp_async_wait<STAGES - 2>();
+      __syncthreads();  // stage kb landed; stage kb-1 free; next ktab visible
+    }
+    if (kb == 0) QB_TRACE(3);
     // the two warps that share a scheduler (warp, warp+4) issue their
     // gathers at different points of the k-block so that one of them always
     // has DMMAs ready while the other does address arithmetic
-    if (early) issue(kb + STAGES - 1);
+    if (early && !(dbg & 1)) issue(kb + STAGES - 1);
     fill_ktab(kb + STAGES);
     const double *tA = sA + (size_t)(kb % STAGES) * Cfg::A_ELEMS;
     const double *tB = sB + (size_t)(kb % STAGES) * Cfg::B_ELEMS;
 #pragma unroll
     for (int kk = 0; kk < BK; kk += 8) {
-      if (kk == 8 && !early) issue(kb + STAGES - 1);
-      double af[MT][4], bf[NT8][2];
+      if (kk == 8 && !early && !(dbg & 1)) issue(kb + STAGES - 1);
+      if (!(dbg & 4) || kb == 0) {
 #pragma unroll
       for (int i = 0; i < MT; ++i) {
         const int r = wm0 + i * 16 + g;
@@ -337,6 +367,7 @@ __device__ __forceinline__ void contract_tile(const ContractParams &p, int pid,
           bf[j][1] = tB[c * sBn + (kk + t + 4) * sBk];
         }
       }
+      }
 #pragma unroll
       for (int i = 0; i < MT; ++i)
 #pragma unroll
@@ -344,6 +375,7 @@ __device__ __forceinline__ void contract_tile(const ContractParams &p, int pid,
     }
   }
   cp_async_wait<0>();
+  QB_TRACE(4);
 
   // ---- stream-K: tail segments park their accumulators, heads collect ----
   if (sk.mode == 1) {
@@ -358,12 +390,14 @@ __device__ __forceinline__ void contract_tile(const ContractParams &p, int pid,
     __threadfence();
     __syncthreads();
     if (tid == 0) atomicExch(&sk.flags[sk.bid], 1);
+    QB_TRACE(6);
     return;
   }
   if (sk.mode == 2) {
     for (int c = sk.peer0; c < sk.peer1; ++c) {
       if (tid == 0) {
         while (atomicAdd(&sk.flags[c], 0) == 0) __nanosleep(100);
+        atomicExch(&sk.flags[c], 0);  // left clean for the next launch
       }
       __syncthreads();
       __threadfence();
@@ -378,6 +412,7 @@ __device__ __forceinline__ void contract_tile(const ContractParams &p, int pid,
     }
   }
 
+  QB_TRACE(5);
   // ---- epilogue ----------------------------------------------------------
   if (p.splitk > 1) {
     // canonical [split][batch][M][Nh] partial buffer
@@ -433,19 +468,20 @@ __device__ __forceinline__ void contract_tile(const ContractParams &p, int pid,
         }
       }
     }
+  QB_TRACE(6);
 }
 
 template <int BM, int BN, int BK, int WARPS_M, int WARPS_N, int STAGES,
-          bool CPLX>
+          bool CPLX, int LA = -1, int LB = -1, int DBG = 0>
 __global__ void __launch_bounds__(WARPS_M *WARPS_N * 32)
     contract_f64_kernel(const __grid_constant__ ContractParams p) {
   const int64_t Kh = CPLX ? 2 * p.K : p.K;
   const int ks = blockIdx.z;
   const int64_t kbeg = (int64_t)ks * p.k_per_split;  // in real-k units
   const int64_t kend = min(Kh, kbeg + p.k_per_split);
-  SkSeg sk{0, 0, 0, 0, nullptr, nullptr};
-  contract_tile<BM, BN, BK, WARPS_M, WARPS_N, STAGES, CPLX>(p, blockIdx.x, blockIdx.y, ks,
-                                                           kbeg, kend, sk);
+  SkSeg sk{0, (int)(blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)), 0, 0, nullptr, nullptr, 0};
+  contract_tile<BM, BN, BK, WARPS_M, WARPS_N, STAGES, CPLX, LA, LB, DBG>(
+      p, blockIdx.x, blockIdx.y, ks, kbeg, kend, sk);
 }
 
 // Stream-K: one persistent CTA per SM; the (tile, k-block) iteration space is
@@ -456,31 +492,38 @@ __global__ void __launch_bounds__(WARPS_M *WARPS_N * 32)
 // HEAD, processed last in its range, i.e. long after the tails were written)
 // adds them in a fixed order and runs the normal epilogue.
 template <int BM, int BN, int BK, int WARPS_M, int WARPS_N, int STAGES,
-          bool CPLX>
+          bool CPLX, int LA = -1, int LB = -1>
 __global__ void __launch_bounds__(WARPS_M *WARPS_N * 32)
     contract_f64_streamk_kernel(const __grid_constant__ ContractParams p) {
   const int64_t Kh = CPLX ? 2 * p.K : p.K;
   const int64_t nkbT = (Kh + BK - 1) / BK;
   const int64_t tiles = (int64_t)p.tiles_m * p.tiles_n;
-  const int64_t total = tiles * nkbT;
   const int G = gridDim.x, bid = blockIdx.x;
-  const int64_t u0 = total * bid / G, u1 = total * (bid + 1) / G;
+  // equal shares of COST: every tile carries sk_head extra k-blocks (fix-up
+  // + epilogue) that are charged to whoever runs its first k-block
+  const int64_t H = p.sk_head, span = nkbT + H, total_cost = tiles * span;
+  auto start = [&](int c) -> int64_t {
+    const int64_t x = total_cost * c / G, t = x / span;
+    return t * nkbT + max(x - t * span - H, (int64_t)0);
+  };
+  const int64_t u0 = start(bid), u1 = start(bid + 1);
   double *part = p.partial;
-  int *flags = reinterpret_cast<int *>(p.partial + (size_t)G * (BM * BN));
+  int *flags = p.flags;
+  int seg = 0;
   for (int64_t u = u0; u < u1;) {
     const int64_t tile = u / nkbT, kb0 = u - tile * nkbT;
     const int64_t kb1 = min(nkbT, kb0 + (u1 - u));
-    SkSeg sk{0, bid, 0, 0, part, flags};
+    SkSeg sk{0, bid, 0, 0, part, flags, seg++};
     if (kb0 > 0) sk.mode = 1;
     else if (kb1 < nkbT) {
       // peers: CTAs after this one whose range starts inside this tile
       sk.mode = 2;
       sk.peer0 = bid + 1;
       int c = bid + 1;
-      while (c < G && total * c / G < (tile + 1) * nkbT) ++c;
+      while (c < G && start(c) < (tile + 1) * nkbT) ++c;
       sk.peer1 = c;
     }
-    contract_tile<BM, BN, BK, WARPS_M, WARPS_N, STAGES, CPLX>(
+    contract_tile<BM, BN, BK, WARPS_M, WARPS_N, STAGES, CPLX, LA, LB>(
         p, (int)tile, 0, 0, kb0 * BK, min(Kh, kb1 * BK), sk);
     u += kb1 - kb0;
     __syncthreads();  // shared memory is reused by the next segment
@@ -522,11 +565,40 @@ __global__ void splitk_reduce_f64_kernel(const __grid_constant__ ContractParams 
   }
 }
 
+// Launch with programmatic stream serialisation: the CTAs of this kernel may
+// become resident while the previous kernel in the stream drains (they build
+// their offset tables, then block in griddepcontrol.wait until it has
+// completed and flushed), which hides the launch latency between the
+// back-to-back contractions of a tree / an MPS sweep.
+template <typename Kern>
+static int launch_pdl(Kern kern, dim3 grid, int threads, size_t smem, cudaStream_t st,
+                      const ContractParams &p) {
+  static const bool pdl = [] {
+    const char *e = getenv("QB_PDL");
+    return e ? atoi(e) != 0 : true;
+  }();
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(st, &cap);
+  if (pdl && cap == cudaStreamCaptureStatusNone) {
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+  }
+  QB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, p));
+  QB_LAUNCH_CHECK();
+  return 0;
+}
+
 template <int BM, int BN, int BK, int WARPS_M, int WARPS_N, int STAGES,
-          bool CPLX>
+          bool CPLX, int LA = -1, int LB = -1, int DBG = 0>
 static int launch_cfg(const ContractParams &p, cudaStream_t st) {
   using Cfg = KernelCfg<BM, BN, BK, WARPS_M, WARPS_N, STAGES>;
-  auto kern = contract_f64_kernel<BM, BN, BK, WARPS_M, WARPS_N, STAGES, CPLX>;
+  auto kern = contract_f64_kernel<BM, BN, BK, WARPS_M, WARPS_N, STAGES, CPLX, LA, LB, DBG>;
   static bool attr_set = false;
   if (!attr_set) {
     QB_CUDA_CHECK(cudaFuncSetAttribute(
@@ -539,15 +611,30 @@ static int launch_cfg(const ContractParams &p, cudaStream_t st) {
   }
   dim3 grid((unsigned)((int64_t)p.tiles_m * p.tiles_n), (unsigned)p.nbatch,
             (unsigned)p.splitk);
-  kern<<<grid, Cfg::NT, Cfg::SMEM, st>>>(p);
-  QB_LAUNCH_CHECK();
-  return 0;
+  return launch_pdl(kern, grid, Cfg::NT, Cfg::SMEM, st, p);
 }
 
-template <bool CPLX>
-static int launch_streamk(const PairPlan &plan, cudaStream_t st) {
-  using Cfg = KernelCfg<128, 128, 16, 4, 4, 4>;
-  auto kern = contract_f64_streamk_kernel<128, 128, 16, 4, 4, 4, CPLX>;
+// layout of the operand tiles in shared memory ([row][k] = "k-major"); for
+// real operands the big-tile kernels are specialised on it so that every
+// fragment address is base + immediate
+static inline int a_kmajor(const ContractParams &p) {
+  return (p.vecA == 2) || (p.vecA == 0 && p.thrA == 1);
+}
+static inline int b_kmajor(const ContractParams &p) {
+  return (p.vecB == 2) || (p.vecB == 0 && p.thrB == 1);
+}
+static inline bool layout_spec() {
+  static const bool on = [] {
+    const char *e = getenv("QB_LAYOUT_SPEC");
+    return e ? atoi(e) != 0 : true;
+  }();
+  return on;
+}
+
+template <bool CPLX, int LA, int LB, int BK = 16, int STAGES = 4>
+static int launch_streamk_l(const PairPlan &plan, cudaStream_t st) {
+  using Cfg = KernelCfg<128, 128, BK, 4, 4, STAGES>;
+  auto kern = contract_f64_streamk_kernel<128, 128, BK, 4, 4, STAGES, CPLX, LA, LB>;
   static bool attr_set = false;
   if (!attr_set) {
     QB_CUDA_CHECK(cudaFuncSetAttribute(
@@ -555,11 +642,48 @@ static int launch_streamk(const PairPlan &plan, cudaStream_t st) {
     attr_set = true;
   }
   const int G = plan.streamk;
-  int *flags = reinterpret_cast<int *>(plan.p.partial + (size_t)G * (128 * 128));
-  QB_CUDA_CHECK(cudaMemsetAsync(flags, 0, sizeof(int) * G, st));
-  kern<<<G, Cfg::NT, Cfg::SMEM, st>>>(plan.p);
-  QB_LAUNCH_CHECK();
-  return 0;
+  if (!plan.flags_clean)
+    QB_CUDA_CHECK(cudaMemsetAsync(plan.p.flags, 0, sizeof(int) * G, st));
+  return launch_pdl(kern, dim3(G), Cfg::NT, Cfg::SMEM, st, plan.p);
+}
+
+template <bool CPLX>
+static int launch_streamk(const PairPlan &plan, cudaStream_t st) {
+  const bool bk32 = cfg0_bk() == 32;
+  if (!CPLX && layout_spec()) {
+    switch (a_kmajor(plan.p) * 2 + b_kmajor(plan.p) + (bk32 ? 4 : 0)) {
+      case 0: return launch_streamk_l<false, 0, 0>(plan, st);
+      case 1: return launch_streamk_l<false, 0, 1>(plan, st);
+      case 2: return launch_streamk_l<false, 1, 0>(plan, st);
+      case 3: return launch_streamk_l<false, 1, 1>(plan, st);
+      case 4: return launch_streamk_l<false, 0, 0, 32, 3>(plan, st);
+      case 5: return launch_streamk_l<false, 0, 1, 32, 3>(plan, st);
+      case 6: return launch_streamk_l<false, 1, 0, 32, 3>(plan, st);
+      default: return launch_streamk_l<false, 1, 1, 32, 3>(plan, st);
+    }
+  }
+  if (bk32) return launch_streamk_l<CPLX, -1, -1, 32, 3>(plan, st);
+  return launch_streamk_l<CPLX, -1, -1>(plan, st);
+}
+
+template <bool CPLX>
+static int launch_cfg0(const ContractParams &p, cudaStream_t st) {
+  if (!CPLX) {
+    if (layout_spec()) {
+      switch (a_kmajor(p) * 2 + b_kmajor(p) + (cfg0_bk() == 32 ? 4 : 0)) {
+        case 0: return launch_cfg<128, 128, 16, 4, 4, 4, false, 0, 0>(p, st);
+        case 1: return launch_cfg<128, 128, 16, 4, 4, 4, false, 0, 1>(p, st);
+        case 2: return launch_cfg<128, 128, 16, 4, 4, 4, false, 1, 0>(p, st);
+        case 3: return launch_cfg<128, 128, 16, 4, 4, 4, false, 1, 1>(p, st);
+        case 4: return launch_cfg<128, 128, 32, 4, 4, 3, false, 0, 0>(p, st);
+        case 5: return launch_cfg<128, 128, 32, 4, 4, 3, false, 0, 1>(p, st);
+        case 6: return launch_cfg<128, 128, 32, 4, 4, 3, false, 1, 0>(p, st);
+        default: return launch_cfg<128, 128, 32, 4, 4, 3, false, 1, 1>(p, st);
+      }
+    }
+  }
+  if (cfg0_bk() == 32) return launch_cfg<128, 128, 32, 4, 4, 3, CPLX>(p, st);
+  return launch_cfg<128, 128, 16, 4, 4, 4, CPLX>(p, st);
 }
 
 template <bool CPLX>
@@ -568,7 +692,7 @@ static int launch_contract_t(const PairPlan &plan, cudaStream_t st) {
   if (plan.streamk > 0 && p.partial) return launch_streamk<CPLX>(plan, st);
   int rc;
   switch (plan.cfg) {
-    case 0: rc = launch_cfg<128, 128, 16, 4, 4, 4, CPLX>(p, st); break;
+    case 0: rc = launch_cfg0<CPLX>(p, st); break;
     case 1: rc = launch_cfg<64, 64, 16, 2, 2, 4, CPLX>(p, st); break;
     case 2: rc = launch_cfg<128, 32, 16, 4, 1, 4, CPLX>(p, st); break;
     case 3: rc = launch_cfg<32, 128, 16, 1, 4, 4, CPLX>(p, st); break;

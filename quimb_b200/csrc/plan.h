@@ -50,6 +50,13 @@ struct ContractParams {
   int32_t tiles_m, tiles_n;
   // C = alpha * A.B + beta * C   (real scalars; beta != 0 reads C)
   double alpha, beta;
+  // stream-K: per-CTA "partial parked" flags (self-resetting: zero between
+  // launches) and the cost, in k-blocks, charged to the CTA that owns a tile's
+  // fix-up + epilogue when the iteration space is cut into equal shares
+  int *flags;
+  int32_t sk_head;
+  // tuning (QB_TRACE=1): per-CTA globaltimer stamps of the kernel phases
+  unsigned long long *trace;
 };
 
 struct PairPlan {
@@ -57,6 +64,7 @@ struct PairPlan {
   int dtype;
   int cfg;           // tile configuration id
   int streamk;       // >0: persistent stream-K launch with this many CTAs
+  bool flags_clean;  // caller keeps the flag words zero between launches
   bool empty_out;    // output has zero elements
   bool zero_fill;    // contracted extent is zero -> C = 0
   int64_t out_elems;
@@ -107,6 +115,22 @@ static const TileCfg kTileCfgs[] = {
     {32, 32, 16, 64},     // 4: small
 };
 constexpr int kNumTileCfgs = 5;
+
+// k-depth of the large tile: 32 (3 stages) or 16 (4 stages); QB_CFG0_BK
+// overrides for tuning
+inline int cfg0_bk() {
+  static const int v = [] {
+    const char *e = getenv("QB_CFG0_BK");
+    int b = e ? atoi(e) : 32;
+    return (b == 16) ? 16 : 32;
+  }();
+  return v;
+}
+inline TileCfg tile_cfg(int c) {
+  TileCfg t = kTileCfgs[c];
+  if (c == 0) t.bk = cfg0_bk();
+  return t;
+}
 
 inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
@@ -311,7 +335,7 @@ inline int plan_pair(const qb_tensor_t *A, const int32_t *la,
   int64_t best_kper = 0;
   for (int c = 0; c < kNumTileCfgs; ++c) {
     if (force_cfg >= 0 && force_cfg < kNumTileCfgs && c != force_cfg) continue;
-    const TileCfg &tc = kTileCfgs[c];
+    const TileCfg tc = tile_cfg(c);
     const int64_t tiles = cdiv(M, tc.bm) * cdiv(N, tc.bn) * p.nbatch;
     const int64_t kblocks = std::max<int64_t>(cdiv(Kh, tc.bk), 1);
     const int64_t slots = 148LL * kOcc[c];
@@ -339,7 +363,7 @@ inline int plan_pair(const qb_tensor_t *A, const int32_t *la,
   }
   cfg = best_cfg;
   plan.cfg = cfg;
-  const TileCfg &tc = kTileCfgs[cfg];
+  const TileCfg tc = tile_cfg(cfg);
   p.tiles_m = (int32_t)cdiv(M, tc.bm);
   p.tiles_n = (int32_t)cdiv(N, tc.bn);
   p.splitk = best_split;
@@ -347,6 +371,7 @@ inline int plan_pair(const qb_tensor_t *A, const int32_t *la,
   // stream-K (large tile only): when the tile count leaves SMs idle in the
   // last wave, cut the (tile, k-block) space into one equal range per SM
   plan.streamk = 0;
+  plan.flags_clean = false;
   {
     static const int sk_env = [] {
       const char *e = getenv("QB_STREAMK");
@@ -361,17 +386,37 @@ inline int plan_pair(const qb_tensor_t *A, const int32_t *la,
       plan.streamk = G;
       p.splitk = 1;
       p.k_per_split = kblocks * tc.bk;
+      // fix-up (wait + collect the peers' partial tiles) + epilogue of a
+      // shared tile cost its owner ~9 us = this many k-blocks (measured with
+      // the in-kernel trace); it gets that much less of the main loop
+      static const int head_us = [] {
+        const char *e = getenv("QB_SK_HEAD_US");
+        return e ? atoi(e) : 9;
+      }();
+      const double kb_us = (double)tc.bm * tc.bn * tc.bk / (64.0 * 0.9) / 1965.0;
+      int64_t H = (int64_t)(head_us / kb_us + 0.5);
+      const int64_t share = tiles * (kblocks + H) / G;
+      if (H >= share / 2) H = 0;
+      p.sk_head = (int32_t)H;
     }
   }
   return 0;
 }
 
-inline int64_t plan_workspace_bytes(const PairPlan &plan) {
+// scratch for partial sums (stream-K parked tiles / split-K partial outputs)
+inline int64_t plan_scratch_bytes(const PairPlan &plan) {
   if (plan.streamk > 0)
-    return (int64_t)plan.streamk * (128 * 128 * 8 + 64);  // partial tiles + flags
+    return (int64_t)plan.streamk * (128 * 128 * 8);
   if (plan.p.splitk <= 1) return 0;
   return (int64_t)plan.p.splitk * plan.p.nbatch * plan.p.M * plan.p.N * 8 *
          (dtype_is_complex(plan.dtype) ? 2 : 1);
+}
+// caller-visible workspace: a 1 KiB header (stream-K flag words, kept zero
+// between launches) followed by the scratch
+constexpr int64_t kWsHeaderBytes = 1024;
+inline int64_t plan_workspace_bytes(const PairPlan &plan) {
+  const int64_t s = plan_scratch_bytes(plan);
+  return s > 0 ? s + kWsHeaderBytes : 0;
 }
 
 #ifdef __CUDACC__

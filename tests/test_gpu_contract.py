@@ -245,6 +245,19 @@ def test_batched_small_contractions_one_launch():
         qb.contract_batched(ta, [0, 1, 2], tb[:-1], [2, 1, 3], [3, 0])
 
 
+def test_batched_complex_full_contracted_extent():
+    """pointer-array batches of complex128 pairs sum over the whole contracted
+    extent (the kernel counts k in real units: 2 per complex element)."""
+    rng = np.random.default_rng(13)
+    n = 9
+    As = [rng.standard_normal((5, 40)) + 1j * rng.standard_normal((5, 40)) for _ in range(n)]
+    Bs = [rng.standard_normal((40, 6)) + 1j * rng.standard_normal((40, 6)) for _ in range(n)]
+    outs = qb.contract_batched([qb.asarray(a).t for a in As], [0, 1],
+                               [qb.asarray(b).t for b in Bs], [1, 2], [0, 2])
+    for a, b, o in zip(As, Bs, outs):
+        np.testing.assert_allclose(o.cpu().numpy(), a @ b, atol=1e-12)
+
+
 @pytest.mark.parametrize("dtype,tol", [("float32", 2e-6), ("complex64", 2e-6)])
 def test_single_precision_dtype_preserved(dtype, tol):
     """f32 / c64 in -> same dtype out (reference: test_dmrg.py:290-300 dtype
