@@ -244,8 +244,32 @@ def contract_pair(a, ia, b, ib, iout):
     return np.einsum(eq, a, b)
 
 
-def array_contract(arrays, inputs, output, optimize="auto", size_dict=None):
-    """Contract ``arrays`` labelled by ``inputs`` into ``output`` order."""
+def array_contract(arrays, inputs, output, optimize="auto", size_dict=None,
+                   strip_exponent=False):
+    """Contract ``arrays`` labelled by ``inputs`` into ``output`` order.
+
+    ``strip_exponent`` (tensor_core.py:330-336; executed by cotengra, absent
+    offline -- its published behaviour restated): every intermediate is
+    divided by its largest magnitude, the log10 of the factors accumulated;
+    returns ``(mantissa, exponent)`` with result = mantissa * 10**exponent."""
+    if strip_exponent:
+        expo = [0.0]
+
+        def strip(x):
+            x = np.asarray(x)
+            f = np.max(np.abs(x)) if x.size else 1.0
+            expo[0] = expo[0] + np.log10(f)
+            return x / f
+    else:
+        def strip(x):
+            return x
+    res = _array_contract(arrays, inputs, output, optimize, size_dict, strip)
+    if strip_exponent:
+        return res, float(expo[0])
+    return res
+
+
+def _array_contract(arrays, inputs, output, optimize, size_dict, strip):
     arrays = list(arrays)
     terms = [tuple(t) for t in inputs]
     output = tuple(output)
@@ -257,27 +281,40 @@ def array_contract(arrays, inputs, output, optimize="auto", size_dict=None):
     if len(arrays) == 1:
         (x,), (t,) = arrays, terms
         if t == output:
-            return x
+            return strip(x)
         if len(set(t)) == len(t) and set(t) == set(output):
-            return np.transpose(x, [t.index(ix) for ix in output])
+            return strip(np.transpose(x, [t.index(ix) for ix in output]))
         eq_in = "".join(chr(97 + list(dict.fromkeys(t)).index(i)) for i in t)
         eq_out = "".join(chr(97 + list(dict.fromkeys(t)).index(i)) for i in output)
-        return np.einsum(f"{eq_in}->{eq_out}", x)
+        return strip(np.einsum(f"{eq_in}->{eq_out}", x))
     path = find_path(terms, output, size_dict, optimize)
     for i, j in path:
         need = _needed_elsewhere(terms, (i, j), output)
         last = len(terms) == 2
         res_inds = output if last else _pair_result(terms[i], terms[j], need)
-        res = contract_pair(arrays[i], terms[i], arrays[j], terms[j], res_inds)
+        res = strip(contract_pair(arrays[i], terms[i], arrays[j], terms[j], res_inds))
         arrays = [x for k, x in enumerate(arrays) if k not in (i, j)] + [res]
         terms = [t for k, t in enumerate(terms) if k not in (i, j)] + [res_inds]
     return arrays[0]
 
 
-def tensor_contract(arrays, inds, output_inds=None, optimize="auto"):
-    """(data, inds_out) of quimb.tensor.tensor_contract for raw arrays."""
+def tensor_contract(arrays, inds, output_inds=None, optimize="auto",
+                    strip_exponent=False, exponent=None):
+    """(data, inds_out) of quimb.tensor.tensor_contract for raw arrays; with
+    ``strip_exponent``: ((mantissa, exponent), inds_out); a supplied base
+    ``exponent`` is added to the stripped one, or scales the plain result by
+    10**exponent (tensor_core.py:330-341)."""
     if output_inds is None:
         inds_out = gen_output_inds(itertools.chain.from_iterable(inds))
     else:
         inds_out = tuple(output_inds)
-    return array_contract(arrays, inds, inds_out, optimize=optimize), inds_out
+    out = array_contract(arrays, inds, inds_out, optimize=optimize,
+                         strip_exponent=strip_exponent)
+    if strip_exponent:
+        data, e = out
+        if exponent is not None:
+            e = e + exponent
+        return (data, e), inds_out
+    if exponent is not None:
+        out = out * 10**exponent
+    return out, inds_out

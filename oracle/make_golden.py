@@ -69,6 +69,16 @@ def contract_cases():
             "result_inds": list(res.inds),
             "dtype": dtype,
         }
+        # strip_exponent (+ a base exponent) through the reference's
+        # tensor_contract (tensor_core.py:330-341)
+        if name in ("three", "env4", "cplx_pair", "scalar", "order_out"):
+            big = [qtn.Tensor(t.data * (10.0 ** (40 * (k + 1))), inds=t.inds)
+                   for k, t in enumerate(ts)]
+            rs, ex = qtn.tensor_contract(*big, preserve_tensor=True, strip_exponent=True,
+                                         exponent=2.5, **kw)
+            store[f"{name}__strip_mantissa"] = np.asarray(rs.data)
+            meta[name]["strip"] = {"exponent": float(ex), "base_exponent": 2.5,
+                                   "input_scales": [40 * (k + 1) for k in range(len(ts))]}
     # error behaviour: index appearing three times without output_inds
     try:
         qtn.tensor_contract(qtn.rand_tensor((2, 2), "ab"), qtn.rand_tensor((2, 2), "bc"),

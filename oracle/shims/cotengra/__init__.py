@@ -133,11 +133,8 @@ def array_contract(arrays, inputs, output=None, optimize="auto", backend=None,
     if output is None:
         output = _cn.gen_output_inds(ix for t in inputs for ix in t)
     path = _resolve(optimize, inputs, tuple(output), size_dict)
-    out = _cn.array_contract(arrays, inputs, tuple(output), optimize=path,
-                             size_dict=size_dict)
-    if strip_exponent:
-        return _strip(out)
-    return out
+    return _cn.array_contract(arrays, inputs, tuple(output), optimize=path,
+                              size_dict=size_dict, strip_exponent=strip_exponent)
 
 
 def array_contract_expression(inputs, output=None, size_dict=None, shapes=None,

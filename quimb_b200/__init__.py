@@ -22,7 +22,7 @@ from . import linalg  # noqa: F401
 from .contract import contract_batched, contract_pair, plan_pair  # noqa: F401
 from . import dist  # noqa: F401
 from .tree import (ContractExpression, GraphedContraction, Tree,  # noqa: F401
-                   array_contract, find_tree, gen_output_inds)
+                   array_contract, find_tree, gen_output_inds, tensor_contract)
 from .mps import (env_left_step, env_right_step, mps_expec, mps_norm,  # noqa: F401
                   mps_norm2)
 from .split import (array_split, qr_stabilized, svd_truncated,  # noqa: F401

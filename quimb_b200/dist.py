@@ -12,7 +12,13 @@ this path are *independent units with a single exchange at the end*:
   * independent networks (many MPS norms / amplitudes): pure replicas.
 
 The DMRG chain itself is sequential (each environment depends on the
-previous one, dmrg.py:297-301); it is not sharded in round 1.
+previous one, dmrg.py:297-301), but its dominant cost -- the Lanczos matvecs
+of the two-site eigensolve -- shards over the left bond with ONE exchange
+step per matvec (``BondShard``): rank r owns the row slab a' in [lo_r, hi_r)
+of the left environment L[a', w, a] and of every Krylov vector, all-gathers
+the input vector (32 MiB at chi = 1024) and all-reduces the handful of inner
+products of the re-orthogonalisation.  Everything else of the sweep (SVD,
+environment updates) is replicated deterministically on every rank.
 """
 
 import itertools
@@ -103,3 +109,63 @@ def _finish(total, arrays, inputs, output, size_dict):
     t = t.contiguous()
     all_reduce_sum(t)
     return t
+
+
+class BondShard:
+    """Row-slab sharding of a bond of size ``n`` over the ranks of a process
+    group: the exchange layer of the sharded two-site eigensolve.
+
+    NCCL moves device tensors directly over NVLink; with the gloo backend
+    (CPU tests, or several ranks sharing one GPU in the single-GPU test) the
+    collectives are staged through host memory.
+    """
+
+    def __init__(self, group=None, rank=None, world_size=None):
+        self.group = group
+        if rank is None or world_size is None:
+            rank, world_size = world()
+        self.rank, self.world_size = int(rank), int(world_size)
+        self.active = (dist.is_available() and dist.is_initialized()
+                       and self.world_size > 1)
+        self._stage = self.active and dist.get_backend(group) != "nccl"
+        self.bytes_gathered = 0
+
+    def slab(self, n, rank=None):
+        """[lo, hi) of this rank's rows of a bond of size ``n`` (balanced)."""
+        r = self.rank if rank is None else rank
+        return (n * r) // self.world_size, (n * (r + 1)) // self.world_size
+
+    def all_reduce_(self, t):
+        if not self.active:
+            return t
+        if self._stage and t.device.type != "cpu":
+            h = t.cpu()
+            dist.all_reduce(h, op=dist.ReduceOp.SUM, group=self.group)
+            t.copy_(h)
+        else:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return t
+
+    def all_gather_rows(self, local, n):
+        """Concatenate the row slabs ``local`` (rows_r, cols) of all ranks into
+        the full (n, cols) matrix, identical on every rank."""
+        cols = local.shape[1]
+        if not self.active:
+            return local
+        full = torch.empty((n, cols), dtype=local.dtype, device=local.device)
+        self.bytes_gathered += full.numel() * full.element_size()
+        even = n % self.world_size == 0
+        if even and not self._stage:
+            dist.all_gather_into_tensor(full, local.contiguous(), group=self.group)
+            return full
+        # ragged slabs / staged backend: pad every slab to the largest one
+        rows = max(self.slab(n, r)[1] - self.slab(n, r)[0] for r in range(self.world_size))
+        src = local.cpu() if self._stage else local
+        pad = torch.zeros((rows, cols), dtype=src.dtype, device=src.device)
+        pad[: src.shape[0]].copy_(src)
+        parts = [torch.empty_like(pad) for _ in range(self.world_size)]
+        dist.all_gather(parts, pad, group=self.group)
+        for r, part in enumerate(parts):
+            lo, hi = self.slab(n, r)
+            full[lo:hi].copy_(part[: hi - lo])
+        return full

@@ -100,11 +100,53 @@ class EffHam2:
                     + ap * s * b * w1 * t * w2 * t + ap * s * t * b * w2 * bp)
 
 
+class ShardedEffHam2(EffHam2):
+    """Bond-sharded matvec: this rank holds the rows
+    a' in [lo, hi) of L[a', w, a] and of the vector.  One all-gather of the
+    input vector per matvec; the three contraction steps are local in a'."""
+
+    def __init__(self, Lenv, W1, W2, Renv, dims, shard):
+        super().__init__(Lenv, W1, W2, Renv, dims)
+        self.shard = shard
+        self.lo, self.hi = shard.slab(dims[0])
+        self.Ls = Array(self.L.t[self.lo:self.hi], self.L.cj)
+        self.cols = dims[1] * dims[2] * dims[3]
+
+    def local_slab(self, v):
+        """Rows [lo, hi) of a full vector, as a flat contiguous Array."""
+        x = ops.materialize(v).reshape(self.dims[0], self.cols)
+        return Array(x.t[self.lo:self.hi].contiguous()).reshape(-1)
+
+    def gather(self, v_local):
+        x = ops.materialize(v_local).t.reshape(self.hi - self.lo, self.cols)
+        return Array(self.shard.all_gather_rows(x, self.dims[0])).reshape(-1)
+
+    def matvec(self, v_local):
+        self.nmatvec += 1
+        x = self.gather(v_local).reshape(self.dims)
+        T = contract_pair(self.Ls.t, [LB_, W_, L_], x.t, [L_, S_, T_, R_],
+                          [LB_, W_, S_, T_, R_], conj_a=self.Ls.cj, conj_b=x.cj)
+        T = contract_pair(T, [LB_, W_, S_, T_, R_], self.W12,
+                          [W_, S_, T_, W2_, SB_, TB_], [LB_, SB_, TB_, W2_, R_])
+        y = contract_pair(T, [LB_, SB_, TB_, W2_, R_], self.R.t,
+                          [RB_, W2_, R_], [LB_, SB_, TB_, RB_], conj_b=self.R.cj)
+        return Array(y).reshape(-1)
+
+    __call__ = matvec
+
+
 class DMRG2:
-    """Two-site DMRG for an open-boundary MPO, on the device."""
+    """Two-site DMRG for an open-boundary MPO, on the device.
+
+    ``shard`` (a ``quimb_b200.dist.BondShard``): run the local eigensolves
+    row-sharded over the ranks of the process group (every rank constructs the
+    same DMRG2 with the same inputs and seed; the rest of the sweep is
+    replicated and bit-identical on all ranks)."""
 
     def __init__(self, ham, bond_dims, cutoffs=1e-8, which="SA", p0=None,
-                 mpo_shape="lrud", mps_shape="lpr", seed=None, dtype=None):
+                 mpo_shape="lrud", mps_shape="lpr", seed=None, dtype=None, shard=None):
+        self.shard = shard if (shard is not None and shard.active) else None
+        self.shard_min_bond = 64
         self.L = len(ham)
         n = self.L
         self.which = which
@@ -197,13 +239,13 @@ class DMRG2:
             self.lenv[i + 1] = env_left_step(self.lenv[i], self._k[i], self.ham[i])
 
     # ---- local update (dmrg.py:803-870) --------------------------------------
-    def _eigs(self, Heff, v0):
+    def _eigs(self, Heff, v0, comm=None):
         backend = self.opts["local_eig_backend"]
         if backend == "SCIPY":
             return eigh_arpack_host_driver(Heff, v0, which=self.which,
                                            ncv=self.opts["local_eig_ncv"],
                                            tol=self.opts["local_eig_tol"])
-        n = v0.size
+        n = v0.size if comm is None else Heff.dims[0] * Heff.cols
         ncv = self.opts["device_eig_ncv"]
         tol = self.opts["local_eig_tol"]
         if n < 800:
@@ -212,7 +254,7 @@ class DMRG2:
             ncv, tol = min(n, 16), 1e-12
         return eigh_lanczos(Heff, v0, which=self.which, ncv=ncv, tol=tol,
                             maxiter=self.opts["local_eig_maxiter"],
-                            return_info=True)
+                            return_info=True, comm=comm)
 
     def _update_local_state_2site(self, i, direction, max_bond=None,
                                   cutoff=1e-10, cutoff_mode="sum2",
@@ -226,7 +268,15 @@ class DMRG2:
         # old two-site tensor as the initial guess (dmrg.py:832)
         v0 = Array(contract_pair(A.t, [L_, S_, 9], B.t, [9, T_, R_],
                                  [L_, S_, T_, R_], conj_a=A.cj, conj_b=B.cj))
-        loc_en, loc_gs, info = self._eigs(Heff, v0)
+        if (self.shard is not None and self.opts["local_eig_backend"] is None
+                and a >= self.shard_min_bond * self.shard.world_size):
+            Hs = ShardedEffHam2(self.lenv[i], self.ham[i], self.ham[i + 1],
+                                self.renv[i + 1], dims, self.shard)
+            loc_en, gs_local, info = self._eigs(Hs, Hs.local_slab(v0), comm=self.shard)
+            loc_gs = Hs.gather(gs_local)
+            Heff.nmatvec = Hs.nmatvec
+        else:
+            loc_en, loc_gs, info = self._eigs(Heff, v0)
         self.nmatvecs.append(Heff.nmatvec)
         mat = loc_gs.reshape(a * s, t * b)
         absorb = get_U_sVH if direction == "right" else get_Us_VH

@@ -48,8 +48,20 @@ def _md_ws(dev):
     return ws
 
 
-def _orthogonalise(V, j, w, h):
-    """Two classical Gram-Schmidt passes of w against V[0..j] (in place)."""
+def _norm_c(x, comm):
+    """2-norm of a (possibly row-sharded) vector as a 0-d device Array."""
+    if comm is None:
+        return _norm(x)
+    flat = ops.materialize(x).reshape(-1)
+    n2 = ops.real(ops.vdot(flat, flat))
+    comm.all_reduce_(n2.t)
+    return ops.sqrt(n2)
+
+
+def _orthogonalise(V, j, w, h, comm=None):
+    """Two classical Gram-Schmidt passes of w against V[0..j] (in place).
+    With ``comm`` the vectors are row slabs: the m dot products are summed
+    over the ranks (one tiny all-reduce per pass)."""
     lib = _lib.load()
     m, n = j + 1, w.numel()
     st = _lib.stream_ptr()
@@ -58,13 +70,15 @@ def _orthogonalise(V, j, w, h):
         rc = lib.qb_multi_dot(_lib.QB_F64, m, n, V.data_ptr(), V.stride(0),
                               w.data_ptr(), h.data_ptr(), ws, st)
         _lib.check(rc, "qb_multi_dot")
+        if comm is not None:
+            comm.all_reduce_(h)
         rc = lib.qb_multi_axpy(_lib.QB_F64, m, n, V.data_ptr(), V.stride(0),
                                h.data_ptr(), -1.0, w.data_ptr(), st)
         _lib.check(rc, "qb_multi_axpy")
 
 
 def eigh_lanczos(matvec, v0, which="SA", ncv=4, tol=1e-3, maxiter=None,
-                 return_info=False):
+                 return_info=False, comm=None):
     """Lowest ('SA') or highest ('LA') eigenpair of a Hermitian operator.
 
     Parameters
@@ -75,6 +89,10 @@ def eigh_lanczos(matvec, v0, which="SA", ncv=4, tol=1e-3, maxiter=None,
         Start vector (any shape, flattened).
     ncv : int
         Krylov basis size between restarts (2 <= ncv <= 16).
+    comm : object with ``all_reduce_(tensor)``, optional
+        Row-sharded mode (quimb_b200.dist.BondShard): ``v0`` and every vector
+        handed to / returned by ``matvec`` is this rank's slab; inner products
+        are summed over the ranks, all ranks take identical decisions.
     Returns ``(theta: float, x: Array[n])`` (+ info dict).
     """
     v0 = ops.materialize(ops.asarray(v0)).reshape(-1)
@@ -90,7 +108,7 @@ def eigh_lanczos(matvec, v0, which="SA", ncv=4, tol=1e-3, maxiter=None,
 
         vr0 = Array(torch.view_as_real(v0.t).reshape(-1))
         theta, xr, info = eigh_lanczos(mv_real, vr0, which=which, ncv=ncv, tol=tol,
-                                       maxiter=maxiter, return_info=True)
+                                       maxiter=maxiter, return_info=True, comm=comm)
         x = Array(torch.view_as_complex(xr.t.reshape(-1, 2)))
         return (theta, x, info) if return_info else (theta, x)
     n = v0.size
@@ -105,11 +123,11 @@ def eigh_lanczos(matvec, v0, which="SA", ncv=4, tol=1e-3, maxiter=None,
     V = torch.zeros((m, n), dtype=dt, device=dev)
     W = torch.empty((m, n), dtype=dt, device=dev)
     w = torch.empty((n,), dtype=dt, device=dev)
-    h = torch.empty((16,), dtype=dt, device=dev)
+    h = torch.zeros((16,), dtype=dt, device=dev)
     eps23 = np.finfo(np.float64).eps ** (2.0 / 3.0)
     sign = 1.0 if which in ("SA", "SR") else -1.0
 
-    nrm = _norm(v0)
+    nrm = _norm_c(v0, comm)
     V[0].copy_(v0.t)
     ops.scale_(Array(V[0]), 1.0, div_by=nrm)
     have_w0 = False
@@ -129,12 +147,14 @@ def eigh_lanczos(matvec, v0, which="SA", ncv=4, tol=1e-3, maxiter=None,
                 W[j].copy_(ops.materialize(Wj).t.reshape(-1))
             if j + 1 < m:
                 w.copy_(W[j])
-                _orthogonalise(V, j, w, h)
-                bnorm = _norm(Array(w))
+                _orthogonalise(V, j, w, h, comm)
+                bnorm = _norm_c(Array(w), comm)
                 V[j + 1].copy_(w)
                 ops.scale_(Array(V[j + 1]), 1.0, div_by=bnorm)
         # projected matrix (m x m): host read #1 of the cycle
         Hm = contract_pair(V[:m], [_J, _N], W[:m], [2, _N], [_J, 2])
+        if comm is not None:
+            comm.all_reduce_(Hm)
         Hh = Hm.cpu().numpy()
         Hh = 0.5 * (Hh + Hh.T)
         evals, evecs = np.linalg.eigh(sign * Hh)
@@ -157,14 +177,14 @@ def eigh_lanczos(matvec, v0, which="SA", ncv=4, tol=1e-3, maxiter=None,
         # host read #2
         w.copy_(hx)
         ops.axpby(-theta, Array(xnew), 1.0, Array(w))
-        resid = float(_norm(Array(w)).item())
+        resid = float(_norm_c(Array(w), comm).item())
         info["restarts"] = cycle
         if resid <= tol * max(eps23, abs(theta)) or not np.isfinite(resid):
             info["converged"] = bool(np.isfinite(resid))
             x = Array(xnew)
             break
         # restart from the Ritz vector; its image is known
-        xn = _norm(Array(xnew))
+        xn = _norm_c(Array(xnew), comm)
         V[0].copy_(xnew)
         ops.scale_(Array(V[0]), 1.0, div_by=xn)
         W[0].copy_(hx)
@@ -172,7 +192,7 @@ def eigh_lanczos(matvec, v0, which="SA", ncv=4, tol=1e-3, maxiter=None,
         have_w0 = True
         x = Array(V[0].clone())
     # normalise the Ritz vector
-    xn = _norm(x)
+    xn = _norm_c(x, comm)
     x = ops.scale_(ops.materialize(x, force=True), 1.0, div_by=xn)
     info.update(nmatvec=nmv, resid=resid, theta=theta, ncv=mmax)
     if return_info:

@@ -246,7 +246,43 @@ def _labels(inds, table):
     return [table.setdefault(ix, len(table)) for ix in inds]
 
 
-def execute(tree, arrays):
+class _Exponent:
+    """Running log10 scale of a contraction with ``strip_exponent=True``
+    (quimb tensor_core.py:330-336 -> cotengra: every intermediate is divided
+    by its largest magnitude and the log10 of that factor accumulated).  The
+    factor never leaves the device: ``qb_scale`` divides by a device scalar,
+    the exponent is read once at the end."""
+
+    def __init__(self):
+        self.total = None
+
+    def strip(self, out, own=True):
+        import torch
+        # own=False: `out` aliases a caller's array -> scale a copy
+        out = ops.materialize(ops.asarray(out), force=not own)
+        factor = out.t.abs().amax() if out.t.numel() else None
+        if factor is None:
+            return out
+        if factor.dtype != torch.float64:
+            factor = factor.double()
+        ops.scale_(out, 1.0, div_by=Array(factor))
+        lg = torch.log10(factor)
+        self.total = lg if self.total is None else self.total + lg
+        return out
+
+    def value(self):
+        return 0.0 if self.total is None else float(self.total.item())
+
+
+def execute(tree, arrays, strip_exponent=False):
+    expo = _Exponent() if strip_exponent else None
+    out = _execute(tree, arrays, expo)
+    if expo is not None:
+        return out, expo.value()
+    return out
+
+
+def _execute(tree, arrays, expo):
     table = {}
     nodes = {i: ops.asarray(a) for i, a in enumerate(arrays)}
     inds = dict(enumerate(tree.inputs))
@@ -254,10 +290,11 @@ def execute(tree, arrays):
         (x,) = nodes.values()
         t = inds[0]
         if t == tree.output:
-            return x
+            return x if expo is None else expo.strip(x, own=False)
         one = ops.ones((), dtype=x.dtype, device=x.device)
-        return Array(contract_pair(x.t, _labels(t, table), one.t, [],
-                                   _labels(tree.output, table), conj_a=x.cj))
+        res = Array(contract_pair(x.t, _labels(t, table), one.t, [],
+                                  _labels(tree.output, table), conj_a=x.cj))
+        return res if expo is None else expo.strip(res)
     for i, j, k, res in tree.steps:
         a, b = nodes.pop(i), nodes.pop(j)
         if a.dtype != b.dtype:
@@ -267,7 +304,7 @@ def execute(tree, arrays):
         out = contract_pair(a.t, _labels(inds[i], table), b.t,
                             _labels(inds[j], table), _labels(res, table),
                             conj_a=a.cj, conj_b=b.cj)
-        nodes[k] = Array(out)
+        nodes[k] = Array(out) if expo is None else expo.strip(Array(out))
         inds[k] = res
     (out,) = nodes.values()
     return out
@@ -284,14 +321,42 @@ def _sizes(inputs, arrays):
     return size_dict
 
 
-def array_contract(arrays, inputs, output=None, optimize="auto"):
-    """Contract device arrays labelled by hashable indices."""
+def array_contract(arrays, inputs, output=None, optimize="auto", strip_exponent=False):
+    """Contract device arrays labelled by hashable indices.  With
+    ``strip_exponent`` returns ``(mantissa, exponent)`` with the result equal
+    to ``mantissa * 10**exponent`` and ``max|mantissa| == 1``."""
     arrays = [ops.asarray(a) for a in arrays]
     inputs = [tuple(t) for t in inputs]
     if output is None:
         output = gen_output_inds(itertools.chain.from_iterable(inputs))
     tree = find_tree(inputs, tuple(output), _sizes(inputs, arrays), optimize)
-    return execute(tree, arrays)
+    return execute(tree, arrays, strip_exponent=strip_exponent)
+
+
+def tensor_contract(arrays, inds, output_inds=None, optimize="auto",
+                    strip_exponent=False, exponent=None):
+    """Array-level mirror of ``quimb.tensor.tensor_contract``
+    (tensor_core.py:224-358) for raw device arrays: returns
+    ``(data, inds_out)``; the output indices are those appearing exactly once,
+    in first-appearance order, unless ``output_inds`` is given.  With
+    ``strip_exponent`` the data is ``(mantissa, exponent)``; a base
+    ``exponent`` is added to the stripped one, or multiplies the plain result
+    by ``10**exponent`` (tensor_core.py:330-341)."""
+    inds = [tuple(t) for t in inds]
+    if output_inds is None:
+        inds_out = gen_output_inds(itertools.chain.from_iterable(inds))
+    else:
+        inds_out = tuple(output_inds)
+    out = array_contract(arrays, inds, inds_out, optimize=optimize,
+                         strip_exponent=strip_exponent)
+    if strip_exponent:
+        data, e = out
+        if exponent is not None:
+            e = e + exponent
+        return (data, e), inds_out
+    if exponent is not None:
+        out = ops.scale_(ops.materialize(out, force=True), 10.0 ** exponent)
+    return out, inds_out
 
 
 class ContractExpression:

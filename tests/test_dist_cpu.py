@@ -64,3 +64,48 @@ def test_shard_units_round_robin():
     assert qd.shard_units(10, 3, 4) == [3, 7]
     assert sorted(sum((qd.shard_units(7, r, 3) for r in range(3)), [])) == list(range(7))
     assert qd.shard_units(2, 5, 8) == []
+
+
+def _shard_worker(rank, world, port, ret):
+    """BondShard on gloo: slabs tile the bond, all_gather_rows reassembles even
+    and ragged slabs, and a row-sharded matvec + inner products reproduce the
+    unsharded numbers (numpy stand-in for the device kernels)."""
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from quimb_b200.dist import BondShard
+    sh = BondShard()
+    ok = sh.active and sh.world_size == world
+    rng = np.random.default_rng(1)
+    for n in (8, 7):                              # even and ragged
+        full = torch.from_numpy(rng.standard_normal((n, 5)))
+        lo, hi = sh.slab(n)
+        got = sh.all_gather_rows(full[lo:hi].clone(), n)
+        ok = ok and torch.equal(got, full)
+        # sharded y = H x and <x|y>: slab rows of H, full x, one all-reduce
+        H = torch.from_numpy(rng.standard_normal((n, n))); H = H + H.T
+        x = full[:, 0].clone()
+        y_loc = H[lo:hi] @ sh.all_gather_rows(x[lo:hi].reshape(-1, 1).clone(), n).reshape(-1)
+        dot = (x[lo:hi] * y_loc).sum().reshape(1)
+        sh.all_reduce_(dot)
+        ok = ok and abs(float(dot) - float(x @ H @ x)) < 1e-12
+    slabs = [sh.slab(11, r) for r in range(world)]
+    ok = ok and slabs[0][0] == 0 and slabs[-1][1] == 11 and all(
+        slabs[i][1] == slabs[i + 1][0] for i in range(world - 1))
+    ret[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+def test_bond_shard_gloo_world2():
+    mp.set_start_method("spawn", force=True)
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [mp.Process(target=_shard_worker, args=(r, 2, port, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert ret[0] and ret[1]

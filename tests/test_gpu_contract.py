@@ -46,6 +46,52 @@ def test_golden_contractions(golden_contract):
         _close(out.to_numpy(), data[f"{name}__out"])
 
 
+def test_golden_strip_exponent(golden_contract):
+    """strip_exponent / base exponent of tensor_contract (tensor_core.py:330-341)
+    against the reference-generated mantissas; the scaled inputs (up to 1e160
+    each) overflow double precision without stripping."""
+    data, meta = golden_contract
+    n = 0
+    for name, m in meta.items():
+        if name.startswith("_") or "strip" not in m:
+            continue
+        sc = m["strip"]["input_scales"]
+        arrays = [qb.asarray(data[f"{name}__in{k}"] * 10.0 ** sc[k])
+                  for k in range(len(m["inds"]))]
+        keep = [a.to_numpy().copy() for a in arrays]
+        (mant, e), inds_out = qb.tensor_contract(arrays, [tuple(i) for i in m["inds"]],
+                                                 m["output_inds"], strip_exponent=True,
+                                                 exponent=m["strip"]["base_exponent"])
+        assert list(inds_out) == m["result_inds"]
+        assert e == pytest.approx(m["strip"]["exponent"], abs=1e-8), name
+        ref = data[f"{name}__strip_mantissa"]
+        np.testing.assert_allclose(mant.to_numpy(), ref, rtol=1e-10, atol=1e-12)
+        for a, k in zip(arrays, keep):                   # inputs are never scaled in place
+            np.testing.assert_array_equal(a.to_numpy(), k)
+        n += 1
+    assert n >= 4
+    # plain result scaled by a base exponent
+    x = np.arange(6.0).reshape(2, 3)
+    out, io = qb.tensor_contract([qb.asarray(x), qb.asarray(x.T.copy())], ["ab", "bc"], exponent=2.0)
+    np.testing.assert_allclose(out.to_numpy(), 100.0 * x @ x.T)
+    assert io == ("a", "c")
+
+
+def test_strip_exponent_long_chain_no_overflow():
+    """An unnormalised MPS-norm-like chain whose value (~1e600) is far outside
+    double range: mantissa/exponent agree with the oracle."""
+    rng = np.random.default_rng(3)
+    mats = [rng.standard_normal((24, 24)) * 1e10 for _ in range(60)]
+    inds = [(i, i + 1) for i in range(60)]
+    (mant, e), _ = qb.tensor_contract([qb.asarray(x) for x in mats], inds, strip_exponent=True,
+                                      optimize="greedy")
+    (mo, eo), _ = cn.tensor_contract(mats, inds, strip_exponent=True, optimize="greedy")
+    assert e > 600 and np.isfinite(e)
+    # different trees -> compare the represented value
+    shift = e - eo
+    np.testing.assert_allclose(mant.to_numpy() * 10.0 ** shift, mo, rtol=1e-9, atol=1e-12)
+
+
 CASES = [
     ("ab,bc->ac", dict(a=37, b=45, c=29)),
     ("ab,bc->ac", dict(a=300, b=257, c=190)),

@@ -25,6 +25,32 @@ def test_contract_matches_reference(golden_contract):
         np.testing.assert_allclose(out, ref, rtol=1e-12, atol=1e-12, err_msg=name)
 
 
+def test_strip_exponent_matches_reference(golden_contract):
+    """tensor_contract(strip_exponent=True, exponent=...) (tensor_core.py:330-341):
+    result = mantissa * 10**exponent, the mantissa has unit max-magnitude and
+    the inputs (scaled up to 1e160) would overflow without stripping."""
+    data, meta = golden_contract
+    n = 0
+    for name, m in meta.items():
+        if name.startswith("_") or "strip" not in m:
+            continue
+        sc = m["strip"]["input_scales"]
+        arrays = [data[f"{name}__in{k}"] * 10.0 ** sc[k] for k in range(len(m["inds"]))]
+        inds = [tuple(i) for i in m["inds"]]
+        (mant, e), inds_out = cn.tensor_contract(arrays, inds, m["output_inds"],
+                                                 strip_exponent=True,
+                                                 exponent=m["strip"]["base_exponent"])
+        assert list(inds_out) == m["result_inds"]
+        assert e == pytest.approx(m["strip"]["exponent"], abs=1e-9), name
+        np.testing.assert_allclose(mant, data[f"{name}__strip_mantissa"], rtol=1e-12, atol=1e-13)
+        assert np.max(np.abs(mant)) == pytest.approx(1.0, abs=1e-14)
+        # consistent with the plain contraction of the unscaled inputs
+        np.testing.assert_allclose(mant * 10.0 ** (e - sum(sc) - m["strip"]["base_exponent"]),
+                                   data[f"{name}__out"], rtol=1e-11, atol=1e-12)
+        n += 1
+    assert n >= 4
+
+
 def test_triple_index_error(golden_contract):
     _, meta = golden_contract
     with pytest.raises(ValueError) as e:

@@ -26,14 +26,28 @@ def main():
     ap.add_argument("--chi", type=int, default=1024)
     ap.add_argument("--cpu-L", type=int, default=24)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--shard", action="store_true",
+                    help="under torchrun: row-shard the local eigensolves over the ranks (NCCL)")
     args = ap.parse_args()
     import torch
     import quimb_b200 as qb
     from oracle import dmrg_np as dm
+    shard = None
+    rank = 0
+    if args.shard:
+        import torch.distributed as dist
+        from quimb_b200.dist import BondShard
+        rank = int(os.environ["RANK"])
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
+        dist.init_process_group("nccl")
+        shard = BondShard()
+        args.no_cpu = True
 
     out = {"L": args.L, "chi": args.chi, "dtype": "f64"}
     mpo = dm.mpo_heis(args.L)
-    d = qb.DMRG2(mpo, args.chi, cutoffs=0.0, mpo_shape="lrdu", seed=2)
+    d = qb.DMRG2(mpo, args.chi, cutoffs=0.0, mpo_shape="lrdu", seed=2, shard=shard)
+    if shard is not None:
+        out["shard"] = {"world_size": shard.world_size, "backend": "nccl"}
     torch.cuda.synchronize()
     site_t = []
     orig = d._update_local_state_2site
@@ -58,7 +72,10 @@ def main():
         "matvecs_per_site": float(np.mean([nmv for (_, _, nmv, _) in site_t])),
         "update_s_total": float(sum(t for (_, t, _, _) in site_t)),
     }
-    print(json.dumps(out), flush=True)
+    if shard is not None:
+        out["shard"]["bytes_gathered"] = shard.bytes_gathered
+    if rank == 0:
+        print(json.dumps(out), flush=True)
     if not args.no_cpu:
         Lc = args.cpu_L
         o = dm.DMRG2(dm.mpo_heis(Lc), args.chi, cutoffs=0.0, seed=2)
@@ -85,9 +102,15 @@ def main():
         if full and fullc:
             out["speedup_per_site_full_chi"] = out["cpu"]["s_per_site_full_chi"] / out["gpu"]["s_per_site_full_chi"]
             out["cpu_sweep_extrapolated_s"] = out["cpu"]["s_per_site_full_chi"] * len(site_t)
-    print(json.dumps(out), flush=True)
-    os.makedirs("gpurun_out", exist_ok=True)
-    json.dump(out, open("gpurun_out/bench_dmrg.json", "w"), indent=1)
+    if rank == 0:
+        if not args.no_cpu:
+            print(json.dumps(out), flush=True)
+        os.makedirs("gpurun_out", exist_ok=True)
+        name = "bench_dmrg_shard%d.json" % shard.world_size if shard else "bench_dmrg.json"
+        json.dump(out, open(os.path.join("gpurun_out", name), "w"), indent=1)
+    if shard is not None:
+        import torch.distributed as dist
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
