@@ -132,7 +132,9 @@ int64_t qb_contract_pair_workspace(const qb_tensor_t *A, const int32_t *la,
 
 // QB_TRACE=1: device buffer the kernels stamp their phase times into
 static constexpr int64_t kTraceEntries = 1 << 20;
-static unsigned long long *trace_buffer() {
+}  // extern "C"
+namespace qb {
+unsigned long long *trace_buffer() {
   static unsigned long long *buf = [] () -> unsigned long long * {
     const char *e = getenv("QB_TRACE");
     if (!e || atoi(e) == 0) return nullptr;
@@ -143,6 +145,8 @@ static unsigned long long *trace_buffer() {
   }();
   return buf;
 }
+}  // namespace qb
+extern "C" {
 
 static int contract_pair_impl(const qb_tensor_t *A, const int32_t *la,
                               const qb_tensor_t *B, const int32_t *lb,

@@ -22,4 +22,7 @@ int gemm_f64(const double *A, int64_t a_rs, int64_t a_cs, const double *B,
              cudaStream_t st, double *splitk_ws = nullptr,
              int64_t splitk_ws_elems = 0, int max_splitk = 1);
 
+// QB_TRACE=1 tuning buffer (api.cu): 2^20 uint64 stamps, null when tracing is off
+unsigned long long *trace_buffer();
+
 }  // namespace qb

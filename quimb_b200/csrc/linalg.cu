@@ -480,7 +480,20 @@ struct JacobiParams {
   double tol;
   int *flag;       // set to 1 when any pair still needed rotating
   int inner_max;   // max inner Jacobi sweeps per visit
+  unsigned long long *trace;  // tuning (QB_TRACE): phase stamps of cluster 0
+  int trace_slot;             // ring of 1024 rounds
 };
+
+__device__ __forceinline__ unsigned long long jac_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define JAC_TRACE(ph)                                                     \
+  do {                                                                    \
+    if (P.trace && blockIdx.x == 0 && threadIdx.x == 0)                   \
+      P.trace[(size_t)P.trace_slot * 8 + (ph)] = jac_ns();             \
+  } while (0)
 
 __device__ __forceinline__ void rr_pair(int k, int round, int nblk, int &p, int &q) {
   // circle-method round robin over nblk players
@@ -506,7 +519,6 @@ __device__ __forceinline__ void jac_load_chunk(double (*Xs)[JPITCH], const doubl
   }
 }
 
-constexpr int JSTG = 4;         // cp.async stages of the row-chunk stream
 constexpr int JCSZ = 2;         // CTAs (one cluster) per column-block pair
 
 // One round-robin round of the one-sided block Jacobi method.  A CLUSTER of
@@ -519,6 +531,7 @@ constexpr int JCSZ = 2;         // CTAs (one cluster) per column-block pair
 //      cyclic Jacobi (two-sided rotations fused into one pass, 2 barriers
 //      per step), eigenvalues sorted descending;
 //   3. the rotation is applied by DMMA to this CTA's rows of W and of V.
+template <int JSTG>  // cp.async stages of the row-chunk stream
 __global__ void __cluster_dims__(JCSZ, 1, 1) __launch_bounds__(256)
     jacobi_pair_kernel(const JacobiParams P) {
   namespace cg = cooperative_groups;
@@ -540,6 +553,7 @@ __global__ void __cluster_dims__(JCSZ, 1, 1) __launch_bounds__(256)
   rr_pair(blockIdx.x / JCSZ, P.round, P.nblk, bp, bq);
   const int cp = bp * JB, cq = bq * JB;
 
+  JAC_TRACE(0);
   // ---------------- phase 1: partial Gram over this CTA's row chunks --------
   double acc[2][4][4];
 #pragma unroll
@@ -584,26 +598,29 @@ __global__ void __cluster_dims__(JCSZ, 1, 1) __launch_bounds__(256)
     cp_async_wait<0>();
     __syncthreads();
   }
-  // deterministic reduction over the 8 warps into Gpart
-  for (int w = 0; w < 8; ++w) {
-    if (warp == w) {
+  JAC_TRACE(1);
+  // deterministic reduction over the 8 warps into Gpart: every warp parks its
+  // fragment in the (now idle) stream buffers, one barrier, then each thread
+  // sums four entries over the warps in a fixed order
+  {
+    double *scr = &Xs[0][0][0];  // 8 x 32 x 32 doubles <= JSTG * JCH * JPITCH
 #pragma unroll
-      for (int i = 0; i < 2; ++i)
+    for (int i = 0; i < 2; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
+      for (int j = 0; j < 4; ++j)
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int r = i * 16 + g + h * 8, c = j * 8 + 2 * t;
-            if (w == 0) {
-              Gpart[r][c] = acc[i][j][2 * h];
-              Gpart[r][c + 1] = acc[i][j][2 * h + 1];
-            } else {
-              Gpart[r][c] += acc[i][j][2 * h];
-              Gpart[r][c + 1] += acc[i][j][2 * h + 1];
-            }
-          }
-    }
+        for (int h = 0; h < 2; ++h) {
+          const int r = i * 16 + g + h * 8, c = j * 8 + 2 * t;
+          *reinterpret_cast<double2 *>(&scr[(warp * JP + r) * JP + c]) =
+              make_double2(acc[i][j][2 * h], acc[i][j][2 * h + 1]);
+        }
     __syncthreads();
+    for (int idx = tid; idx < JP * JP; idx += 256) {
+      double sum = 0.0;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) sum += scr[w * JP * JP + idx];
+      Gpart[idx / JP][idx % JP] = sum;
+    }
   }
   cluster.sync();
   // full Gram = sum over the cluster (same order everywhere), symmetrised
@@ -640,6 +657,7 @@ __global__ void __cluster_dims__(JCSZ, 1, 1) __launch_bounds__(256)
     return m2;
   };
   const double off0 = offmax();
+  JAC_TRACE(2);
   // all CTAs of the cluster take the same decision (same G)
   if (off0 <= P.tol) {
     cluster.sync();  // peers may still be reading our Gpart
@@ -704,6 +722,7 @@ __global__ void __cluster_dims__(JCSZ, 1, 1) __launch_bounds__(256)
       __syncthreads();
     }
   }
+  JAC_TRACE(3);
   // sort: larger column norms first (ties by index) -> new column order
   if (tid < JP) {
     const double d = G[tid][tid];
@@ -726,6 +745,7 @@ __global__ void __cluster_dims__(JCSZ, 1, 1) __launch_bounds__(256)
   }
   __syncthreads();
 
+  JAC_TRACE(4);
   // ---------------- phase 3: apply J to this CTA's rows of W and V ----------
   {
     const int nchw = (P.rows_w + JCH - 1) / JCH, nchv = (P.rows_v + JCH - 1) / JCH;
@@ -788,7 +808,9 @@ __global__ void __cluster_dims__(JCSZ, 1, 1) __launch_bounds__(256)
     }
     cp_async_wait<0>();
   }
+  JAC_TRACE(5);
   cluster.sync();  // nobody exits while peers may read its shared memory
+  JAC_TRACE(6);
 }
 
 // column norms of W (rows x ld, first ncols columns)
@@ -906,12 +928,26 @@ static int svd_tall_f64(int64_t m, int64_t n, const double *X, double *U,
   QB_LAUNCH_CHECK();
   pad_copy_kernel<<<blocks, 256, 0, st>>>(nullptr, 0, 0, 0, V, npad, npad, 1);
   QB_LAUNCH_CHECK();
-  constexpr int kJacSmem = JSTG * JCH * JPITCH * 8;
+  // stream depth (QB_JAC_STAGES: 4, 8 or 10): measured identical -- the row
+  // streams are bound by the DMMA rate (64 rows x 32 x 32 FMAs per chunk =
+  // 1024 pipe clocks per SM), not by bytes in flight
+  static const int jstg = [] {
+    const char *e = getenv("QB_JAC_STAGES");
+    const int v = e ? atoi(e) : 4;
+    return v <= 4 ? 4 : (v <= 8 ? 8 : 10);
+  }();
+  const int kJacSmem = jstg * JCH * JPITCH * 8;
   static bool attr_set = false;
   if (!attr_set) {
-    QB_CUDA_CHECK(cudaFuncSetAttribute(jacobi_pair_kernel,
+    QB_CUDA_CHECK(cudaFuncSetAttribute(jacobi_pair_kernel<4>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       kJacSmem));
+                                       4 * JCH * JPITCH * 8));
+    QB_CUDA_CHECK(cudaFuncSetAttribute(jacobi_pair_kernel<8>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       8 * JCH * JPITCH * 8));
+    QB_CUDA_CHECK(cudaFuncSetAttribute(jacobi_pair_kernel<10>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       10 * JCH * JPITCH * 8));
     attr_set = true;
   }
   JacobiParams P;
@@ -919,6 +955,7 @@ static int svd_tall_f64(int64_t m, int64_t n, const double *X, double *U,
   P.nblk = (int)(npad / JB);
   P.tol = 1e-15 * sqrt((double)n) * 8.0;
   P.flag = flag;
+  P.trace = trace_buffer() ? trace_buffer() + 16 * 8192 : nullptr;
   {
     static const int inner = [] { const char *e = getenv("QB_JAC_INNER"); return e ? atoi(e) : 1; }();
     P.inner_max = inner;
@@ -933,7 +970,11 @@ static int svd_tall_f64(int64_t m, int64_t n, const double *X, double *U,
     QB_CUDA_CHECK(cudaMemsetAsync(flag, 0, sizeof(int), st));
     for (int r = 0; r < P.nblk - 1; ++r) {
       P.round = r;
-      jacobi_pair_kernel<<<(P.nblk / 2) * JCSZ, 256, kJacSmem, st>>>(P);
+      P.trace_slot = (sweeps * (P.nblk - 1) + r) & 1023;
+      const unsigned grid = (unsigned)(P.nblk / 2) * JCSZ;
+      if (jstg == 4) jacobi_pair_kernel<4><<<grid, 256, kJacSmem, st>>>(P);
+      else if (jstg == 8) jacobi_pair_kernel<8><<<grid, 256, kJacSmem, st>>>(P);
+      else jacobi_pair_kernel<10><<<grid, 256, kJacSmem, st>>>(P);
       QB_LAUNCH_CHECK();
     }
     int h = 0;

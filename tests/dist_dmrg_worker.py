@@ -52,11 +52,12 @@ def main():
         ok = ok and abs(ds.energy - e0) < 1e-6
     ok = ok and sh.bytes_gathered > 0
     # the replicated part of the sweep stays bit-identical on all ranks
-    chk = torch.stack([a.t.abs().sum().double() for a in ds.state]).cpu()
+    cdev = "cuda" if args.backend == "nccl" else "cpu"   # NCCL reduces device tensors only
+    chk = torch.stack([a.t.abs().sum().double() for a in ds.state]).to(cdev)
     lo, hi = chk.clone(), chk.clone()
     dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
     ok = ok and bool(torch.equal(lo, hi))
-    flag = torch.tensor([1.0 if ok else 0.0])
+    flag = torch.tensor([1.0 if ok else 0.0], device=cdev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
         print(f"sharded E={ds.energy:.12f} unsharded E={d1.energy:.12f} exact={e0} "
