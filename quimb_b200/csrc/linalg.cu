@@ -528,8 +528,8 @@ constexpr int JCSZ = 2;         // CTAs (one cluster) per column-block pair
 //      reduced over warps and then over the cluster through distributed
 //      shared memory (fixed order: deterministic);
 //   2. every CTA diagonalises the same 32 x 32 Gram by parallel-ordered
-//      cyclic Jacobi (two-sided rotations fused into one pass, 2 barriers
-//      per step), eigenvalues sorted descending;
+//      cyclic Jacobi (two-sided rotations fused into one pass over a
+//      ping-pong copy of the Gram: one barrier per step), sorted descending;
 //   3. the rotation is applied by DMMA to this CTA's rows of W and of V.
 template <int JSTG>  // cp.async stages of the row-chunk stream
 __global__ void __cluster_dims__(JCSZ, 1, 1) __launch_bounds__(256)
@@ -539,11 +539,11 @@ __global__ void __cluster_dims__(JCSZ, 1, 1) __launch_bounds__(256)
   const int rank = (int)cluster.block_rank();
   extern __shared__ __align__(16) unsigned char jac_smem[];
   double(*Xs)[JCH][JPITCH] = reinterpret_cast<double(*)[JCH][JPITCH]>(jac_smem);
-  __shared__ double G[JP][JP + 1];
+  __shared__ double Gbuf[2][JP][JP + 1];
+  double(*G)[JP + 1] = Gbuf[0];   // current Gram; the eigen-solve ping-pongs
+  double(*Gn)[JP + 1] = Gbuf[1];
   __shared__ double Gpart[JP][JP];
   __shared__ __align__(16) double Jm[JP][JPITCH];
-  __shared__ double rot[JB][2];
-  __shared__ int rotpq[JB][2];
   __shared__ double redmax[8];
   __shared__ int rank_s[JP];
 
@@ -590,10 +590,13 @@ __global__ void __cluster_dims__(JCSZ, 1, 1) __launch_bounds__(256)
         bf[j][0] = X[kb + t][j * 8 + g];
         bf[j][1] = X[kb + t + 4][j * 8 + g];
       }
+      // the Gram is symmetric: the lower-left 16 x 16 block (a = 1, j < 2)
+      // is the mirror of the upper-right one and is not computed
 #pragma unroll
       for (int a = 0; a < 2; ++a)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) dmma_16x8x8(acc[a][j], af[a], bf[j]);
+        for (int j = 0; j < 4; ++j)
+          if (a == 0 || j >= 2) dmma_16x8x8(acc[a][j], af[a], bf[j]);
     }
     cp_async_wait<0>();
     __syncthreads();
@@ -616,10 +619,12 @@ __global__ void __cluster_dims__(JCSZ, 1, 1) __launch_bounds__(256)
         }
     __syncthreads();
     for (int idx = tid; idx < JP * JP; idx += 256) {
+      const int r = idx / JP, c = idx % JP;
+      const int src = (r >= 16 && c < 16) ? (c * JP + r) : idx;  // mirrored block
       double sum = 0.0;
 #pragma unroll
-      for (int w = 0; w < 8; ++w) sum += scr[w * JP * JP + idx];
-      Gpart[idx / JP][idx % JP] = sum;
+      for (int w = 0; w < 8; ++w) sum += scr[w * JP * JP + src];
+      Gpart[r][c] = sum;
     }
   }
   cluster.sync();
@@ -676,28 +681,30 @@ __global__ void __cluster_dims__(JCSZ, 1, 1) __launch_bounds__(256)
       if (off <= 1e-15 || off <= 1e-4 * off0) break;
     }
     for (int step = 0; step < JP - 1; ++step) {
-      if (tid < JB) {
-        int p, q;
-        rr_pair(tid, step, JP, p, q);
-        const double app = G[p][p], aqq = G[q][q], apq = G[p][q];
-        double c = 1.0, s = 0.0;
+      // One barrier per step: thread (k1, k2) owns the 2x2 block (rows of pair
+      // k1) x (columns of pair k2).  The 16 rotations of the step are computed
+      // once per warp (lanes 0-15, pinned arithmetic so that all warps get
+      // bit-identical c, s) and handed out by shuffles; the rotated block goes
+      // to the other Gram buffer; J <- J R for column pair k2, rows k1, k1+16.
+      const int k1 = tid >> 4, k2 = tid & 15;
+      int p1, q1, p2, q2;
+      rr_pair(k1, step, JP, p1, q1);
+      rr_pair(k2, step, JP, p2, q2);
+      double c = 1.0, s = 0.0;
+      if (lane < 16) {  // lane == k2 here
+        const double app = G[p2][p2], aqq = G[q2][q2], apq = G[p2][q2];
         if (fabs(apq) > 1e-300) {
-          // t = sgn(z) / (|z| + sqrt(1 + z^2)), z = (aqq - app) / (2 apq),
-          // rearranged to one sqrt + one division + one rsqrt
-          const double a = aqq - app, b = 2.0 * apq;
-          const double tt = copysign(fabs(b), a * b) / (fabs(a) + sqrt(a * a + b * b));
-          c = rsqrt(1.0 + tt * tt);
-          s = c * tt;
+          // t = sgn(z) / (|z| + sqrt(1 + z^2)), z = (aqq - app) / (2 apq)
+          const double a = __dsub_rn(aqq, app), b = __dmul_rn(2.0, apq);
+          const double h = sqrt(__fma_rn(a, a, __dmul_rn(b, b)));
+          const double tt = __ddiv_rn(copysign(fabs(b), __dmul_rn(a, b)), __dadd_rn(fabs(a), h));
+          c = rsqrt(__fma_rn(tt, tt, 1.0));
+          s = __dmul_rn(c, tt);
         }
-        rot[tid][0] = c; rot[tid][1] = s;
-        rotpq[tid][0] = p; rotpq[tid][1] = q;
       }
-      __syncthreads();
+      const double c2 = __shfl_sync(0xffffffffu, c, k2), s2 = __shfl_sync(0xffffffffu, s, k2);
+      const double c1 = __shfl_sync(0xffffffffu, c, k1), s1 = __shfl_sync(0xffffffffu, s, k1);
       {
-        // G <- R^T G R, one 2x2 block (pair k1 rows x pair k2 columns) per thread
-        const int k1 = tid >> 4, k2 = tid & 15;
-        const double c1 = rot[k1][0], s1 = rot[k1][1], c2 = rot[k2][0], s2 = rot[k2][1];
-        const int p1 = rotpq[k1][0], q1 = rotpq[k1][1], p2 = rotpq[k2][0], q2 = rotpq[k2][1];
         const double gpp = G[p1][p2], gpq = G[p1][q2], gqp = G[q1][p2], gqq = G[q1][q2];
         // columns first
         const double a0 = c2 * gpp - s2 * gpq, a1 = s2 * gpp + c2 * gpq;
@@ -706,20 +713,17 @@ __global__ void __cluster_dims__(JCSZ, 1, 1) __launch_bounds__(256)
         double n00 = c1 * a0 - s1 * b0, n01 = c1 * a1 - s1 * b1;
         double n10 = s1 * a0 + c1 * b0, n11 = s1 * a1 + c1 * b1;
         if (k1 == k2) { n01 = 0.0; n10 = 0.0; }  // the annihilated pair
-        G[p1][p2] = n00; G[p1][q2] = n01; G[q1][p2] = n10; G[q1][q2] = n11;
-        // J <- J R : 32 rows x 16 pairs = 2 items per thread
+        Gn[p1][p2] = n00; Gn[p1][q2] = n01; Gn[q1][p2] = n10; Gn[q1][q2] = n11;
 #pragma unroll
         for (int it = 0; it < 2; ++it) {
-          const int idx = tid + 256 * it;
-          const int k = idx & 15, r = idx >> 4;  // 16 distinct column pairs per half-warp
-          const double c = rot[k][0], s = rot[k][1];
-          const int p = rotpq[k][0], q = rotpq[k][1];
-          const double jp = Jm[r][p], jq = Jm[r][q];
-          Jm[r][p] = c * jp - s * jq;
-          Jm[r][q] = s * jp + c * jq;
+          const int r = k1 + 16 * it;
+          const double jp = Jm[r][p2], jq = Jm[r][q2];
+          Jm[r][p2] = c2 * jp - s2 * jq;
+          Jm[r][q2] = s2 * jp + c2 * jq;
         }
       }
       __syncthreads();
+      { double(*tmp)[JP + 1] = G; G = Gn; Gn = tmp; }
     }
   }
   JAC_TRACE(3);

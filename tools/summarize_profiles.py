@@ -89,7 +89,8 @@ if __name__ == "__main__":
     full(f"prof_contract_{TAG}.ncu-rep", f"{TAG}_contract_kernel_ncu_full.txt", [
         f"# ncu --set full --clock-control none --import-source on -k regex:contract_f64_streamk -s 1000 -c 2 "
         "(bench.py: MPS norm L=200 chi=1024 fp64)",
-        "# persistent stream-K launch of the 128x128x16 DMMA contraction kernel, 148 CTAs",
+        "# persistent stream-K launch of the 128x128x32 (3-stage, 16 warps, compile-time tile layouts) DMMA",
+        "# contraction kernel, 148 CTAs, programmatic dependent launch",
         "# launch 1: E[a',a].A[a,(b,p)]  M=1024 N=2048 K=1024;  launch 2: conj(A)[(a',p),b'].T  M=N=1024 K=2048",
         "# algorithmic per launch: 4.295 GFLOP, 33.5 MB (fp64) -> tensor bound; DMMA peak measured 37.16 TFLOP/s"])
     full(f"prof_ozaki_{TAG}.ncu-rep", f"{TAG}_ozaki_gemm_ncu_full.txt", [
@@ -97,6 +98,7 @@ if __name__ == "__main__":
         "# tcgen05 kind::i8 error-free-split GEMM, 128x64 tiles, 36 slice products, TMA + TMEM",
         "# algorithmic: 137.4 GFLOP fp64 = 4.95 int8 POP; 3.03 ms -> 1.63 POP/s int8, L2 bound"])
     full(f"prof_jacobi_{TAG}.ncu-rep", f"{TAG}_jacobi_svd_ncu_full.txt", [
-        "# ncu --set full -k regex:jacobi_pair -s 300 -c 2 (tools/svd_prof.py 2048): FIRST clustered version",
-        "# (cluster 4, inner tolerance 2e-16); the committed kernel uses cluster 2, one inner sweep, fused rotations"])
+        "# ncu --set full --clock-control none --import-source on -k regex:jacobi_pair -s 300 -c 2 (tools/svd_prof.py 2048)",
+        "# committed kernel: cluster 2, symmetric Gram, single-pass warp reduction, one inner sweep with",
+        "# one barrier per step (per-warp rotations, ping-pong Gram), fused rotations"])
     print(os.listdir(P))
