@@ -12,6 +12,10 @@ what `method="svd"` / `"qr"` run on numpy arrays):
   qr_stabilized          decomp.py:2147-2216 (_qr_stabilized_numba / _lq_...)
   sgn                    decomp.py:634-648
   option parsing         decomp.py:201-291, 369-424 (codes only)
+  svd:eig                decomp.py:1168-1361 (svd_via_eig), :1364-1444
+  svd:rand               decomp.py:1689-1861 (svd_rand_truncated)
+  eigh                   decomp.py:1899-1969 (+ _with_diag_shift :1867-1881)
+  safe_inverse           decomp.py:501-551
   fuse / tensor_split    quimb/tensor/array_ops.py:95-180,
                          quimb/tensor/tensor_core.py:392-668 (array part)
 
@@ -141,9 +145,10 @@ def do_absorb(U, s, VH, absorb):
     raise ValueError(f"Invalid absorb mode: {absorb}")
 
 
-def trim_and_renorm(U, s, VH, cutoff, cutoff_mode, max_bond, absorb, renorm):
+def trim_and_renorm(U, s, VH, cutoff, cutoff_mode, max_bond, absorb, renorm,
+                    use_abs=False):
     """decomp.py:968-1029; returns (left, s, right, error, n_keep)."""
-    sabs = s
+    sabs = np.abs(s) if use_abs else s
     error = 0.0
     n_keep = s.size
     if (cutoff > 0.0) or (renorm > 0):
@@ -184,6 +189,212 @@ def svd_truncated(x, cutoff=-1.0, cutoff_mode=4, max_bond=-1, absorb=0,
         info["n_keep"] = n_keep
         info["svals"] = s
     return left, sv, right
+
+
+def safe_inverse(x, cutoff=None, power=1.0):
+    """decomp.py:501-551."""
+    xmax = np.max(x) if x.ndim == 1 else np.expand_dims(np.max(x, axis=-1), -1)
+    xmax = np.where(xmax > 0.0, xmax, 1.0)
+    c = np.finfo(x.dtype).eps if cutoff is None else cutoff / xmax
+    y = x / xmax
+    q = power + 1.0
+    return y / ((y ** q + c ** q) * xmax ** power)
+
+
+def _dag(x):
+    return np.conj(np.swapaxes(x, -2, -1))
+
+
+def svd_via_eig(x, absorb=None, max_bond=-1, descending=True, right=None):
+    """decomp.py:1168-1361 (the generic, array-API version)."""
+    m, n = x.shape
+    xdag = _dag(x)
+    absorb = ABSORB_MAP[absorb]
+    if right is None:
+        if m > n:
+            right = True
+        elif m < n:
+            right = False
+        else:
+            right = absorb in (get_VH, get_sVH, get_sqVH, get_Us_VH)
+    if right:
+        s2, V = np.linalg.eigh(xdag @ x)
+        if 0 < max_bond < min(m, n):
+            s2 = s2[-max_bond:]
+            V = V[:, -max_bond:]
+        if descending:
+            s2 = np.flip(s2, axis=-1)
+            V = np.flip(V, axis=-1)
+        s2 = np.clip(s2, 0.0, None)
+        if absorb == get_s:
+            return None, np.sqrt(s2), None
+        if absorb == get_VH:
+            return None, None, _dag(V)
+        if absorb == get_sVH:
+            return None, None, np.sqrt(s2)[:, None] * _dag(V)
+        if absorb == get_sqVH:
+            return None, None, np.sqrt(np.sqrt(s2))[:, None] * _dag(V)
+        Us = x @ V
+        if absorb == get_Us:
+            return Us, None, None
+        if absorb == get_Us_VH:
+            return Us, None, _dag(V)
+        s = np.sqrt(s2)
+        eps = np.finfo(s.dtype).eps
+        smax = s[0:1] if descending else s[-1:]
+        sinv = safe_inverse(s, smax * eps * max(m, n))
+        U = Us * sinv[None, :]
+        if absorb == get_U:
+            return U, None, None
+        if absorb == get_Usq:
+            return U * np.sqrt(s)[None, :], None, None
+        VH = _dag(V)
+        if absorb is None:
+            return U, s, VH
+        if absorb == get_U_sVH:
+            return U, None, s[:, None] * VH
+        if absorb == get_Usq_sqVH:
+            sq = np.sqrt(s)
+            return U * sq[None, :], None, sq[:, None] * VH
+    else:
+        s2, U = np.linalg.eigh(x @ xdag)
+        if 0 < max_bond < min(m, n):
+            s2 = s2[-max_bond:]
+            U = U[:, -max_bond:]
+        if descending:
+            s2 = np.flip(s2, axis=-1)
+            U = np.flip(U, axis=-1)
+        s2 = np.clip(s2, 0.0, None)
+        if absorb == get_s:
+            return None, np.sqrt(s2), None
+        if absorb == get_U:
+            return U, None, None
+        if absorb == get_Us:
+            return U * np.sqrt(s2)[None, :], None, None
+        if absorb == get_Usq:
+            return U * np.sqrt(np.sqrt(s2))[None, :], None, None
+        sVH = _dag(U) @ x
+        if absorb == get_sVH:
+            return None, None, sVH
+        if absorb == get_U_sVH:
+            return U, None, sVH
+        s = np.sqrt(s2)
+        eps = np.finfo(s.dtype).eps
+        smax = s[0:1] if descending else s[-1:]
+        sinv = safe_inverse(s, smax * eps * max(m, n))
+        VH = sinv[:, None] * sVH
+        if absorb == get_VH:
+            return None, None, VH
+        if absorb is None:
+            return U, s, VH
+        if absorb == get_Us_VH:
+            return U * s[None, :], None, VH
+        sq = np.sqrt(s)
+        if absorb == get_Usq_sqVH:
+            return U * sq[None, :], None, sq[:, None] * VH
+        if absorb == get_sqVH:
+            return None, None, sq[:, None] * VH
+    raise ValueError(f"Invalid absorb mode: {absorb}")
+
+
+def svd_via_eig_truncated(x, cutoff=-1.0, cutoff_mode=4, max_bond=-1, absorb=0,
+                          renorm=0, info=None):
+    """decomp.py:1364-1444."""
+    absorb = ABSORB_MAP[absorb]
+    cutoff_mode = CUTOFF_MODE_MAP[cutoff_mode]
+    need_full = (cutoff > 0.0) or (renorm > 0) or (info is not None and "error" in info)
+    if need_full:
+        U, s, VH = svd_via_eig(x, absorb=None, max_bond=-1, descending=True)
+        left, sv, right, error, n_keep = trim_and_renorm(
+            U, s, VH, cutoff, cutoff_mode, max_bond, absorb, renorm)
+        if info is not None:
+            info["error"] = error
+            info["n_keep"] = n_keep
+        return left, sv, right
+    return svd_via_eig(x, absorb=absorb, max_bond=max_bond, descending=False)
+
+
+def with_diag_shift(x, shift=0.0):
+    """decomp.py:1867-1881."""
+    if shift < 0.0:
+        shift = np.finfo(x.dtype).eps
+    if shift > 0.0:
+        x = x + shift * np.trace(x) * np.eye(x.shape[-1])
+    return x
+
+
+def eigh_truncated(x, cutoff=-1.0, cutoff_mode=4, max_bond=-1, absorb=0, renorm=0,
+                   positive=0, shift=False):
+    """decomp.py:1899-1969 / numba :1972-2020."""
+    absorb = ABSORB_MAP[absorb]
+    cutoff_mode = CUTOFF_MODE_MAP[cutoff_mode]
+    shift = {False: 0.0, True: -1.0}.get(shift, shift)
+    x = with_diag_shift(x, shift)
+    s, U = np.linalg.eigh(x)
+    if not positive:
+        k = np.argsort(-np.abs(s))
+        s, U = s[k], U[:, k]
+    else:
+        s = s[::-1].copy()
+        U = U[:, ::-1]
+        if absorb in (get_Usq_sqVH, get_Usq, get_sqVH):
+            s[s < 0.0] = 0.0
+    VH = _dag(U)
+    left, sv, right, _, _ = trim_and_renorm(U, s, VH, cutoff, cutoff_mode, max_bond,
+                                            absorb, renorm, use_abs=not positive)
+    return left, sv, right
+
+
+def svd_rand_truncated(x, max_bond, absorb=0, oversample=10, num_iterations=2,
+                       right=None, seed=None):
+    """decomp.py:1689-1861 with method_lorthog='qr', method_reduced='svd'."""
+    absorb = ABSORB_MAP[absorb]
+    if max_bond is None:
+        max_bond = -1
+    m, n = x.shape
+    k = min(m, n) if max_bond < 0 else min(m, n, max_bond)
+    k_sketch = min(m, n, k + oversample)
+    if right is None:
+        if absorb in (get_U_sVH, get_U, get_sVH):
+            right = True
+        elif absorb in (get_Us_VH, get_Us, get_VH):
+            right = False
+        else:
+            right = m > n
+    rng = np.random.default_rng(seed)
+    xdag = _dag(x)
+    if right:
+        y = x @ rng.normal(size=(n, k_sketch))
+        for _ in range(num_iterations):
+            y = x @ (xdag @ y)
+        Q, _, _ = qr_stabilized(y, absorb=get_U)
+        if k >= k_sketch:
+            if absorb == get_U_sVH:
+                return Q, None, _dag(Q) @ x
+            if absorb == get_sVH:
+                return None, None, _dag(Q) @ x
+            if absorb == get_U:
+                return Q, None, None
+        B = _dag(Q) @ x
+    else:
+        y = rng.normal(size=(k_sketch, m)) @ x
+        for _ in range(num_iterations):
+            y = (y @ xdag) @ x
+        Q, _, _ = qr_stabilized(_dag(y), absorb=get_U)
+        if k >= k_sketch:
+            if absorb == get_Us_VH:
+                return x @ Q, None, _dag(Q)
+            if absorb == get_Us:
+                return x @ Q, None, None
+            if absorb == get_VH:
+                return None, None, _dag(Q)
+        B = x @ Q
+    U, s, VH = svd_truncated(B, cutoff=0.0, max_bond=k, absorb=absorb)
+    if U is not None and right:
+        U = Q @ U
+    if VH is not None and not right:
+        VH = VH @ _dag(Q)
+    return U, s, VH
 
 
 def sgn(x):
@@ -271,7 +482,7 @@ def parse_method_absorb(method="auto", absorb="auto", truncation=True):
         if absorb == "auto":
             absorb = "left"
     if absorb == "auto":
-        absorb = {"svd": get_Usq_sqVH, "qr": get_U_sVH}[method]
+        absorb = {"qr": get_U_sVH}.get(method, get_Usq_sqVH)
     else:
         absorb = ABSORB_MAP[absorb]
     return method, absorb

@@ -212,6 +212,126 @@ def decomp_cases():
     json.dump(meta, open(os.path.join(OUT, "decomp.json"), "w"), indent=1, default=str)
 
 
+def _gauge_free(left, sv, right):
+    """Gauge-invariant images of a split result for storage."""
+    out = {}
+    if sv is not None:
+        out["s"] = np.asarray(sv)
+    if left is not None and right is not None:
+        out["rec"] = left @ (np.diag(sv) @ right if sv is not None else right)
+    elif left is not None:
+        out["lgram"] = left @ left.conj().T
+    elif right is not None:
+        out["rgram"] = right.conj().T @ right
+    return out
+
+
+def decomp2_cases():
+    """Gram-matrix SVD ('svd:eig'), Hermitian 'eigh' split and randomized SVD
+    ('svd:rand') of the reference on its numpy backend."""
+    rng = np.random.default_rng(11)
+    store, meta = {}, {}
+    q1 = np.linalg.qr(rng.standard_normal((20, 20)))[0]
+    q2 = np.linalg.qr(rng.standard_normal((20, 20)))[0]
+    sym = rng.standard_normal((18, 18))
+    hc = rng.standard_normal((14, 14)) + 1j * rng.standard_normal((14, 14))
+    ps = rng.standard_normal((16, 9))
+    mats = {
+        "tall": rng.standard_normal((24, 10)),
+        "wide": rng.standard_normal((9, 20)),
+        "square": rng.standard_normal((16, 16)),
+        "lowrank": rng.standard_normal((20, 4)) @ rng.standard_normal((4, 18)),
+        "cplx": rng.standard_normal((12, 14)) + 1j * rng.standard_normal((12, 14)),
+        "decay": (q1 * (0.6 ** np.arange(20))[None, :]) @ q2,
+        "sym": sym + sym.T,
+        "psd": ps @ ps.T,
+        "herm": hc + hc.conj().T,
+    }
+    for k, v in mats.items():
+        store[f"mat__{k}"] = v
+    eig_cases = []
+    for mname in ("tall", "wide", "square", "lowrank", "cplx", "decay"):
+        x = mats[mname]
+        for (cutoff, mode, max_bond, absorb, renorm, want_err) in [
+            (-1.0, 4, -1, None, 0, False),
+            (1e-2, 4, -1, 0, 0, True),
+            (1e-3, 3, -1, -1, 0, True),
+            (-1.0, 4, 5, 1, 0, False),
+            (-1.0, 4, 6, -1, 0, False),
+            (-1.0, 4, 4, 0, 0, False),
+            (1e-2, 6, -1, 0, 1, True),
+            (-1.0, 4, 5, 11, 0, False),
+            (-1.0, 4, 5, -10, 0, False),
+            (-1.0, 4, -1, 10, 0, False),
+            (-1.0, 4, -1, -11, 0, False),
+            (-1.0, 4, 7, 2, 0, False),
+            (1e-1, 2, 8, None, 0, True),
+        ]:
+            info = {"error": None} if want_err else None
+            left, sv, right = decomp.svd_via_eig_truncated(
+                x, cutoff=cutoff, cutoff_mode=mode, max_bond=max_bond,
+                absorb=absorb, renorm=renorm, info=info)
+            key = f"eig__{mname}__{len(eig_cases)}"
+            for nm, v in _gauge_free(left, sv, right).items():
+                store[f"{key}__{nm}"] = v
+            parts = [a for a in (left, right) if a is not None]
+            k = (left.shape[1] if left is not None else
+                 right.shape[0] if right is not None else sv.shape[0])
+            eig_cases.append({
+                "key": key, "mat": mname, "cutoff": cutoff, "cutoff_mode": mode,
+                "max_bond": max_bond, "absorb": absorb, "renorm": renorm,
+                "n_keep": int(k),
+                "error": None if info is None else float(info["error"]),
+                "has": [left is not None, sv is not None, right is not None]})
+    meta["eig_cases"] = eig_cases
+    eigh_cases = []
+    for mname in ("sym", "psd", "herm"):
+        x = mats[mname]
+        for kw in [dict(absorb=None), dict(absorb=None, max_bond=6),
+                   dict(absorb=-1, cutoff=1e-2, cutoff_mode=4),
+                   dict(absorb=1, cutoff=0.2, cutoff_mode=2),
+                   dict(absorb=0, positive=1, max_bond=5) if mname == "psd" else dict(absorb=1, max_bond=5),
+                   dict(absorb=None, shift=True, cutoff=1e-3, cutoff_mode=3, renorm=2)]:
+            left, sv, right = decomp.eigh_truncated(x, **kw)
+            key = f"eigh__{mname}__{len(eigh_cases)}"
+            for nm, v in _gauge_free(left, sv, right).items():
+                store[f"{key}__{nm}"] = v
+            eigh_cases.append({"key": key, "mat": mname, "kw": kw,
+                               "n_keep": int(left.shape[1])})
+    meta["eigh_cases"] = eigh_cases
+    rand_cases = []
+    for mname, max_bond, absorb in [("lowrank", 4, 0), ("lowrank", 6, 1), ("lowrank", 5, -1),
+                                    ("decay", 8, 0), ("decay", 6, None), ("decay", 12, 1),
+                                    ("tall", 4, -1), ("wide", 5, 0), ("cplx", 6, 0),
+                                    ("decay", 5, 10), ("decay", 5, -11), ("tall", 10, 1)]:
+        x = mats[mname]
+        left, sv, right = decomp.svd_rand_truncated(x, max_bond=max_bond, absorb=absorb, seed=5)
+        sfull = np.linalg.svd(x, compute_uv=False)
+        k = (left.shape[1] if left is not None else right.shape[0])
+        rec_err = None
+        if left is not None and right is not None:
+            rec = left @ (np.diag(sv) @ right if sv is not None else right)
+            rec_err = float(np.linalg.norm(x - rec))
+        rand_cases.append({"mat": mname, "max_bond": max_bond, "absorb": absorb,
+                           "n_keep": int(k), "rec_err": rec_err,
+                           "optimal_err": float(np.sqrt(np.sum(sfull[k:] ** 2))),
+                           "has": [left is not None, sv is not None, right is not None]})
+    meta["rand_cases"] = rand_cases
+    meta["parse_split_opts"] = []
+    for kw in [dict(method="svd:eig"), dict(method="svd:eig", absorb="rfactor", max_bond=5, cutoff=None),
+               dict(method="svd:rand", max_bond=7), dict(method="svd:rand", max_bond=7, absorb="left", cutoff=1e-3),
+               dict(method="eigh", renorm=True, cutoff_mode="sum1"), dict(method="eigh", absorb=None),
+               dict(method="lq"), dict(method="qr", absorb="lorthog")]:
+        method, opts = decomp.parse_split_opts(**kw)
+        meta["parse_split_opts"].append({"kw": kw, "method": method, "opts": opts})
+    meta["svals"] = {}
+    for mname in ("tall", "wide", "cplx"):
+        store[f"svals__{mname}__svd"] = np.asarray(decomp.array_svals(mats[mname], method="svd"))
+        store[f"svals__{mname}__eig"] = np.asarray(decomp.array_svals(mats[mname], method="svd:eig"))
+    np.savez_compressed(os.path.join(OUT, "decomp2.npz"), **store)
+    json.dump(meta, open(os.path.join(OUT, "decomp2.json"), "w"), indent=1, default=str)
+
+
 def mps_dmrg_cases():
     store, meta = {}, {}
     # Heisenberg MPO of the reference, as arrays (lrud layout) + dense check
@@ -256,9 +376,10 @@ def mps_dmrg_cases():
 
 
 if __name__ == "__main__":
-    contract_cases()
-    decomp_cases()
-    mps_dmrg_cases()
+    only = set(sys.argv[1:])
+    for fn in (contract_cases, decomp_cases, decomp2_cases, mps_dmrg_cases):
+        if not only or fn.__name__ in only:
+            fn()
     print("golden fixtures written to", OUT)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

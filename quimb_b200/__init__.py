@@ -25,8 +25,10 @@ from .tree import (ContractExpression, GraphedContraction, Tree,  # noqa: F401
                    array_contract, find_tree, gen_output_inds, tensor_contract)
 from .mps import (env_left_step, env_right_step, mps_expec, mps_norm,  # noqa: F401
                   mps_norm2)
-from .split import (array_split, qr_stabilized, svd_truncated,  # noqa: F401
-                    tensor_canonize_bond, tensor_compress_bond, tensor_split)
+from .split import (array_split, array_svals, eigh_truncated,  # noqa: F401
+                    qr_stabilized, svd_rand_truncated, svd_truncated,
+                    svd_via_eig, svd_via_eig_truncated, tensor_canonize_bond,
+                    tensor_compress_bond, tensor_split)
 from .lanczos import eigh_lanczos  # noqa: F401
 from .dmrg import DMRG2  # noqa: F401
 from .integration import register_with_quimb  # noqa: F401

@@ -280,12 +280,14 @@ class DMRG2:
         self.nmatvecs.append(Heff.nmatvec)
         mat = loc_gs.reshape(a * s, t * b)
         absorb = get_U_sVH if direction == "right" else get_Us_VH
-        if method != "svd":
-            raise ValueError("quimb_b200.DMRG2: only method='svd' is implemented")
-        from .split import parse_split_opts
-        _, sopts = parse_split_opts("svd", absorb, max_bond, cutoff, cutoff_mode)
+        if method not in ("svd", "svd:eig"):
+            raise ValueError("quimb_b200.DMRG2: bond_compress_method must be "
+                             "'svd' or 'svd:eig'")
+        from .split import array_split
         sinfo = {"error": None}
-        left, _, right = svd_truncated(mat, info=sinfo, **sopts)
+        left, _, right = array_split(mat, method=method, absorb=absorb,
+                                     max_bond=max_bond, cutoff=cutoff,
+                                     cutoff_mode=cutoff_mode, info=sinfo)
         kdim = left.shape[1]
         self._k[i] = ops.materialize(left).reshape(a, s, kdim)
         self._k[i + 1] = ops.materialize(right).reshape(kdim, t, b)

@@ -45,6 +45,19 @@ def register_with_quimb():
     decomp.qr_stabilized.register(name)(_qr_stabilized)
     done.append("qr_stabilized")
 
+    def _svd_via_eig_truncated(x, cutoff=-1.0, cutoff_mode=4, max_bond=-1, absorb=0,
+                               renorm=0, info=None, **kwargs):
+        return split.svd_via_eig_truncated(x, cutoff=cutoff, cutoff_mode=cutoff_mode,
+                                           max_bond=max_bond, absorb=absorb,
+                                           renorm=renorm, info=info)
+
+    for nm, fn in (("svd_via_eig_truncated", _svd_via_eig_truncated),
+                   ("svd_rand_truncated", split.svd_rand_truncated),
+                   ("eigh_truncated", split.eigh_truncated)):
+        if hasattr(decomp, nm) and hasattr(getattr(decomp, nm), "register"):
+            getattr(decomp, nm).register(name)(fn)
+            done.append(nm)
+
     def _norm_fro(x):
         from .linalg import norm
         return norm(x)

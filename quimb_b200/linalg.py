@@ -248,15 +248,38 @@ def norm(x, ord=None):
     return ops.sqrt(ops.real(ops.vdot(flat, flat)))
 
 
-def eigh(x):
-    """Small dense symmetric eigenproblems (Lanczos tridiagonals, DMRG's
-    dense-Heff branch for prod(dims) < 800) are host-side control logic in
-    the reference too (dmrg.py:690); they are solved on the host."""
-    if x.shape[0] > 64:
-        raise NotImplementedError(
-            "quimb_b200.linalg.eigh: only the tiny projected (Krylov) problems "
-            "are solved here; for operators use eigh_lanczos (no dense device "
-            "eigh yet, and no CPU fallback)")
-    a = ops.to_numpy(x)
-    w, v = np.linalg.eigh(a)
-    return ops.asarray(w), ops.asarray(v)
+def eigh(x, host_below=64):
+    """Hermitian eigendecomposition ``x = v diag(w) v^H`` (``w`` ascending,
+    as numpy / the reference's ``xp.linalg.eigh``).
+
+    Tiny problems (n <= ``host_below``: Lanczos tridiagonals, DMRG's dense-Heff
+    branch for prod(dims) < 800, dmrg.py:690) are host-side control logic in
+    the reference too and are solved on the host.  Anything larger runs on the
+    device through the one-sided Jacobi kernel: with ``sigma = |x|_F`` the
+    matrix ``x + sigma I`` is positive semi-definite, so its singular value
+    decomposition *is* its eigendecomposition (U = V) and
+    ``w = s - sigma``; eigenvalues are accurate to ``eps * |x|_F`` like any
+    backward-stable dense eigensolver.  complex128 goes through the real
+    embedding, float32 / complex64 through the exact widening pass (both
+    inherited from :func:`svd`).  ``sigma`` never leaves the device."""
+    x = ops.asarray(x)
+    if x.ndim != 2 or x.shape[0] != x.shape[1]:
+        raise ValueError(f"eigh: expected a square matrix, got shape {x.shape}")
+    n = x.shape[0]
+    if n <= host_below:
+        a = ops.to_numpy(x)
+        w, v = np.linalg.eigh(a)
+        return ops.asarray(w), ops.asarray(v)
+    xm = ops.materialize(x, force=True)            # private copy (shifted in place)
+    _lib.require_cuda(xm.t)
+    sigma = norm(xm)                               # 0-d, real, on the device
+    sg = sigma.t.to(_REAL_OF[xm.t.dtype])
+    xm.t.diagonal().add_(sg)
+    _, s, VH = svd(xm)
+    w = (s.t - sg.to(s.t.dtype)).flip(0)           # ascending
+    v = Array(VH.t.flip(0).transpose(0, 1), not VH.cj)   # v[:, i] = conj(VH[k-1-i, :])
+    return Array(w), v
+
+
+_REAL_OF = {torch.float32: torch.float32, torch.float64: torch.float64,
+            torch.complex64: torch.float32, torch.complex128: torch.float64}

@@ -48,11 +48,30 @@ _SVD_ABSORBS = set(_ABSORB_MAP.values())
 _QR_ABSORBS = {get_U_sVH, get_U, get_sVH, get_Us_VH, get_Us, get_VH}
 
 
-_DEFAULT_ABSORB = {"svd": get_Usq_sqVH, "qr": get_U_sVH}
+_DEFAULT_ABSORB = {"svd": get_Usq_sqVH, "svd:eig": get_Usq_sqVH,
+                   "svd:rand": get_Usq_sqVH, "eigh": get_Usq_sqVH,
+                   "qr": get_U_sVH}
+# which options each driver takes (the reference inspects the signature of
+# _SPLIT_FNS[method], decomp.py:391-422)
+_METHOD_OPTS = {
+    "svd": ("absorb", "max_bond", "cutoff", "cutoff_mode", "renorm"),
+    "svd:eig": ("absorb", "max_bond", "cutoff", "cutoff_mode", "renorm"),
+    "eigh": ("absorb", "max_bond", "cutoff", "cutoff_mode", "renorm"),
+    "svd:rand": ("absorb", "max_bond"),
+    "qr": ("absorb",),
+}
 
 
 def parse_method_absorb(method="auto", absorb="auto", truncation=True):
-    """decomp.py:307-365: resolve 'auto' settings, map aliases to codes."""
+    """decomp.py:294-365: resolve 'auto' settings, map aliases to codes."""
+    if method == "eig":
+        import warnings
+        warnings.warn(
+            "`method='eig'` has been renamed to `method='svd:eig'` for "
+            "consistency. In future it might apply the non-hermitian "
+            "eigendecomposition instead of the SVD via eig, use 'svd:eig' "
+            "to keep the current behaviour.", FutureWarning)
+        method = "svd:eig"
     if method == "auto":
         if truncation or absorb == "auto":
             method = "svd"
@@ -66,7 +85,8 @@ def parse_method_absorb(method="auto", absorb="auto", truncation=True):
             absorb = "left"
     if method not in _DEFAULT_ABSORB:
         raise ValueError(f"quimb_b200: split method {method!r} is not "
-                         "implemented (available: 'svd', 'qr', 'lq')")
+                         "implemented (available: 'svd', 'svd:eig', 'svd:rand', "
+                         "'eigh', 'qr', 'lq')")
     if absorb == "auto":
         absorb = _DEFAULT_ABSORB[method]
     else:
@@ -77,23 +97,28 @@ def parse_method_absorb(method="auto", absorb="auto", truncation=True):
 def parse_split_opts(method="auto", absorb="auto", max_bond=None,
                      cutoff=1e-10, cutoff_mode="rsum2", renorm=None):
     """Resolve options to numeric codes exactly as decomp.py:369-424 does for
-    the methods this backend implements ('svd', 'qr' / 'lq')."""
+    the methods this backend implements ('svd', 'svd:eig', 'svd:rand', 'eigh',
+    'qr' / 'lq'): only the options the driver takes are injected."""
     max_bond = -1 if max_bond is None else max_bond
     cutoff = -1.0 if cutoff is None else cutoff
     truncation = (max_bond > 0) or (cutoff > 0.0)
     method, absorb = parse_method_absorb(method, absorb, truncation)
+    takes = _METHOD_OPTS[method]
     opts = {"absorb": absorb}
-    if method == "svd":
+    if method == "qr" and absorb is None:
+        raise ValueError("You can't return the singular values separately when "
+                         f"`method='{method}'`.")
+    if "max_bond" in takes:
+        opts["max_bond"] = max_bond
+    if "cutoff" in takes:
+        opts["cutoff"] = cutoff
         cutoff_mode = _CUTOFF_MODE_MAP[cutoff_mode]
+        opts["cutoff_mode"] = cutoff_mode
         if renorm is True:
             renorm = _RENORM_LOOKUP.get(cutoff_mode, 0)
         else:
             renorm = 0 if renorm is None else renorm
-        opts.update(max_bond=max_bond, cutoff=cutoff, cutoff_mode=cutoff_mode,
-                    renorm=renorm)
-    elif absorb is None:
-        raise ValueError("You can't return the singular values separately when "
-                         f"`method='{method}'`.")
+        opts["renorm"] = renorm
     return method, opts
 
 
@@ -123,20 +148,60 @@ def svals_to_keep(s_host, cutoff, cutoff_mode, max_bond, renorm):
     return int(n_keep.value), float(f.value), float(err.value)
 
 
-def svd_truncated(x, cutoff=-1.0, cutoff_mode=4, max_bond=-1,
-                  absorb=get_Usq_sqVH, renorm=0, info=None):
-    """Truncated SVD of a 2-d device array; returns (left, s, right) with
-    ``None`` for parts the absorb mode does not request."""
-    absorb = _ABSORB_MAP[absorb]
-    cutoff_mode = _CUTOFF_MODE_MAP[cutoff_mode]
-    U, s, VH = linalg.svd(x)
-    s_host = s.t.cpu().numpy()  # the one host read of the split
-    n_keep, f, err = svals_to_keep(s_host, cutoff, cutoff_mode, max_bond, renorm)
+def _rdmul(x, d, sqrt_d=False):
+    """x[:, j] *= d[j]^p on a contiguous copy-if-needed (decomp.py:580-589)."""
+    x = x if x.is_contiguous() else x.contiguous()
+    return _scale_diag(x, d, 1, sqrt_d)
+
+
+def _ldmul(d, x, sqrt_d=False):
+    """x[i, :] *= d[i]^p (decomp.py:607-616)."""
+    x = x if x.is_contiguous() else x.contiguous()
+    return _scale_diag(x, d, 0, sqrt_d)
+
+
+def _do_absorb(Ut, st, Vt, absorb):
+    """decomp.py:662-690 on torch views: returns (left, s, right) Arrays with
+    ``None`` for parts the mode does not request.  Factors that get scaled are
+    private copies (slices of U / VH are made contiguous first)."""
+    if absorb is None:
+        return Array(Ut), Array(st), Array(Vt)
+    if absorb == get_s:
+        return None, Array(st), None
+    left = right = None
+    if absorb in (get_Us_VH, get_Us):
+        left = _rdmul(Ut, st)
+    elif absorb in (get_Usq_sqVH, get_Usq):
+        left = _rdmul(Ut, st, True)
+    elif absorb in (get_U_sVH, get_U):
+        left = Ut
+    if absorb in (get_U_sVH, get_sVH):
+        right = _ldmul(st, Vt)
+    elif absorb in (get_Usq_sqVH, get_sqVH):
+        right = _ldmul(st, Vt, True)
+    elif absorb in (get_Us_VH, get_VH):
+        right = Vt if Vt.is_contiguous() else Vt.contiguous()
+    if left is None and right is None:
+        raise ValueError(f"Invalid absorb mode: {absorb}")
+    return (None if left is None else Array(left), None,
+            None if right is None else Array(right))
+
+
+def _trim_renorm_absorb(Ut, st, Vt, cutoff=-1.0, cutoff_mode=4, max_bond=-1,
+                        absorb=get_Usq_sqVH, renorm=0, use_abs=False, info=None):
+    """``_trim_and_renorm_svd_result`` (decomp.py:724-826 / numba :968-1029)
+    for device factors ``Ut (m,k)``, ``st (k,)``, ``Vt (k,n)`` (torch views,
+    ``st`` real and ordered by decreasing magnitude).  The truncation rule is
+    the reference's, evaluated by the C library on the host copy of the
+    (absolute) values -- the one device->host read of a split: the kept rank
+    decides the output shapes."""
+    s_host = st.detach().cpu().numpy().astype(np.float64, copy=False)
+    sabs = np.abs(s_host) if use_abs else s_host
+    n_keep, f, err = svals_to_keep(sabs, cutoff, cutoff_mode, max_bond, renorm)
     if info is not None and "error" in info:
         info["error"] = err
     if info is not None:
         info["n_keep"] = n_keep
-    Ut, st, Vt = U.t, s.t, VH.t
     if n_keep < st.shape[0]:
         Ut = Ut[:, :n_keep].contiguous()
         Vt = Vt[:n_keep, :]
@@ -144,33 +209,290 @@ def svd_truncated(x, cutoff=-1.0, cutoff_mode=4, max_bond=-1,
         if f != 1.0:
             st = st * f
         st = st.contiguous()
-    want_left = absorb in (None, get_Usq, get_Us, get_Us_VH, get_Usq_sqVH,
-                           get_U_sVH, get_U)
-    want_right = absorb in (None, get_VH, get_Us_VH, get_Usq_sqVH, get_U_sVH,
-                            get_sVH, get_sqVH)
-    left = right = sv = None
-    if absorb is None:
-        return Array(Ut), Array(st), Array(Vt)
-    if absorb == get_s:
-        return None, Array(st), None
-    if want_left:
-        if absorb in (get_Us_VH, get_Us):
-            left = _scale_diag(Ut if Ut.is_contiguous() else Ut.contiguous(), st, 1, False)
-        elif absorb in (get_Usq_sqVH, get_Usq):
-            left = _scale_diag(Ut if Ut.is_contiguous() else Ut.contiguous(), st, 1, True)
+    return _do_absorb(Ut, st, Vt, absorb)
+
+
+def svd_truncated(x, cutoff=-1.0, cutoff_mode=4, max_bond=-1,
+                  absorb=get_Usq_sqVH, renorm=0, info=None):
+    """Truncated SVD of a 2-d device array; returns (left, s, right) with
+    ``None`` for parts the absorb mode does not request
+    (decomp.py:829-898)."""
+    absorb = _ABSORB_MAP[absorb]
+    cutoff_mode = _CUTOFF_MODE_MAP[cutoff_mode]
+    U, s, VH = linalg.svd(x)
+    return _trim_renorm_absorb(U.t, s.t, VH.t, cutoff, cutoff_mode, max_bond,
+                               absorb, renorm, info=info)
+
+
+def svdvals(x):
+    """Singular values only, descending (decomp.py:1159-1165)."""
+    return linalg.svd(x)[1]
+
+
+# ------------------------------------------------ SVD via the Gram matrix ---
+def _dag(x):
+    return x.conj().transpose(1, 0)
+
+
+def _safe_inverse(s, cutoff):
+    """decomp.py:501-551 with power=1 on a real device vector ``s``; ``cutoff``
+    is a 0-d / 1-element device tensor.  Stays on the device (no sync)."""
+    xmax = s.max()
+    xmax = torch.where(xmax > 0.0, xmax, torch.ones_like(xmax))
+    c = cutoff / xmax
+    y = s / xmax
+    return y / ((y * y + c * c) * xmax)
+
+
+def svd_via_eig(x, absorb=None, max_bond=-1, descending=True, right=None):
+    """SVD through the Hermitian eigendecomposition of the Gram matrix
+    (``x^H x`` for tall, ``x x^H`` for wide), with static truncation and the
+    per-absorb shortcuts of decomp.py:1168-1361.  Gram matrix and
+    back-multiplications are launches of the contraction kernel (conjugate
+    transposes are load flags), the eigendecomposition is the device
+    ``linalg.eigh``; singular values below ``sqrt(eps) * s_max`` carry the
+    method's inherent loss of relative accuracy, exactly as in the reference.
+    """
+    x = ops.asarray(x)
+    if x.ndim != 2:
+        raise ValueError("svd_via_eig: only 2-d arrays are supported")
+    m, n = x.shape
+    absorb = _ABSORB_MAP[absorb]
+    xdag = _dag(x)
+    if right is None:
+        if m > n:
+            right = True
+        elif m < n:
+            right = False
         else:
-            left = Ut
-        left = Array(left)
-    if want_right:
-        Vc = Vt if Vt.is_contiguous() else Vt.contiguous()
-        if absorb in (get_U_sVH, get_sVH):
-            right = _scale_diag(Vc, st, 0, False)
-        elif absorb in (get_Usq_sqVH, get_sqVH):
-            right = _scale_diag(Vc, st, 0, True)
+            right = absorb in (get_VH, get_sVH, get_sqVH, get_Us_VH)
+    eps = float(np.finfo(x.dtype).eps)
+
+    def eig_desc(G):
+        s2, V = linalg.eigh(G)                      # ascending
+        s2t, Vt = s2.t, V
+        k = s2t.shape[0]
+        lo = k - max_bond if 0 < max_bond < min(m, n) else 0
+        s2t = s2t[lo:]
+        Vt = Array(V.t[:, lo:], V.cj)
+        if descending:
+            s2t = s2t.flip(0)
+            Vt = Array(Vt.t.flip(1), Vt.cj)
+        return torch.clamp(s2t, min=0.0), Vt
+
+    if right:
+        s2, V = eig_desc(ops.matmul(xdag, x))
+        if absorb == get_s:
+            return None, Array(torch.sqrt(s2)), None
+        VH = _dag(V)
+        if absorb == get_VH:
+            return None, None, ops.materialize(VH)
+        if absorb == get_sVH:
+            return None, None, Array(_ldmul(torch.sqrt(s2), ops.materialize(VH, force=True).t))
+        if absorb == get_sqVH:
+            return None, None, Array(_ldmul(torch.sqrt(torch.sqrt(s2)),
+                                            ops.materialize(VH, force=True).t))
+        Us = ops.matmul(x, V)
+        if absorb == get_Us:
+            return Us, None, None
+        if absorb == get_Us_VH:
+            return Us, None, ops.materialize(VH)
+        s = torch.sqrt(s2)
+        smax = s[0:1] if descending else s[-1:]
+        sinv = _safe_inverse(s, smax * eps * max(m, n))
+        U = _rdmul(Us.t, sinv)
+        if absorb == get_U:
+            return Array(U), None, None
+        if absorb == get_Usq:
+            return Array(_rdmul(U, s, True)), None, None
+        VHm = ops.materialize(VH, force=True).t
+        if absorb is None:
+            return Array(U), Array(s), Array(VHm)
+        if absorb == get_U_sVH:
+            return Array(U), None, Array(_ldmul(s, VHm))
+        if absorb == get_Usq_sqVH:
+            return Array(_rdmul(U, s, True)), None, Array(_ldmul(s, VHm, True))
+    else:
+        s2, U = eig_desc(ops.matmul(x, xdag))
+        if absorb == get_s:
+            return None, Array(torch.sqrt(s2)), None
+        if absorb == get_U:
+            return ops.materialize(U), None, None
+        if absorb == get_Us:
+            return Array(_rdmul(ops.materialize(U, force=True).t, torch.sqrt(s2))), None, None
+        if absorb == get_Usq:
+            return Array(_rdmul(ops.materialize(U, force=True).t,
+                                torch.sqrt(torch.sqrt(s2)))), None, None
+        sVH = ops.matmul(_dag(U), x)
+        if absorb == get_sVH:
+            return None, None, sVH
+        if absorb == get_U_sVH:
+            return ops.materialize(U), None, sVH
+        s = torch.sqrt(s2)
+        smax = s[0:1] if descending else s[-1:]
+        sinv = _safe_inverse(s, smax * eps * max(m, n))
+        VH = _ldmul(sinv, sVH.t)
+        if absorb == get_VH:
+            return None, None, Array(VH)
+        Um = ops.materialize(U, force=True).t
+        if absorb is None:
+            return Array(Um), Array(s), Array(VH)
+        if absorb == get_Us_VH:
+            return Array(_rdmul(Um, s)), None, Array(VH)
+        if absorb == get_Usq_sqVH:
+            return Array(_rdmul(Um, s, True)), None, Array(_ldmul(s, VH, True))
+        if absorb == get_sqVH:
+            return None, None, Array(_ldmul(s, VH, True))
+    raise ValueError(f"Invalid absorb mode: {absorb}")
+
+
+def svd_via_eig_truncated(x, cutoff=-1.0, cutoff_mode=4, max_bond=-1,
+                          absorb=get_Usq_sqVH, renorm=0, info=None):
+    """``method='svd:eig'`` (decomp.py:1364-1444): full spectrum + dynamic
+    truncation when a cutoff / renorm / error is requested, else the one-step
+    statically truncated shortcuts of :func:`svd_via_eig`."""
+    absorb = _ABSORB_MAP[absorb]
+    cutoff_mode = _CUTOFF_MODE_MAP[cutoff_mode]
+    need_full = (cutoff > 0.0) or (renorm > 0) or (info is not None and "error" in info)
+    if need_full:
+        U, s, VH = svd_via_eig(x, absorb=None, max_bond=-1, descending=True)
+        return _trim_renorm_absorb(U.t, s.t, VH.t, cutoff, cutoff_mode, max_bond,
+                                   absorb, renorm, info=info)
+    return svd_via_eig(x, absorb=absorb, max_bond=max_bond, descending=False)
+
+
+def svdvals_eig(x):
+    """decomp.py:1673-1686: singular values from the smaller Gram matrix."""
+    return svd_via_eig(x, absorb=get_s, descending=True)[1]
+
+
+# ------------------------------------------------------- randomized SVD -----
+def svd_rand_truncated(x, max_bond, absorb=get_Usq_sqVH, oversample=10,
+                       num_iterations=2, method_lorthog="qr", method_reduced="svd",
+                       right=None, lorthog_opts=None, reduced_opts=None, seed=None):
+    """``method='svd:rand'`` (decomp.py:1689-1861): randomized range finder
+    (Gaussian sketch + ``num_iterations`` power iterations, all tensor-core
+    GEMMs on the contraction kernel), orthonormal basis by the device QR,
+    small factorisation of the reduced matrix, expansion back.  The Gaussian
+    sketch is drawn on the device by torch's generator (the container
+    library), seeded by ``seed``."""
+    absorb = _ABSORB_MAP[absorb]
+    if max_bond is None:
+        max_bond = -1
+    lorthog_opts = dict(lorthog_opts or {})
+    lorthog_opts.setdefault("method", method_lorthog)
+    x = ops.asarray(x)
+    if x.ndim != 2:
+        raise ValueError("svd_rand_truncated: only 2-d arrays are supported")
+    m, n = x.shape
+    if max_bond < 0:
+        import warnings
+        warnings.warn("Using 'svd:rand' without `max_bond` is inefficient, "
+                      "consider simply using 'svd' or 'svd:eig' instead.")
+        k = min(m, n)
+    else:
+        k = min(m, n, max_bond)
+    k_sketch = min(m, n, k + oversample)
+    if right is None:
+        if absorb in (get_U_sVH, get_U, get_sVH):
+            right = True
+        elif absorb in (get_Us_VH, get_Us, get_VH):
+            right = False
         else:
-            right = Vc
-        right = Array(right)
-    return left, sv, right
+            right = m > n
+    if isinstance(seed, torch.Generator):
+        gen = seed
+    else:
+        gen = torch.Generator(device=x.t.device)
+        if seed is None:
+            gen.seed()
+        else:
+            gen.manual_seed(int(seed))
+    rdt = x.t.real.dtype if x.t.dtype.is_complex else x.t.dtype
+
+    def normal(shape):
+        # the reference draws a real sketch also for complex x (rng.normal)
+        om = torch.randn(shape, generator=gen, dtype=rdt, device=x.t.device)
+        return Array(om.to(x.t.dtype) if x.t.dtype.is_complex else om)
+
+    xdag = _dag(x)
+    if right:
+        y = ops.matmul(x, normal((n, k_sketch)))
+        for _ in range(num_iterations):
+            y = ops.matmul(x, ops.matmul(xdag, y))
+        Q, _, _ = array_split(y, absorb=get_U, **lorthog_opts)
+        if k >= k_sketch:
+            if absorb == get_U_sVH:
+                return Q, None, ops.matmul(_dag(Q), x)
+            if absorb == get_sVH:
+                return None, None, ops.matmul(_dag(Q), x)
+            if absorb == get_U:
+                return Q, None, None
+        B = ops.matmul(_dag(Q), x)
+    else:
+        y = ops.matmul(normal((k_sketch, m)), x)
+        for _ in range(num_iterations):
+            y = ops.matmul(ops.matmul(y, xdag), x)
+        Q, _, _ = array_split(_dag(y), absorb=get_U, **lorthog_opts)
+        if k >= k_sketch:
+            if absorb == get_Us_VH:
+                return ops.matmul(x, Q), None, ops.materialize(_dag(Q))
+            if absorb == get_Us:
+                return ops.matmul(x, Q), None, None
+            if absorb == get_VH:
+                return None, None, ops.materialize(_dag(Q))
+        B = ops.matmul(x, Q)
+    reduced_opts = dict(reduced_opts or {})
+    reduced_opts.setdefault("method", method_reduced)
+    reduced_opts.setdefault("cutoff", 0.0)
+    U, s, VH = array_split(B, absorb=absorb, max_bond=k, **reduced_opts)
+    if U is not None and right:
+        U = ops.matmul(Q, U)
+    if VH is not None and not right:
+        VH = ops.matmul(VH, _dag(Q))
+    return U, s, VH
+
+
+# --------------------------------------------------- Hermitian 'eigh' split --
+def _with_diag_shift(x, shift=0.0):
+    """decomp.py:1867-1881: x + shift * trace(x) * I (shift < 0: machine eps)."""
+    x = ops.asarray(x)
+    if shift < 0.0:
+        shift = float(np.finfo(x.dtype).eps)
+    if shift > 0.0:
+        xm = ops.materialize(x, force=True)
+        tr = ops.trace(xm)
+        xm.t.diagonal().add_(shift * tr.t)
+        return xm
+    return x
+
+
+def eigh_truncated(x, cutoff=-1.0, cutoff_mode=4, max_bond=-1,
+                   absorb=get_Usq_sqVH, renorm=0, positive=0, shift=False):
+    """``method='eigh'`` (decomp.py:1899-1969): SVD-like split of a Hermitian
+    matrix from its eigendecomposition; values keep their sign unless
+    ``positive`` (then negative ones are clipped for the sqrt absorbs)."""
+    absorb = _ABSORB_MAP[absorb]
+    cutoff_mode = _CUTOFF_MODE_MAP[cutoff_mode]
+    shift = {False: 0.0, True: -1.0}.get(shift, shift)
+    x = _with_diag_shift(x, shift)
+    w, V = linalg.eigh(x)
+    wt = w.t
+    if not positive:
+        # largest magnitude first (stable order on the host copy: the values
+        # are read for the truncation rule anyway)
+        idx = np.argsort(-np.abs(wt.detach().cpu().numpy()), kind="stable")
+        idx = torch.as_tensor(idx, dtype=torch.int64, device=wt.device)
+        st = wt.index_select(0, idx)
+        Ut = V.resolve().index_select(1, idx)
+    else:
+        st = wt.flip(0)
+        Ut = V.resolve().flip(1)
+        if absorb in (get_Usq_sqVH, get_Usq, get_sqVH):
+            st = torch.clamp(st, min=0.0)
+    Vt = ops.materialize(Array(Ut.transpose(0, 1), True)).t      # U^H
+    return _trim_renorm_absorb(Ut, st.contiguous(), Vt, cutoff, cutoff_mode,
+                               max_bond, absorb, renorm, use_abs=not positive)
 
 
 def qr_stabilized(x, absorb=get_U_sVH, stabilized=True):
@@ -191,19 +513,37 @@ def qr_stabilized(x, absorb=get_U_sVH, stabilized=True):
     raise ValueError(f"Invalid absorb mode for qr_stabilized: {absorb}")
 
 
+_SPLIT_FNS = {
+    "svd": svd_truncated,
+    "svd:eig": svd_via_eig_truncated,
+    "svd:rand": svd_rand_truncated,
+    "eigh": eigh_truncated,
+    "qr": qr_stabilized,
+}
+_SPLIT_VALUES_FNS = {"svd": svdvals, "svd:eig": svdvals_eig}
+
+
 def array_split(x, method="auto", absorb="auto", max_bond=None, cutoff=1e-10,
-                cutoff_mode="rsum2", renorm=None, info=None):
-    """decomp.py:35-174 for the implemented methods."""
+                cutoff_mode="rsum2", renorm=None, info=None, **kwargs):
+    """decomp.py:35-174 for the implemented methods; ``kwargs`` go to the
+    driver (e.g. ``positive`` / ``shift`` for 'eigh', ``oversample`` / ``seed``
+    for 'svd:rand')."""
     method, opts = parse_split_opts(method, absorb, max_bond, cutoff,
                                     cutoff_mode, renorm)
-    if method == "svd":
-        return svd_truncated(x, info=info, **opts)
-    return qr_stabilized(x, absorb=opts["absorb"])
+    if method in ("svd", "svd:eig"):
+        opts["info"] = info
+    return _SPLIT_FNS[method](x, **opts, **kwargs)
+
+
+def array_svals(x, method="svd", **kwargs):
+    """decomp.py:177-198: singular values without the factors."""
+    method = parse_method_absorb(method, None, True)[0]
+    return _SPLIT_VALUES_FNS[method](x, **kwargs)
 
 
 def tensor_split(x, inds, left_inds, right_inds=None, method="auto",
                  absorb="auto", max_bond=None, cutoff=1e-10,
-                 cutoff_mode="rel", renorm=None, info=None):
+                 cutoff_mode="rel", renorm=None, info=None, **split_opts):
     """Array-level ``tensor_split(..., get='arrays')`` (tensor_core.py:392-668):
     transpose to (left..., right...), fuse to a matrix (one permute-copy
     kernel), split, unfuse.  Returns the non-None parts in order
@@ -227,7 +567,7 @@ def tensor_split(x, inds, left_inds, right_inds=None, method="auto",
     left, s, right = array_split(mat, method=method, absorb=absorb,
                                  max_bond=max_bond, cutoff=cutoff,
                                  cutoff_mode=cutoff_mode, renorm=renorm,
-                                 info=info)
+                                 info=info, **split_opts)
     out = []
     if left is not None:
         out.append(left.reshape(*ldims, -1))

@@ -49,3 +49,8 @@ def golden_decomp():
 @pytest.fixture(scope="session")
 def golden_mps():
     return load_golden("mps_dmrg")
+
+
+@pytest.fixture(scope="session")
+def golden_decomp2():
+    return load_golden("decomp2")

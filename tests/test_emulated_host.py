@@ -27,6 +27,7 @@ _SKIP = {
     # spawns worker processes on the real device
     "test_gpu_mps_dmrg": {"test_bond_sharded_eigensolve_two_ranks_one_gpu"},
     "test_gpu_split": set(),
+    "test_gpu_split2": set(),
 }
 
 

@@ -193,3 +193,76 @@ def test_bond_canonize_compress_match_reference(golden_decomp):
         assert xa.shape == ra.shape and xb.shape == rb.shape and xa.shape[1] == c["bond"]
         np.testing.assert_allclose(np.einsum("axb,cxd->abcd", xa, xb),
                                    np.einsum("axb,cxd->abcd", ra, rb), atol=1e-11)
+
+
+def _images(left, sv, right):
+    out = {}
+    if sv is not None:
+        out["s"] = sv
+    if left is not None and right is not None:
+        out["rec"] = left @ (np.diag(sv) @ right if sv is not None else right)
+    elif left is not None:
+        out["lgram"] = left @ left.conj().T
+    elif right is not None:
+        out["rgram"] = right.conj().T @ right
+    return out
+
+
+def test_svd_via_eig_oracle_matches_reference(golden_decomp2):
+    """oracle 'svd:eig' (decomp.py:1168-1444) vs the reference's numba path:
+    both lose relative accuracy below sqrt(eps) * smax, by the method."""
+    data, meta = golden_decomp2
+    for c in meta["eig_cases"]:
+        x = data[f"mat__{c['mat']}"]
+        info = {"error": None} if c["error"] is not None else None
+        left, sv, right = dn.svd_via_eig_truncated(
+            x, cutoff=c["cutoff"], cutoff_mode=c["cutoff_mode"], max_bond=c["max_bond"],
+            absorb=c["absorb"], renorm=c["renorm"], info=info)
+        assert [left is not None, sv is not None, right is not None] == c["has"], c
+        smax = np.linalg.norm(x, 2)
+        if info is not None:
+            assert info["n_keep"] == c["n_keep"], c
+            assert abs(info["error"] - c["error"]) <= 1e-7 * smax
+        for nm, val in _images(left, sv, right).items():
+            if c["mat"] == "lowrank" and nm.endswith("gram") and c["absorb"] in (10, -11):
+                continue
+            scale = smax ** (2 if nm.endswith("gram") else 1)
+            np.testing.assert_allclose(val, data[f"{c['key']}__{nm}"], atol=2e-7 * scale,
+                                       err_msg=str(c))
+
+
+def test_eigh_truncated_oracle_matches_reference(golden_decomp2):
+    data, meta = golden_decomp2
+    for c in meta["eigh_cases"]:
+        x = data[f"mat__{c['mat']}"]
+        left, sv, right = dn.eigh_truncated(x, **c["kw"])
+        assert left.shape[1] == c["n_keep"], c
+        for nm, val in _images(left, sv, right).items():
+            np.testing.assert_allclose(val, data[f"{c['key']}__{nm}"],
+                                       atol=1e-11 * np.linalg.norm(x, 2), err_msg=str(c))
+
+
+def test_svd_rand_oracle_matches_reference(golden_decomp2):
+    """Same numpy Generator and seed as the reference -> same sketch: the
+    reconstruction error agrees to rounding."""
+    data, meta = golden_decomp2
+    for c in meta["rand_cases"]:
+        x = data[f"mat__{c['mat']}"]
+        left, sv, right = dn.svd_rand_truncated(x, c["max_bond"], absorb=c["absorb"], seed=5)
+        assert [left is not None, sv is not None, right is not None] == c["has"], c
+        k = left.shape[1] if left is not None else right.shape[0]
+        assert k == c["n_keep"], c
+        if c["rec_err"] is not None:
+            rec = left @ (np.diag(sv) @ right if sv is not None else right)
+            err = np.linalg.norm(x - rec)
+            assert abs(err - c["rec_err"]) <= 1e-8 * np.linalg.norm(x) + 1e-6 * c["rec_err"], c
+
+
+def test_svals_drivers_match_reference(golden_decomp2):
+    data, _ = golden_decomp2
+    for mname in ("tall", "wide", "cplx"):
+        x = data[f"mat__{mname}"]
+        np.testing.assert_allclose(np.linalg.svd(x, compute_uv=False),
+                                   data[f"svals__{mname}__svd"], rtol=1e-12)
+        np.testing.assert_allclose(dn.svd_via_eig(x, absorb=dn.get_s)[1],
+                                   data[f"svals__{mname}__eig"], rtol=1e-9)
