@@ -152,24 +152,45 @@ def require_cuda(t, what="operand"):
         )
 
 
+_DESC_CACHE = {}
+_LABEL_CACHE = {}
+
+
 def desc(t, ptr_override=None):
-    """Build the C descriptor of a (strided) torch tensor view."""
-    if t.dim() > QB_MAX_RANK:
-        raise ValueError(f"tensor rank {t.dim()} exceeds QB_MAX_RANK")
+    """C descriptor of a (strided) torch tensor view.  Descriptors are plain
+    values the library only reads, so they are memoised on (pointer, dtype,
+    shape, strides): trees over many small tensors are host-bound and filling
+    a 528-byte ctypes struct costs ~4 us."""
+    ptr = t.data_ptr() if ptr_override is None else ptr_override
+    key = (ptr, t.dtype, t.shape, t.stride())
+    d = _DESC_CACHE.get(key)
+    if d is not None:
+        return d
+    rank = t.dim()
+    if rank > QB_MAX_RANK:
+        raise ValueError(f"tensor rank {rank} exceeds QB_MAX_RANK")
     d = qb_tensor_t()
-    d.ptr = t.data_ptr() if ptr_override is None else ptr_override
+    d.ptr = ptr
     d.dtype = qb_dtype(t.dtype)
-    d.rank = t.dim()
-    for i, (s, st) in enumerate(zip(t.shape, t.stride())):
-        d.shape[i] = s
-        d.stride[i] = st
+    d.rank = rank
+    if rank:
+        d.shape[:rank] = list(t.shape)
+        d.stride[:rank] = list(t.stride())
+    if len(_DESC_CACHE) >= 8192:
+        _DESC_CACHE.clear()
+    _DESC_CACHE[key] = d
     return d
 
 
 def labels(seq):
-    arr = (ctypes.c_int32 * max(len(seq), 1))()
-    for i, v in enumerate(seq):
-        arr[i] = v
+    """int32 label array (memoised per label tuple)."""
+    key = tuple(seq)
+    arr = _LABEL_CACHE.get(key)
+    if arr is None:
+        arr = (ctypes.c_int32 * max(len(key), 1))(*key)
+        if len(_LABEL_CACHE) >= 8192:
+            _LABEL_CACHE.clear()
+        _LABEL_CACHE[key] = arr
     return arr
 
 
