@@ -332,6 +332,62 @@ def decomp2_cases():
     json.dump(meta, open(os.path.join(OUT, "decomp2.json"), "w"), indent=1, default=str)
 
 
+def _dump_tn2d(tn, key, store):
+    """Store every tensor of a 2D network: data, index names, site, layer."""
+    recs = []
+    for k, t in enumerate(tn.tensors):
+        site = [tg for tg in t.tags if tg.startswith("I")]
+        assert len(site) == 1
+        i, j = map(int, site[0][1:].split(","))
+        layer = "KET" if "KET" in t.tags else ("BRA" if "BRA" in t.tags else None)
+        store[f"{key}__t{k}"] = np.asarray(t.data)
+        recs.append({"inds": list(map(str, t.inds)), "site": [i, j], "layer": layer})
+    return recs
+
+
+def boundary_cases():
+    """contract_boundary (mode='mps') of the reference on small PEPS norm
+    networks (two-layer) and flat 2D networks."""
+    store, meta = {}, {}
+    nets = {}
+    p = qtn.PEPS.rand(4, 4, bond_dim=3, phys_dim=2, seed=4, dtype="complex128")
+    nets["peps44"] = (p.make_norm(), ("KET", "BRA"))
+    p2 = qtn.PEPS.rand(3, 5, bond_dim=2, phys_dim=2, seed=7, dtype="float64")
+    nets["peps35"] = (p2.make_norm(), ("KET", "BRA"))
+    p3 = qtn.PEPS.rand(5, 3, bond_dim=2, phys_dim=2, seed=9, dtype="complex64")
+    nets["peps53_c64"] = (p3.make_norm(), ("KET", "BRA"))
+    nets["flat55"] = (qtn.TN2D_rand(5, 5, D=3, seed=2), None)
+    nets["flat64"] = (qtn.TN2D_rand(6, 4, D=2, seed=3, dtype="complex128"), None)
+    for name, (tn, layers) in nets.items():
+        recs = _dump_tn2d(tn, name, store)
+        exact = complex(tn.contract(all, optimize="auto-hq"))
+        runs = []
+        for kw in [dict(max_bond=4, cutoff=0.0), dict(max_bond=8, cutoff=0.0),
+                   dict(max_bond=16, cutoff=0.0), dict(max_bond=8),
+                   dict(max_bond=6, cutoff=0.0, sequence=["xmin"]),
+                   dict(max_bond=6, cutoff=0.0, sequence=["ymin", "ymax"]),
+                   dict(max_bond=5, cutoff=1e-3, sequence=["xmax"]),
+                   dict(max_bond=6, cutoff=0.0, canonize=False)]:
+            v = complex(tn.contract_boundary(layer_tags=layers, **kw))
+            runs.append({"kw": kw, "value": [v.real, v.imag]})
+        meta[name] = {"Lx": tn.Lx, "Ly": tn.Ly, "layers": layers, "tensors": recs,
+                      "exact": [exact.real, exact.imag], "runs": runs,
+                      "dtype": str(tn.dtype)}
+    # PEPS site-array convention (for peps_norm_tensors): arrays in site order
+    for i in range(4):
+        for j in range(4):
+            t = p[i, j]
+            store[f"peps44_site__{i}_{j}"] = np.asarray(t.data)
+    meta["peps44_site_inds"] = {f"{i},{j}": list(map(str, p[i, j].inds))
+                                for i in range(4) for j in range(4)}
+    meta["peps44_bonds"] = {
+        f"{i},{j}": {"up": (str(list(qtn.bonds(p[i, j], p[i + 1, j]))[0]) if i < 3 else None),
+                     "right": (str(list(qtn.bonds(p[i, j], p[i, j + 1]))[0]) if j < 3 else None)}
+        for i in range(4) for j in range(4)}
+    np.savez_compressed(os.path.join(OUT, "boundary.npz"), **store)
+    json.dump(meta, open(os.path.join(OUT, "boundary.json"), "w"), indent=1)
+
+
 def mps_dmrg_cases():
     store, meta = {}, {}
     # Heisenberg MPO of the reference, as arrays (lrud layout) + dense check
@@ -377,7 +433,8 @@ def mps_dmrg_cases():
 
 if __name__ == "__main__":
     only = set(sys.argv[1:])
-    for fn in (contract_cases, decomp_cases, decomp2_cases, mps_dmrg_cases):
+    for fn in (contract_cases, decomp_cases, decomp2_cases, boundary_cases,
+               mps_dmrg_cases):
         if not only or fn.__name__ in only:
             fn()
     print("golden fixtures written to", OUT)

@@ -111,6 +111,8 @@ def qr(x, stabilized=False, want_q=True, want_r=True):
         return Q, R
     lib = _lib.load()
     dev = x.t.device
+    if m > _QR_MAX_ROWS and m >= n:
+        return _tsqr(x, stabilized, want_q, want_r)
     if m < n:
         # QR of the leading m x m block, R2 = Q^T X[:, m:]
         q, r1 = qr(Array(x.t[:, :m]), stabilized=stabilized)
@@ -130,6 +132,38 @@ def qr(x, stabilized=False, want_q=True, want_r=True):
                         _lib.stream_ptr())
     _lib.check(rc, "qb_qr_stab")
     return (Array(Q) if want_q else None), (Array(R) if want_r else None)
+
+
+# the Householder panel kernel keeps one panel row per thread in registers
+# (csrc/linalg.cu: qr_geometry); taller matrices are factored by blocks
+_QR_MAX_ROWS = 16384
+
+
+def _tsqr(x, stabilized, want_q, want_r):
+    """Tall-skinny QR for m > 16384 rows (e.g. the (chi d D^2) x (chi D)
+    boundary tensors of BASELINE config 5): row blocks are factored
+    independently, the stacked R factors are factored again (recursively), and
+    Q is assembled with one tensor-core GEMM per block."""
+    m, n = x.shape
+    nblk = -(-m // _QR_MAX_ROWS)
+    rows = -(-m // nblk)
+    if rows < n or nblk * n >= m:
+        raise ValueError(f"quimb_b200.linalg.qr: shape {x.shape} is not supported "
+                         f"(more than {_QR_MAX_ROWS} rows and {n} columns)")
+    qs, rs = [], []
+    for lo in range(0, m, rows):
+        q, r = qr(Array(x.t[lo:lo + rows]), stabilized=False, want_q=want_q)
+        qs.append(q)
+        rs.append(r.t)
+    stacked = Array(torch.cat(rs, dim=0))                  # (nblk * n, n)
+    q2, r = qr(stacked, stabilized=stabilized, want_q=want_q, want_r=want_r)
+    if not want_q:
+        return None, r
+    Q = torch.empty((m, n), dtype=x.t.dtype, device=x.t.device)
+    for b, (lo, q) in enumerate(zip(range(0, m, rows), qs)):
+        blk = ops.tensordot(q, Array(q2.t[b * n:(b + 1) * n]), axes=((1,), (0,)))
+        Q[lo:lo + q.shape[0]] = blk.t
+    return Array(Q), r
 
 
 def _select_complex_pairs(s_host, gram_fn):
@@ -189,6 +223,12 @@ def svd(x, full_matrices=False, return_sweeps=False):
         out = svd(xt, return_sweeps=return_sweeps)
         u, s, vh = out[:3]
         res = (Array(vh.t.t()), s, Array(u.t.t()))
+        return res + (out[3],) if return_sweeps else res
+    if m > _QR_MAX_ROWS:
+        # X = Q R (blocked QR), R = Ur s VH (Jacobi), U = Q Ur (one GEMM)
+        q, r = qr(x)
+        out = svd(r, return_sweeps=return_sweeps)
+        res = (ops.tensordot(q, out[0], axes=((1,), (0,))), out[1], out[2])
         return res + (out[3],) if return_sweeps else res
     lib = _lib.load()
     dev = x.t.device

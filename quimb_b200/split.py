@@ -610,11 +610,16 @@ def tensor_canonize_bond(a, a_inds, b, b_inds, absorb="right"):
 
 
 def tensor_compress_bond(a, a_inds, b, b_inds, max_bond=None, cutoff=1e-10,
-                         cutoff_mode="rel", absorb="both", renorm=None, info=None):
-    """Array-level ``tensor_compress_bond`` (tensor_core.py:864-1094, the
-    default ``reduced=True`` pipeline): QR(a), LQ(b), truncated SVD of the
-    reduced core, factors folded back with two contractions.  Outputs keep the
-    index order of the inputs."""
+                         cutoff_mode="rel", absorb="both", renorm=None, info=None,
+                         reduced=True, method="svd"):
+    """Array-level ``tensor_compress_bond`` (tensor_core.py:864-1094).
+
+    ``reduced=True`` (default): QR(a), LQ(b), truncated SVD of the reduced
+    core, factors folded back with two contractions.  ``reduced='left'`` /
+    ``'right'``: the neighbour is already isometric, split only ``a`` (or
+    ``b``) and absorb the remainder into the other tensor (what
+    ``compress_plane`` uses, tn2d/core.py:1098).  ``reduced=False``: contract
+    the pair and split it.  Outputs keep the index order of the inputs."""
     from .contract import contract_pair
     a, b = ops.asarray(a), ops.asarray(b)
     a_inds, b_inds = tuple(a_inds), tuple(b_inds)
@@ -625,17 +630,47 @@ def tensor_compress_bond(a, a_inds, b, b_inds, max_bond=None, cutoff=1e-10,
     bond = shared[0]
     lix = tuple(ix for ix in a_inds if ix != bond)
     rix = tuple(ix for ix in b_inds if ix != bond)
-    qa, ra = tensor_split(a, a_inds, lix, (bond,), method="qr")      # (*lix,k1), (k1,bond)
-    lb_, qb = tensor_split(b, b_inds, (bond,), rix, method="lq")     # (bond,k2), (k2,*rix)
-    core = ops.tensordot(ra, lb_, axes=((1,), (0,)))                 # (k1, k2)
-    _, opts = parse_split_opts("svd", absorb, max_bond, cutoff, cutoff_mode, renorm)
-    cl, _, cr = svd_truncated(core, info=info, **opts)               # (k1,k), (k,k2)
     lab = {ix: i for i, ix in enumerate(dict.fromkeys(a_inds + b_inds))}
     K1, K2, KB = len(lab), len(lab) + 1, lab[bond]
-    la = [lab[ix] for ix in lix] + [K1]
-    new_a = Array(contract_pair(qa.t, la, cl.t, [K1, KB], [lab[ix] for ix in a_inds],
-                                conj_a=qa.cj, conj_b=cl.cj))
-    lq = [K2] + [lab[ix] for ix in rix]
-    new_b = Array(contract_pair(cr.t, [KB, K2], qb.t, lq, [lab[ix] for ix in b_inds],
-                                conj_a=cr.cj, conj_b=qb.cj))
-    return new_a, new_b
+    kw = dict(method=method, absorb=absorb, max_bond=max_bond, cutoff=cutoff,
+              cutoff_mode=cutoff_mode, renorm=renorm, info=info)
+    if reduced is True:
+        qa, ra = tensor_split(a, a_inds, lix, (bond,), method="qr")    # (*lix,k1), (k1,bond)
+        lb_, qb = tensor_split(b, b_inds, (bond,), rix, method="lq")   # (bond,k2), (k2,*rix)
+        core = ops.tensordot(ra, lb_, axes=((1,), (0,)))               # (k1, k2)
+        parts = tensor_split(core, (K1, K2), (K1,), (K2,), **kw)       # (k1,k), (k,k2)
+        cl, cr = parts[0], parts[-1]
+        if len(parts) == 3 and info is not None:
+            info["singular_values"] = parts[1]
+        la = [lab[ix] for ix in lix] + [K1]
+        new_a = Array(contract_pair(qa.t, la, cl.t, [K1, KB], [lab[ix] for ix in a_inds],
+                                    conj_a=qa.cj, conj_b=cl.cj))
+        lq = [K2] + [lab[ix] for ix in rix]
+        new_b = Array(contract_pair(cr.t, [KB, K2], qb.t, lq, [lab[ix] for ix in b_inds],
+                                    conj_a=cr.cj, conj_b=qb.cj))
+        return new_a, new_b
+    if reduced == "left":
+        # right neighbour isometric: split a only, push the remainder into b
+        na, tc = tensor_split(a, a_inds, lix, (bond,), **kw)           # (*lix,k), (k,bond)
+        new_a = na.transpose(*_out_perm(lix + (bond,), a_inds))
+        out = [K1 if ix == bond else lab[ix] for ix in b_inds]
+        new_b = Array(contract_pair(tc.t, [K1, KB], b.t, [lab[ix] for ix in b_inds], out,
+                                    conj_a=tc.cj, conj_b=b.cj))
+        return new_a, new_b
+    if reduced == "right":
+        tc, nb = tensor_split(b, b_inds, (bond,), rix, **kw)           # (bond,k), (k,*rix)
+        new_b = nb.transpose(*_out_perm((bond,) + rix, b_inds))
+        out = [K1 if ix == bond else lab[ix] for ix in a_inds]
+        new_a = Array(contract_pair(a.t, [lab[ix] for ix in a_inds], tc.t, [KB, K1], out,
+                                    conj_a=a.cj, conj_b=tc.cj))
+        return new_a, new_b
+    if reduced is False:
+        full_inds = lix + rix
+        full = Array(contract_pair(a.t, [lab[ix] for ix in a_inds], b.t,
+                                   [lab[ix] for ix in b_inds],
+                                   [lab[ix] for ix in full_inds], conj_a=a.cj, conj_b=b.cj))
+        na, nb = tensor_split(full, full_inds, lix, rix, **kw)
+        return (na.transpose(*_out_perm(lix + (bond,), a_inds)),
+                nb.transpose(*_out_perm((bond,) + rix, b_inds)))
+    raise ValueError(f"Unrecognized value for `reduced` argument: {reduced}."
+                     "Valid options are {True, False, 'left', 'right'}.")

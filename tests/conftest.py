@@ -54,3 +54,8 @@ def golden_mps():
 @pytest.fixture(scope="session")
 def golden_decomp2():
     return load_golden("decomp2")
+
+
+@pytest.fixture(scope="session")
+def golden_boundary():
+    return load_golden("boundary")
