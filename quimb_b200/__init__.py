@@ -31,7 +31,8 @@ from .split import (array_split, array_svals, eigh_truncated,  # noqa: F401
                     tensor_compress_bond, tensor_split)
 from .lanczos import eigh_lanczos  # noqa: F401
 from . import boundary  # noqa: F401
-from .boundary import BoundaryContractor2D, contract_boundary, peps_norm_tensors  # noqa: F401
+from .boundary import (BoundaryContractor2D, contract_boundary,  # noqa: F401
+                       contract_boundary_two_sided, peps_norm_tensors)
 from .dmrg import DMRG2  # noqa: F401
 from .integration import register_with_quimb  # noqa: F401
 

@@ -341,3 +341,99 @@ def peps_norm_tensors(arrays, site_inds=None):
             out.append((x, kin, (i, j), "KET"))
             out.append((x.conj(), bin_, (i, j), "BRA"))
     return out, Lx, Ly
+
+
+# ------------------------------------------------------------ two-sided ------
+def _bcast_line(line, src, group, stage):
+    """Broadcast the labelled tensors of one boundary line from rank ``src``
+    (``line`` is ignored on the other ranks): one object broadcast of the
+    metadata, one tensor broadcast per boundary tensor (NVLink under NCCL;
+    staged through the host for gloo).  Complex data travels as real pairs."""
+    import torch
+    import torch.distributed as dist
+    from .ops import default_device
+    me = dist.get_rank(group)
+    meta = [None]
+    if me == src:
+        meta[0] = [(coo, t.inds, t.layer, tuple(t.data.shape), str(t.data.dtype))
+                   for coo, ts in line for t in ts]
+    dist.broadcast_object_list(meta, src=src, group=group)
+    out = {}
+    flat = [t for _, ts in line for t in ts] if me == src else None
+    for k, (coo, inds, layer, shape, dtype) in enumerate(meta[0]):
+        if me == src:
+            buf = ops.materialize(flat[k].data, force=True).t
+        else:
+            from .array import torch_dtype
+            buf = torch.empty(shape, dtype=torch_dtype(dtype), device=default_device())
+        wire = torch.view_as_real(buf) if buf.dtype.is_complex else buf
+        if stage and wire.device.type != "cpu":
+            host = wire.cpu()
+            dist.broadcast(host, src=src, group=group)
+            wire.copy_(host)
+        else:
+            dist.broadcast(wire, src=src, group=group)
+        out.setdefault(tuple(coo), []).append(LTensor(Array(buf), inds, layer))
+    return out
+
+
+def contract_boundary_two_sided(tensors, Lx, Ly, max_bond=None, cutoff=1e-10,
+                                canonize=True, layer_tags=None, compress_opts=None,
+                                optimize="auto", group=None, **step_opts):
+    """The default interleaved sequence ('xmin', 'xmax') -- or ('ymin', 'ymax')
+    for Lx < Ly -- of ``contract_boundary`` with the two opposing half-sweeps
+    on different GPUs (they are independent,
+    tn2d/core.py:2528-2543): rank 0 contracts inwards from the min side, rank 1
+    from the max side, the two boundary lines are exchanged (one broadcast
+    each, the only communication) and every rank performs the final exact
+    contraction of the two lines.  Bit-for-bit the same sequence of operations
+    as the single-process run, so the value is identical; ranks >= 2 only
+    receive.  Without a process group it runs both halves locally."""
+    import torch.distributed as dist
+    active = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    rank = dist.get_rank(group) if active else 0
+    plane = "x" if Lx >= Ly else "y"
+    L = Lx if plane == "x" else Ly
+    n_steps = max(L - 2, 0)
+    n_min, n_max = (n_steps + 1) // 2, n_steps // 2
+    tensors = list(tensors)
+    bc = BoundaryContractor2D(tensors, Lx, Ly)
+    other = (0, (Ly if plane == "x" else Lx) - 1)
+
+    def run(side, count):
+        for s in range(count):
+            lo = s if side == "min" else L - 2 - s
+            rng_i = (lo, lo + 1)
+            xr, yr = (rng_i, other) if plane == "x" else (other, rng_i)
+            bc.contract_boundary_from(xr, yr, plane + side, max_bond, cutoff=cutoff,
+                                      canonize=canonize, layer_tags=layer_tags,
+                                      compress_opts=compress_opts, **step_opts)
+
+    def line(i):
+        js = range(other[0], other[1] + 1)
+        coos = [(i, j) if plane == "x" else (j, i) for j in js]
+        return [(c, bc.sites[c]) for c in coos]
+
+    i_min, i_max = n_min, L - 1 - n_max
+    if not active:
+        run("min", n_min)
+        run("max", n_max)
+    else:
+        if rank == 0:
+            run("min", n_min)
+        elif rank == 1:
+            run("max", n_max)
+        stage = dist.get_backend(group) != "nccl"
+        got_min = _bcast_line(line(i_min) if rank == 0 else None, 0, group, stage)
+        got_max = _bcast_line(line(i_max) if rank == 1 else None, 1, group, stage)
+        if rank != 0:
+            for c, ts in got_min.items():
+                bc.sites[c] = ts
+        if rank != 1:
+            for c, ts in got_max.items():
+                bc.sites[c] = ts
+    keep = {c for c, _ in line(i_min)} | {c for c, _ in line(i_max)}
+    rest = list(itertools.chain.from_iterable(bc.sites[c] for c in sorted(keep)))
+    data, inds = tensor_contract([t.data for t in rest], [t.inds for t in rest],
+                                 optimize=optimize)
+    return data if inds else (data.item() if isinstance(data, Array) else data)

@@ -109,3 +109,46 @@ def test_bond_shard_gloo_world2():
         p.join(timeout=120)
         assert p.exitcode == 0
     assert ret[0] and ret[1]
+
+
+def _boundary_worker(rank, world, port, ret):
+    """Two-sided boundary contraction on gloo: rank 0 sweeps in from xmin,
+    rank 1 from xmax, one broadcast of each boundary line, every rank does the
+    final contraction.  The host layer runs against the ABI emulator (test
+    infrastructure); the exchange layer is the real one."""
+    import json
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from tests.abi_emulator import emulated_abi
+    from quimb_b200 import boundary as bd
+    data = np.load(os.path.join(ROOT, "tests", "golden", "boundary.npz"))
+    meta = json.load(open(os.path.join(ROOT, "tests", "golden", "boundary.json")))
+    ok = True
+    with emulated_abi():
+        for name in ("peps44", "flat55", "peps35"):
+            m = meta[name]
+            ts = [(data[f"{name}__t{k}"], r["inds"], tuple(r["site"]), r["layer"])
+                  for k, r in enumerate(m["tensors"])]
+            for run in (m["runs"][1], m["runs"][3]):
+                v = bd.contract_boundary_two_sided(ts, m["Lx"], m["Ly"],
+                                                   layer_tags=m["layers"], **run["kw"])
+                ref = complex(*run["value"])
+                ok = ok and abs(v - ref) <= 1e-10 * abs(ref)
+    ret[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+def test_two_sided_boundary_contraction_gloo_world2():
+    mp.set_start_method("spawn", force=True)
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = 33500 + (os.getpid() % 2000)
+    procs = [mp.Process(target=_boundary_worker, args=(r, 2, port, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=240)
+        assert p.exitcode == 0
+    assert ret[0] and ret[1]
