@@ -388,6 +388,68 @@ def boundary_cases():
     json.dump(meta, open(os.path.join(OUT, "boundary.json"), "w"), indent=1)
 
 
+def tebd_cases():
+    """gate_split / gate_with_auto_swap / TEBD of the reference (numpy)."""
+    store, meta = {}, {}
+    rng = np.random.default_rng(21)
+    # --- gate_split on a random MPS --------------------------------------
+    p = qtn.MPS_rand_state(6, 5, seed=8, dtype="complex128")
+    for i in range(6):
+        store[f"gs_mps__{i}"] = np.asarray(p[i].data)
+    meta["gs_mps_inds"] = [list(map(str, p[i].inds)) for i in range(6)]
+    G = rng.standard_normal((4, 4)) + 1j * rng.standard_normal((4, 4))
+    store["gs_gate"] = G
+    gs = []
+    for kw in [dict(where=(2, 3)), dict(where=(2, 3), max_bond=3, cutoff=0.0, absorb="right"),
+               dict(where=(3, 2), absorb="left"), dict(where=(0, 1), cutoff=1e-2, cutoff_mode="rel"),
+               dict(where=(4, 5), max_bond=2)]:
+        q = p.copy()
+        q.canonicalize_(kw["where"])
+        q.gate_split_(G, **kw)
+        key = f"gs__{len(gs)}"
+        store[key + "__dense"] = np.asarray(q.to_dense()).reshape(-1)
+        gs.append({"key": key, "kw": {k: (list(v) if k == "where" else v) for k, v in kw.items()},
+                   "bond": int(q.bond_size(*sorted(kw["where"])))})
+    meta["gate_split"] = gs
+    sw = []
+    for where in [(1, 4), (4, 1), (0, 5), (2, 3)]:
+        q = p.copy()
+        q.gate_with_auto_swap_(G, where, cutoff=1e-12)
+        key = f"swap__{len(sw)}"
+        store[key + "__dense"] = np.asarray(q.to_dense()).reshape(-1)
+        sw.append({"key": key, "where": list(where)})
+    meta["auto_swap"] = sw
+    # --- TEBD -------------------------------------------------------------
+    runs = []
+    for L, order, dt, T, imag, bz in [(8, 4, 0.05, 0.4, False, 0.0), (7, 2, 0.02, 0.1, False, 0.3),
+                                      (8, 2, 0.1, 1.0, True, 0.0), (6, 4, None, 0.3, False, 0.0)]:
+        H = qtn.ham_1d_heis(L, bz=bz, cyclic=False)
+        p0 = qtn.MPS_neel_state(L)
+        kw = dict(dt=dt) if dt is not None else dict(tol=1e-3)
+        tebd = qtn.TEBD(p0, H, progbar=False, imag=imag,
+                        split_opts=dict(cutoff=1e-12), **kw)
+        tebd.update_to(T, order=order)
+        pt = tebd.pt
+        key = f"tebd__{len(runs)}"
+        store[key + "__dense"] = np.asarray(pt.to_dense()).reshape(-1)
+        terms = {f"{a},{b}": np.asarray(h) for (a, b), h in H.terms.items()}
+        for k2, h in terms.items():
+            store[f"{key}__term__{k2}"] = h
+        runs.append({"key": key, "L": L, "order": order, "dt": dt, "T": T, "imag": imag,
+                     "bz": bz, "tol": None if dt is not None else 1e-3,
+                     "terms": sorted(terms), "err": float(tebd.err), "t": float(tebd.t),
+                     "max_bond": int(pt.max_bond()),
+                     "energy": float(np.real(qtn.expec_TN_1D(pt.H, qtn.MPO_ham_heis(L, bz=bz), pt)
+                                             / (pt.H @ pt)))})
+    meta["tebd"] = runs
+    store["heis_h2"] = np.asarray(qu.ham_heis(2, cyclic=False))
+    meta["trotter"] = {str(o): [[int(k), float(f)] for k, f in
+                                __import__("quimb.tensor.tnag.tebd", fromlist=["x"]).trotter_schedule(2, o)]
+                       for o in (1, 2, 4)}
+    np.savez_compressed(os.path.join(OUT, "tebd.npz"), **store)
+    json.dump(meta, open(os.path.join(OUT, "tebd.json"), "w"), indent=1)
+
+
 def mps_dmrg_cases():
     store, meta = {}, {}
     # Heisenberg MPO of the reference, as arrays (lrud layout) + dense check
@@ -433,7 +495,7 @@ def mps_dmrg_cases():
 
 if __name__ == "__main__":
     only = set(sys.argv[1:])
-    for fn in (contract_cases, decomp_cases, decomp2_cases, boundary_cases,
+    for fn in (contract_cases, decomp_cases, decomp2_cases, boundary_cases, tebd_cases,
                mps_dmrg_cases):
         if not only or fn.__name__ in only:
             fn()

@@ -59,3 +59,8 @@ def golden_decomp2():
 @pytest.fixture(scope="session")
 def golden_boundary():
     return load_golden("boundary")
+
+
+@pytest.fixture(scope="session")
+def golden_tebd():
+    return load_golden("tebd")

@@ -29,6 +29,7 @@ _SKIP = {
     "test_gpu_split": set(),
     "test_gpu_split2": set(),
     "test_gpu_boundary": set(),
+    "test_gpu_tebd": set(),
 }
 
 

@@ -266,3 +266,59 @@ def test_svals_drivers_match_reference(golden_decomp2):
                                    data[f"svals__{mname}__svd"], rtol=1e-12)
         np.testing.assert_allclose(dn.svd_via_eig(x, absorb=dn.get_s)[1],
                                    data[f"svals__{mname}__eig"], rtol=1e-9)
+
+
+def _golden_tebd():
+    import json
+    import os
+    root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    return np.load(os.path.join(root, "tebd.npz")), json.load(open(os.path.join(root, "tebd.json")))
+
+
+def _lpr(a, i, n):
+    """quimb 'lrp' site array -> (l, p, r)."""
+    if a.ndim == 2:
+        a = a[None] if i == 0 else a[:, None]
+    return np.transpose(a, (0, 2, 1))
+
+
+def test_gate_split_and_swaps_oracle_match_reference():
+    from oracle import tebd_np as tn
+    data, meta = _golden_tebd()
+    raw = [data[f"gs_mps__{i}"] for i in range(6)]
+    G = data["gs_gate"]
+    for c in meta["gate_split"]:
+        kw = dict(c["kw"])
+        where = tuple(kw.pop("where"))
+        s = [_lpr(a, i, 6) for i, a in enumerate(raw)]
+        tn.canonicalize(s, where)
+        tn.gate_split(s, G, where, **kw)
+        assert s[min(where)].shape[2] == c["bond"]
+        np.testing.assert_allclose(dm.mps_to_dense(s).reshape(-1), data[c["key"] + "__dense"],
+                                   atol=1e-12)
+    for c in meta["auto_swap"]:
+        s = [_lpr(a, i, 6) for i, a in enumerate(raw)]
+        tn.gate_with_auto_swap(s, G, tuple(c["where"]), cutoff=1e-12)
+        np.testing.assert_allclose(dm.mps_to_dense(s).reshape(-1), data[c["key"] + "__dense"],
+                                   atol=1e-11)
+
+
+def test_tebd_oracle_matches_reference():
+    from oracle import tebd_np as tn
+    data, meta = _golden_tebd()
+    for o, sched in meta["trotter"].items():
+        assert [[k, f] for k, f in tn.trotter_schedule(2, int(o))] == sched
+    for r in meta["tebd"]:
+        L = r["L"]
+        terms = {tuple(map(int, k.split(","))): data[f"{r['key']}__term__{k}"]
+                 for k in r["terms"]}
+        p0 = [np.zeros((1, 2, 1)) for _ in range(L)]
+        for i in range(L):
+            p0[i][0, i % 2, 0] = 1.0
+        kw = dict(dt=r["dt"]) if r["dt"] is not None else dict(tol=r["tol"])
+        t = tn.TEBD(p0, terms, imag=r["imag"], split_opts=dict(cutoff=1e-12), **kw)
+        t.update_to(r["T"], order=r["order"])
+        assert abs(t.err - r["err"]) <= 1e-12 * max(1.0, r["err"])
+        assert max(a.shape[2] for a in t.sites) == r["max_bond"]
+        np.testing.assert_allclose(dm.mps_to_dense(t.sites).reshape(-1),
+                                   data[r["key"] + "__dense"], atol=1e-8)
