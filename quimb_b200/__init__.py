@@ -30,7 +30,8 @@ from .split import (array_split, array_svals, eigh_truncated,  # noqa: F401
                     svd_via_eig, svd_via_eig_truncated, tensor_canonize_bond,
                     tensor_compress_bond, tensor_split)
 from .lanczos import eigh_lanczos  # noqa: F401
-from . import boundary, tebd  # noqa: F401
+from . import boundary, linop, tebd  # noqa: F401
+from .linop import TNLinearOperator  # noqa: F401
 from .tebd import TEBD, LocalHam1D, gate_split, gate_with_auto_swap  # noqa: F401
 from .boundary import (BoundaryContractor2D, contract_boundary,  # noqa: F401
                        contract_boundary_two_sided, peps_norm_tensors)

@@ -58,6 +58,12 @@ def register_with_quimb():
             getattr(decomp, nm).register(name)(fn)
             done.append(nm)
 
+    for nm in ("fuse", "unfuse"):
+        fn = getattr(array_ops, nm, None)
+        if fn is not None and hasattr(fn, "register"):
+            fn.register(name)(getattr(ops, nm))
+            done.append(nm)
+
     def _norm_fro(x):
         from .linalg import norm
         return norm(x)

@@ -7,6 +7,7 @@ kernels behind the C ABI.  Cold element-wise helpers forward to torch on the
 wrapped tensor (torch is the container library here).
 """
 
+import builtins
 import ctypes
 import numbers
 
@@ -16,6 +17,9 @@ import torch
 from . import _lib
 from .array import Array, default_device, torch_dtype
 from .contract import contract_pair
+
+# this module shadows min / all / any with array versions further down
+builtins_min, builtins_all, builtins_any = builtins.min, builtins.all, builtins.any
 
 
 # ------------------------------------------------------------ conversion ---
@@ -93,6 +97,63 @@ def reshape(x, shape):
         return Array(x.t.view(shape), x.cj)  # free when strides allow it
     except RuntimeError:
         return Array(materialize(x).t.view(shape))
+
+
+def calc_fuse_perm_and_shape(shape, axes_groups):
+    """quimb/tensor/array_ops.py:95-145 (bit-exact index bookkeeping): the
+    fused axes are inserted at the minimum index of any fused axis, ungrouped
+    axes keep their order; ``perm`` / ``new_shape`` are None for no-ops."""
+    shape = tuple(shape)
+    ndim = len(shape)
+    num_groups = len(axes_groups)
+    ax2group = {ax: g for g, axes in enumerate(axes_groups) for ax in axes}
+    position = builtins_min(g for gax in axes_groups for g in gax)
+    axes_before = tuple(ax for ax in range(position)
+                        if ax2group.setdefault(ax, None) is None)
+    axes_after = tuple(ax for ax in range(position, ndim)
+                       if ax2group.setdefault(ax, None) is None)
+    perm = (*axes_before, *(ax for g in axes_groups for ax in g), *axes_after)
+    new_axes = {ax: ax for ax in axes_before}
+    for i, g in enumerate(axes_groups):
+        for ax in g:
+            new_axes[ax] = position + i
+    for i, ax in enumerate(axes_after):
+        new_axes[ax] = position + num_groups + i
+    new_shape = [1] * (len(axes_before) + num_groups + len(axes_after))
+    for i, d in enumerate(shape):
+        new_shape[new_axes[i]] *= d
+    if builtins_all(i == ax for i, ax in enumerate(perm)):
+        perm = None
+    new_shape = tuple(new_shape)
+    if shape == new_shape:
+        new_shape = None
+    return perm, new_shape
+
+
+def fuse(x, *axes_groups, backend=None):
+    """quimb's ``fuse`` (array_ops.py:148-180): transpose + reshape, i.e. at
+    most ONE permute-copy kernel (and none when the strides already allow the
+    view)."""
+    x = asarray(x)
+    axes_groups = tuple(map(tuple, axes_groups))
+    if not builtins_any(axes_groups):
+        return x
+    perm, new_shape = calc_fuse_perm_and_shape(x.shape, axes_groups)
+    if perm is not None:
+        x = x.transpose(*perm)
+    if new_shape is not None:
+        x = reshape(x, new_shape)
+    return x
+
+
+def unfuse(x, axis, axis_dims, backend=None):
+    """array_ops.py:183-217: split one axis back into ``axis_dims`` (a view)."""
+    axis_dims = tuple(axis_dims)
+    if len(axis_dims) == 1:
+        return x
+    x = asarray(x)
+    shape = x.shape
+    return reshape(x, (*shape[:axis], *axis_dims, *shape[axis + 1:]))
 
 
 def transpose(x, axes=None):

@@ -30,6 +30,7 @@ _SKIP = {
     "test_gpu_split2": set(),
     "test_gpu_boundary": set(),
     "test_gpu_tebd": set(),
+    "test_gpu_linop": set(),
 }
 
 

@@ -137,3 +137,28 @@ def test_no_cpu_fallback():
     a = torch.zeros(3, 3, dtype=torch.float64)
     with pytest.raises(_lib.QuimbB200Error):
         qb.contract_pair(a, [0, 1], a, [1, 2], [0, 2])
+
+
+def test_fuse_perm_and_shape_match_reference_rule():
+    """calc_fuse_perm_and_shape is pure index bookkeeping: bit-exact against
+    the oracle restatement and the documented example of array_ops.py:150-160."""
+    from quimb_b200 import ops
+    from oracle import decomp_np as dn
+    perm, shape = ops.calc_fuse_perm_and_shape((2, 3, 4, 5, 6, 7, 8, 9, 10), ((5, 3), (7, 2, 6)))
+    assert perm == (0, 1, 5, 3, 7, 2, 6, 4, 8)
+    assert shape == (2, 3, 7 * 5, 9 * 4 * 8, 6, 10)
+    assert ops.calc_fuse_perm_and_shape((2, 3, 4), ((0,), (1,), (2,))) == (None, None)
+    assert ops.calc_fuse_perm_and_shape((2, 3, 4), ((0, 1),)) == (None, (6, 4))
+    rng = np.random.default_rng(0)
+    for _ in range(50):
+        nd = int(rng.integers(2, 7))
+        shape = tuple(int(v) for v in rng.integers(1, 5, size=nd))
+        axes = list(rng.permutation(nd))
+        k = int(rng.integers(1, nd + 1))
+        cut = int(rng.integers(0, k + 1))
+        groups = tuple(g for g in (tuple(int(a) for a in axes[:cut]),
+                                   tuple(int(a) for a in axes[cut:k])) if g)
+        perm, new_shape = ops.calc_fuse_perm_and_shape(shape, groups)
+        operm, oshape = dn.calc_fuse_perm_and_shape(shape, groups)
+        assert (tuple(range(nd)) if perm is None else perm) == operm
+        assert (shape if new_shape is None else new_shape) == oshape
