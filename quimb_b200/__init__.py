@@ -23,8 +23,9 @@ from .contract import contract_batched, contract_pair, plan_pair  # noqa: F401
 from . import dist  # noqa: F401
 from .tree import (ContractExpression, GraphedContraction, Tree,  # noqa: F401
                    array_contract, find_tree, gen_output_inds, tensor_contract)
-from .mps import (env_left_step, env_right_step, mps_expec, mps_norm,  # noqa: F401
-                  mps_norm2)
+from .mps import (MovingEnvironment, compute_left_environments,  # noqa: F401
+                  compute_right_environments, env_left_step, env_right_step,
+                  mps_expec, mps_norm, mps_norm2)
 from .split import (array_split, array_svals, eigh_truncated,  # noqa: F401
                     qr_stabilized, svd_rand_truncated, svd_truncated,
                     svd_via_eig, svd_via_eig_truncated, tensor_canonize_bond,

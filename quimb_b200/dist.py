@@ -169,3 +169,74 @@ class BondShard:
             lo, hi = self.slab(n, r)
             full[lo:hi].copy_(part[: hi - lo])
         return full
+
+
+def mps_norm2_two_ended(sites, shape="lrp", group=None):
+    """<psi|psi> with the chain contracted from both ends at once (SURVEY.md
+    8e, cfg2): rank 0 carries the (chi, chi) environment in from the left over
+    the first half of the sites, rank 1 from the right over the second half;
+    ONE broadcast of the 8 MiB right environment (chi = 1024) and one
+    (chi x chi) . (chi x chi) trace join them.  Each rank needs only its half
+    of the site tensors resident (pass ``None`` for the others).  Beyond two
+    ranks the chain does not shard this way (replicas only); without a process
+    group both halves run locally.  Returns a 0-d device Array (identical on
+    all ranks)."""
+    from . import ops
+    from .array import Array
+    from .contract import contract_pair
+    from .mps import norm_step, norm_step_right, site_lpr
+    n = len(sites)
+    if n < 2:
+        from .mps import mps_norm2
+        return mps_norm2(sites, shape)
+    half = n // 2
+    active = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    rank = dist.get_rank(group) if active else 0
+
+    def left():
+        E = None
+        for i in range(half):
+            A = site_lpr(sites[i], shape, i, n)
+            if E is None:
+                E = ops.eye(A.shape[0], dtype=A.dtype, device=A.device)
+            E = norm_step(E, A)
+        return E
+
+    def right():
+        E = None
+        for i in range(n - 1, half - 1, -1):
+            A = site_lpr(sites[i], shape, i, n)
+            if E is None:
+                E = ops.eye(A.shape[2], dtype=A.dtype, device=A.device)
+            E = norm_step_right(E, A)
+        return E
+
+    if not active:
+        EL, ER = left(), right()
+    else:
+        EL = left() if rank == 0 else None
+        ER = right() if rank == 1 else None
+        stage = dist.get_backend(group) != "nccl"
+        out = []
+        for src, E in ((0, EL), (1, ER)):
+            meta = [None]
+            if rank == src:
+                meta[0] = (tuple(E.shape), str(E.t.dtype))
+            dist.broadcast_object_list(meta, src=src, group=group)
+            shp, dt = meta[0]
+            if rank == src:
+                buf = ops.materialize(E, force=True).t
+            else:
+                buf = torch.empty(shp, dtype=getattr(torch, dt.split(".")[-1]),
+                                  device=ops.default_device())
+            wire = torch.view_as_real(buf) if buf.dtype.is_complex else buf
+            if stage and wire.device.type != "cpu":
+                host = wire.cpu()
+                dist.broadcast(host, src=src, group=group)
+                wire.copy_(host)
+            else:
+                dist.broadcast(wire, src=src, group=group)
+            out.append(Array(buf))
+        EL, ER = out
+    # <psi|psi> = sum_{a', a} EL[a', a] ER[a', a]
+    return Array(contract_pair(EL.t, [0, 1], ER.t, [0, 1], [], conj_a=EL.cj, conj_b=ER.cj))

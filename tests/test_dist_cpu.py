@@ -152,3 +152,38 @@ def test_two_sided_boundary_contraction_gloo_world2():
         p.join(timeout=240)
         assert p.exitcode == 0
     assert ret[0] and ret[1]
+
+
+def _two_ended_worker(rank, world, port, ret):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from tests.abi_emulator import emulated_abi
+    from quimb_b200 import dist as qd
+    from oracle import dmrg_np as dm
+    ok = True
+    with emulated_abi():
+        for L, chi, dtype in ((9, 6, "float64"), (12, 5, "complex128"), (2, 3, "float64")):
+            sites = dm.mps_rand(L, chi, seed=L, dtype=dtype)
+            # each rank only holds its half
+            mine = [s if ((i < L // 2) == (rank == 0)) else None for i, s in enumerate(sites)]
+            v = qd.mps_norm2_two_ended(mine, shape="lpr").item()
+            ref = dm.mps_norm2(sites)
+            ok = ok and abs(v - ref) <= 1e-11 * abs(ref)
+    ret[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+def test_two_ended_mps_norm_gloo_world2():
+    mp.set_start_method("spawn", force=True)
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = 35500 + (os.getpid() % 2000)
+    procs = [mp.Process(target=_two_ended_worker, args=(r, 2, port, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=240)
+        assert p.exitcode == 0
+    assert ret[0] and ret[1]

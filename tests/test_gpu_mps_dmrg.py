@@ -170,3 +170,48 @@ def test_bond_sharded_eigensolve_two_ranks_one_gpu(dtype):
            "--same-gpu", "--dtype", dtype]
     pr = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=root)
     assert "DIST_DMRG_OK" in pr.stdout, pr.stdout[-2000:] + pr.stderr[-2000:]
+
+
+def test_environments_and_moving_environment_vs_oracle():
+    L, chi = 9, 6
+    sites = dm.mps_rand(L, chi, seed=11)
+    mpo = dm.mpo_heis(L)
+    dev = [qb.asarray(s) for s in sites]
+    H = [qb.asarray(w) for w in mpo]
+    # norm environments: <psi|psi> from any cut
+    le = qb.compute_left_environments(dev, shape="lpr")
+    re = qb.compute_right_environments(dev, shape="lpr")
+    assert sorted(le) == list(range(1, L)) and sorted(re) == list(range(0, L - 1))
+    n2 = dm.mps_norm2(sites)
+    for i in range(1, L - 1):
+        # <psi|psi> = sum L_i[a', a] conj(A_i)[a', p, b'] A_i[a, p, b] R_i[b', b]
+        A = sites[i]
+        val = np.einsum("xa,xpy,apb,yb->", le[i].to_numpy(), A.conj(), A, re[i].to_numpy(),
+                        optimize=True)
+        assert abs(val - n2) <= 1e-11 * abs(n2)
+    # energy environments against the oracle's step functions
+    leh = qb.compute_left_environments(dev, H, shape="lpr", mpo_shape="lrdu")
+    E = np.ones((1, 1, 1))
+    for i in range(L - 1):
+        E = dm.env_step_left(E, sites[i], mpo[i])
+        np.testing.assert_allclose(leh[i + 1].to_numpy(), E, rtol=1e-11, atol=1e-12)
+    reh = qb.compute_right_environments(dev, H, shape="lpr", mpo_shape="lrdu")
+    E = np.ones((1, 1, 1))
+    for i in range(L - 1, 0, -1):
+        E = dm.env_step_right(E, sites[i], mpo[i])
+        np.testing.assert_allclose(reh[i - 1].to_numpy(), E, rtol=1e-11, atol=1e-12)
+    # moving window: every position reproduces <psi|H|psi>
+    from quimb_b200.mps import mpo_lrud
+    Hl = [mpo_lrud(w, "lrdu", i, L) for i, w in enumerate(H)]
+    expec = dm.mps_expec(sites, mpo)
+    for begin in ("left", "right"):
+        me = qb.MovingEnvironment(dev, Hl, begin=begin, bsz=2)
+        order = list(range(L - 1)) if begin == "left" else list(range(L - 2, -1, -1))
+        for i in order + order[::-1]:
+            me.move_to(i)
+            Le, Re = (t.to_numpy() for t in me())
+            A, B = sites[i], sites[i + 1]
+            # oracle MPO layout is (l, r, bra, ket)
+            val = np.einsum("xwa,apm,mqb,wvPp,vuQq,xPn,nQy,yub->", Le, A, B, mpo[i],
+                            mpo[i + 1], A.conj(), B.conj(), Re, optimize=True)
+            assert abs(val - expec) <= 1e-10 * abs(expec), (begin, i)
