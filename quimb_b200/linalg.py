@@ -288,11 +288,15 @@ def norm(x, ord=None):
     return ops.sqrt(ops.real(ops.vdot(flat, flat)))
 
 
-def eigh(x, host_below=64):
+# matrices up to this size are "tiny projected problems" solved on the host
+_EIGH_HOST_BELOW = 64
+
+
+def eigh(x, host_below=None):
     """Hermitian eigendecomposition ``x = v diag(w) v^H`` (``w`` ascending,
     as numpy / the reference's ``xp.linalg.eigh``).
 
-    Tiny problems (n <= ``host_below``: Lanczos tridiagonals, DMRG's dense-Heff
+    Tiny problems (n <= ``host_below``, default ``_EIGH_HOST_BELOW`` = 64: Lanczos tridiagonals, DMRG's dense-Heff
     branch for prod(dims) < 800, dmrg.py:690) are host-side control logic in
     the reference too and are solved on the host.  Anything larger runs on the
     device through the one-sided Jacobi kernel: with ``sigma = |x|_F`` the
@@ -306,6 +310,8 @@ def eigh(x, host_below=64):
     if x.ndim != 2 or x.shape[0] != x.shape[1]:
         raise ValueError(f"eigh: expected a square matrix, got shape {x.shape}")
     n = x.shape[0]
+    if host_below is None:
+        host_below = _EIGH_HOST_BELOW
     if n <= host_below:
         a = ops.to_numpy(x)
         w, v = np.linalg.eigh(a)

@@ -46,8 +46,9 @@ def _reexport():
         for name, obj in vars(mod).items():
             if name.startswith("test_") and callable(obj) and name not in skip:
                 globals()[f"test_emu__{modname[9:]}__{name[5:]}"] = obj
-            elif name.startswith("golden_") or name.startswith("_fixture"):
-                globals()[name] = obj
+            elif type(obj).__name__ == "FixtureFunctionDefinition" or hasattr(
+                    obj, "_pytestfixturefunction"):
+                globals()[name] = obj            # module-level fixtures travel along
 
 
 _reexport()

@@ -178,3 +178,133 @@ def test_array_split_dispatch_and_tensor_split_methods():
                 qb.asarray(x), "abcd", "ac", method=method, cutoff=0.0, absorb="left"))
         rec = np.einsum("ack,kbd->abcd", l, r)
         np.testing.assert_allclose(rec, x, atol=1e-9)
+
+
+# ---- the reference's own property tests for these drivers, restated --------
+# (tests/test_tensor/test_decomp.py:302-375, 378-437, 464-486, 748-790)
+@pytest.fixture(params=["host_eigh", "device_eigh"])
+def eigh_mode(request, monkeypatch):
+    """Small Gram matrices take the host branch of linalg.eigh (n <= 64, control
+    logic); 'device_eigh' forces the Jacobi path so it sees the same cases."""
+    if request.param == "device_eigh":
+        monkeypatch.setattr(qb.linalg, "_EIGH_HOST_BELOW", 0)
+    return request.param
+
+
+@pytest.mark.parametrize("da,db", [(5, 5), (5, 7), (7, 5)])
+@pytest.mark.parametrize("k", [-1, 6, 8])
+@pytest.mark.parametrize("descending", [True, False])
+def test_svd_via_eig_properties(da, db, k, descending, eigh_mode):
+    rng = np.random.default_rng(da * 100 + db * 10 + k + 2 + int(descending))
+    x = rng.uniform(size=(da, db))
+    x /= np.linalg.norm(x)
+    Ux, sx, VHx = np.linalg.svd(x, full_matrices=False)
+    kk = min(da, db, k) if k > 0 else min(da, db)
+    sx, Ux, VHx = sx[:kk], Ux[:, :kk], VHx[:kk]
+    if not descending:
+        sx, Ux, VHx = sx[::-1], Ux[:, ::-1], VHx[::-1]
+    for absorb in ["U", "s", "VH", "Us", "sVH", "U,s,VH", "U,sVH", "Us,VH"]:
+        U, s, VH = (_np(t) for t in split.svd_via_eig(
+            qb.asarray(x), max_bond=k, absorb=absorb, descending=descending))
+        if absorb in ("U", "U,s,VH", "U,sVH"):
+            assert U.shape == (da, kk)
+            np.testing.assert_allclose(U.T @ U, np.eye(kk), atol=1e-9)
+            np.testing.assert_allclose(np.abs(U.T @ Ux), np.eye(kk), atol=1e-8)
+        if absorb in ("s", "U,s,VH"):
+            assert s.shape == (kk,)
+            np.testing.assert_allclose(s, sx, atol=1e-9)
+            assert np.all(np.diff(s) <= 0) if descending else np.all(np.diff(s) >= 0)
+        if absorb in ("VH", "Us,VH", "U,s,VH"):
+            assert VH.shape == (kk, db)
+            np.testing.assert_allclose(VH @ VH.T, np.eye(kk), atol=1e-9)
+            np.testing.assert_allclose(np.abs(VHx @ VH.T), np.eye(kk), atol=1e-8)
+        if absorb in ("Us", "Us,VH"):
+            np.testing.assert_allclose(U.T @ U, np.diag(sx ** 2), atol=1e-9)
+        if absorb in ("sVH", "U,sVH"):
+            np.testing.assert_allclose(VH @ VH.T, np.diag(sx ** 2), atol=1e-9)
+        if absorb in ("Us,VH", "U,sVH", "U,s,VH"):
+            rec = (U * s) @ VH if absorb == "U,s,VH" else U @ VH
+            if k > min(da, db) or k < 0:
+                np.testing.assert_allclose(rec, x, atol=1e-9)
+            else:
+                assert np.linalg.norm(x - rec) < 0.2
+
+
+@pytest.mark.parametrize("da,db", [(4, 8), (8, 4), (6, 6)])
+@pytest.mark.parametrize("right", [True, False, None])
+def test_svd_rand_right_param(right, da, db):
+    rng = np.random.default_rng(da * 10 + db + (3 if right is None else int(right)))
+    x = rng.uniform(size=(da, db))
+    x /= np.linalg.norm(x)
+    U, s, VH = (_np(t) for t in split.svd_rand_truncated(
+        qb.asarray(x), absorb=None, max_bond=3, right=right, seed=17))
+    assert U.shape == (da, 3) and s.shape == (3,) and VH.shape == (3, db)
+    assert np.all(s >= 0)
+    np.testing.assert_allclose(U.T @ U, np.eye(3), atol=1e-9)
+    np.testing.assert_allclose(VH @ VH.T, np.eye(3), atol=1e-9)
+    assert np.linalg.norm(x - (U * s) @ VH) < 0.5
+
+
+@pytest.mark.parametrize("absorb", ["U", "s", "VH", "Us", "sVH", "U,s,VH", "U,sVH", "Us,VH"])
+@pytest.mark.parametrize("k", [-1, 4])
+def test_svd_rand_absorb_modes(absorb, k):
+    rng = np.random.default_rng(5 + k)
+    x = rng.uniform(size=(7, 5))
+    x /= np.linalg.norm(x)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        U, s, VH = (_np(t) for t in split.svd_rand_truncated(
+            qb.asarray(x), max_bond=k, absorb=absorb, seed=3))
+    kk = 5 if k < 0 else k
+    sx = np.linalg.svd(x, compute_uv=False)[:kk]
+    want = {"U": (1, 0, 0), "s": (0, 1, 0), "VH": (0, 0, 1), "Us": (1, 0, 0), "sVH": (0, 0, 1),
+            "U,s,VH": (1, 1, 1), "U,sVH": (1, 0, 1), "Us,VH": (1, 0, 1)}[absorb]
+    assert tuple(int(t is not None) for t in (U, s, VH)) == want
+    if absorb in ("s", "U,s,VH"):
+        np.testing.assert_allclose(s, sx, atol=1e-6 if k > 0 else 1e-9)
+    if absorb in ("U", "U,sVH", "U,s,VH"):
+        np.testing.assert_allclose(U.T @ U, np.eye(kk), atol=1e-9)
+    if absorb in ("VH", "Us,VH", "U,s,VH"):
+        np.testing.assert_allclose(VH @ VH.T, np.eye(kk), atol=1e-9)
+    if absorb in ("Us,VH", "U,sVH"):
+        assert np.linalg.norm(x - U @ VH) < (1e-9 if k < 0 else 0.3)
+
+
+def test_eigh_shift_semantics(eigh_mode):
+    """array_split(method='eigh', shift=...) (test_decomp.py:748-790): False /
+    default add nothing, a float adds shift * trace, True adds eps * trace."""
+    x = np.diag([4.0, 1.0, 0.0])
+    tr = 5.0
+
+    def vals(**kw):
+        return _np(qb.array_split(qb.asarray(x), method="eigh", absorb="s", cutoff=0.0,
+                                  positive=1, **kw)[1])
+    np.testing.assert_allclose(vals(), [4.0, 1.0, 0.0], atol=1e-12)
+    np.testing.assert_allclose(vals(shift=False), [4.0, 1.0, 0.0], atol=1e-12)
+    np.testing.assert_allclose(vals(shift=0.1), np.array([4.0, 1.0, 0.0]) + 0.1 * tr,
+                               atol=1e-12)
+    np.testing.assert_allclose(vals(shift=True),
+                               np.array([4.0, 1.0, 0.0]) + np.finfo(float).eps * tr, atol=1e-12)
+
+
+@pytest.mark.parametrize("method", ["svd", "svd:eig", "svd:rand", "qr", "lq"])
+@pytest.mark.parametrize("absorb", ["left", "right"])
+@pytest.mark.parametrize("m,n", [(8, 5), (5, 5), (5, 8)])
+def test_isometric_factor_across_methods(method, absorb, m, n, eigh_mode):
+    """Every method returns x = L @ R with the non-absorbing factor isometric
+    (test_decomp.py:517-553)."""
+    if eigh_mode == "device_eigh" and method != "svd:eig":
+        pytest.skip("eigh mode only matters for svd:eig")
+    rng = np.random.default_rng(m * 10 + n)
+    x = rng.standard_normal((m, n))
+    kw = dict(seed=1, max_bond=min(m, n)) if method == "svd:rand" else {}
+    if method in ("svd", "svd:eig"):
+        kw["cutoff"] = 0.0
+    L, _, R = (_np(t) for t in qb.array_split(qb.asarray(x), method=method, absorb=absorb, **kw))
+    np.testing.assert_allclose(L @ R, x, atol=1e-9)
+    k = min(m, n)
+    if absorb == "right":
+        np.testing.assert_allclose(L.T @ L, np.eye(k), atol=1e-8)
+    else:
+        np.testing.assert_allclose(R @ R.T, np.eye(k), atol=1e-8)
