@@ -53,12 +53,16 @@ def slice_assignments(sliced_inds, size_dict):
     return list(itertools.product(*ranges))
 
 
-def contract_sliced(arrays, inputs, output, sliced_inds, optimize="auto",
-                    contract_fn=None, rank=None, world_size=None, reduce=True):
+def contract_sliced(arrays, inputs, output, sliced_inds=None, optimize="auto",
+                    contract_fn=None, rank=None, world_size=None, reduce=True,
+                    target_width=None, min_slices=None):
     """Slice-parallel contraction: sum over all assignments of ``sliced_inds``
     of the contraction with those indices fixed; assignments are sharded over
     the ranks and combined with one all-reduce.
 
+    ``sliced_inds=None`` picks the indices with :func:`quimb_b200.tree.
+    find_slices` (at least one slice per rank, intermediates of at most
+    ``2**target_width`` elements).
     ``contract_fn(arrays, inputs, output, optimize)`` defaults to the device
     tree executor; the CPU tests inject a stand-in to exercise the sharding
     and the collective without a GPU.
@@ -66,6 +70,18 @@ def contract_sliced(arrays, inputs, output, sliced_inds, optimize="auto",
     if contract_fn is None:
         from .tree import array_contract as contract_fn
     inputs = [tuple(t) for t in inputs]
+    if sliced_inds is None:
+        # choose the slices from the tree: enough of them to feed every rank
+        # and narrow enough to fit ``target_width`` (log2 elements)
+        from .tree import find_slices, find_tree
+        sd = {}
+        for t, x in zip(inputs, arrays):
+            for ix, d in zip(t, x.shape):
+                sd[ix] = int(d)
+        full_tree = find_tree(inputs, tuple(output), sd, optimize)
+        if min_slices is None:
+            min_slices = world()[1] if world_size is None else world_size
+        sliced_inds = find_slices(full_tree, target_width, min_slices)[0]
     sliced = tuple(sliced_inds)
     if any(ix in output for ix in sliced):
         raise ValueError("cannot slice an output index")

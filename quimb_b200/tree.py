@@ -91,6 +91,71 @@ class Tree:
         return math.log2(w)
 
 
+def find_slices(tree, target_width=None, min_slices=None, max_slices=1 << 20):
+    """Choose indices to slice (fix to each of their values and sum) so that
+    the largest intermediate of ``tree`` has at most ``2**target_width``
+    elements and / or there are at least ``min_slices`` independent
+    contractions -- the unit multi-GPU runs shard (quimb/tensor/
+    tensor_core.py:255-259; the role of cotengra's SliceFinder).  Greedy: the
+    index whose removal shrinks the widest intermediates most, ties broken by
+    total cost.  Returns ``(sliced_inds, n_slices, width, cost_per_slice)``.
+    Host-only."""
+    out_set = set(tree.output)
+    node_inds = dict(enumerate(tree.inputs))
+    steps = []
+    for i, j, k, res in tree.steps:
+        steps.append((tuple(node_inds[i]), tuple(node_inds[j]), tuple(res)))
+        node_inds[k] = res
+    sz = dict(tree.size_dict)
+
+    def measure(removed):
+        width, cost = 1, 0
+        for a, b, r in steps:
+            w = math.prod(sz[ix] for ix in r if ix not in removed)
+            c = math.prod(sz[ix] for ix in set(a) | set(b) if ix not in removed)
+            width = max(width, w)
+            cost += c
+        return width, cost
+
+    sliced, nsl = [], 1
+    width, cost = measure(set())
+
+    def done():
+        ok_w = target_width is None or width <= 2 ** target_width
+        ok_n = min_slices is None or nsl >= min_slices
+        return ok_w and ok_n
+
+    while not done():
+        removed = set(sliced)
+        # candidates: indices of the widest intermediates (or any inner index
+        # when only the slice count is short)
+        cands = set()
+        for a, b, r in steps:
+            w = math.prod(sz[ix] for ix in r if ix not in removed)
+            if w == width or target_width is None or width <= 2 ** (target_width or 0):
+                cands.update(ix for ix in r if ix not in removed and ix not in out_set)
+        if not cands:
+            for a, b, r in steps:
+                cands.update(ix for ix in set(a) | set(b)
+                             if ix not in removed and ix not in out_set)
+        cands = {ix for ix in cands if sz[ix] > 1}
+        if not cands:
+            break
+        best = None
+        for ix in sorted(cands, key=str):
+            w, c = measure(removed | {ix})
+            key = (w, c * sz[ix])
+            if best is None or key < best[0]:
+                best = (key, ix, w, c)
+        _, ix, width, cost = best
+        sliced.append(ix)
+        nsl *= sz[ix]
+        if nsl > max_slices:
+            raise ValueError(f"find_slices: more than {max_slices} slices would be "
+                             "needed; use a better contraction tree")
+    return tuple(sliced), nsl, math.log2(width), cost
+
+
 def linear_to_ssa(path, n):
     ids = list(range(n))
     nxt = n

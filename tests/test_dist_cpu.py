@@ -33,6 +33,9 @@ def _worker(rank, world, port, ret):
                                    contract_fn=_np_contract)
     ref = np.einsum("isk,ksl,lt->it", a, b, c)
     ok = np.allclose(out.numpy(), ref, atol=1e-12)
+    # automatic choice of the sliced indices: at least one slice per rank
+    out2, mine2 = qd.contract_sliced([a, b, c], inputs, ("i", "t"), contract_fn=_np_contract)
+    ok = ok and np.allclose(out2.numpy(), ref, atol=1e-12) and len(mine2) >= 1
     # units are disjoint and cover everything
     allu = [None] * world
     dist.all_gather_object(allu, mine)

@@ -51,3 +51,20 @@ def test_cuda_graph_replay_of_a_tree():
     v2 = complex(g(*arrays2).item())
     assert qb.launch_count() == n0          # no host-side launches: graph replay
     assert abs(v2 - amp2) <= 1e-10
+
+
+@pytest.mark.parametrize("Lx,Ly,depth,gate", [(3, 3, 8, "fsim"), (2, 4, 12, "cz"),
+                                              (4, 4, 8, "fsim")])
+def test_grid_circuit_amplitude_matches_statevector(Lx, Ly, depth, gate):
+    """BASELINE configs[3] geometry at CPU-checkable size: qubits on a grid,
+    random U3 layers, fSim / CZ on the bond patterns A, B, C, D in turn."""
+    from tests.circuit_util import grid_bond_patterns, random_grid_circuit_amplitude
+    pats = grid_bond_patterns(Lx, Ly)
+    allb = [b for p in pats for b in p]
+    assert len(allb) == len(set(allb)) == Lx * (Ly - 1) + Ly * (Lx - 1)
+    rng = np.random.default_rng(Lx * 10 + Ly)
+    for bits in ([0] * (Lx * Ly), rng.integers(0, 2, Lx * Ly).tolist()):
+        arrays, inputs, output, amp = random_grid_circuit_amplitude(
+            Lx, Ly, depth, seed=3, bits=bits, gate=gate)
+        out = qb.array_contract(arrays, inputs, output, optimize="greedy")
+        assert abs(complex(out.item()) - amp) <= 1e-10 * max(1.0, abs(amp))

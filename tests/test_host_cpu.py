@@ -162,3 +162,27 @@ def test_fuse_perm_and_shape_match_reference_rule():
         operm, oshape = dn.calc_fuse_perm_and_shape(shape, groups)
         assert (tuple(range(nd)) if perm is None else perm) == operm
         assert (shape if new_shape is None else new_shape) == oshape
+
+
+def test_find_slices_reduces_width_and_partitions_the_sum():
+    from tests.circuit_util import random_grid_circuit_amplitude
+    arrays, inputs, output, amp = random_grid_circuit_amplitude(3, 3, 8, seed=1)
+    sz = {ix: 2 for t in inputs for ix in t}
+    tr = tree.find_tree(inputs, output, sz, "greedy")
+    w0 = tr.contraction_width()
+    sl, n, w, cost = tree.find_slices(tr, target_width=w0 - 3)
+    assert w <= w0 - 3 and n == 2 ** len(sl) and len(set(sl)) == len(sl)
+    assert not set(sl) & set(output)
+    sl8, n8, _, _ = tree.find_slices(tr, min_slices=8)
+    assert n8 >= 8
+    # the sliced contractions sum to the full one (numpy stand-in executor)
+    import itertools as it
+    total = 0.0
+    for vals in it.product(*[range(2) for _ in sl]):
+        fix = dict(zip(sl, vals))
+        sub = [a[tuple(fix[ix] if ix in fix else slice(None) for ix in t)]
+               for a, t in zip(arrays, inputs)]
+        red = [tuple(ix for ix in t if ix not in fix) for t in inputs]
+        total += complex(cn.array_contract(sub, red, output, "greedy"))
+    assert abs(total - amp) < 1e-10
+    assert tree.find_slices(tr) == ((), 1, w0, tr.contraction_cost())
