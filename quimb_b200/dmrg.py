@@ -49,7 +49,8 @@ def get_default_opts():
         "bond_compress_cutoff_mode": "sum2",
         "local_eig_tol": 1e-3,
         "local_eig_ncv": 4,          # ARPACK's basis size in parity mode
-        "device_eig_ncv": 16,        # max basis size of the device Lanczos
+        "device_eig_ncv": 32,        # max basis size of the device Lanczos
+        "device_eig_min_steps": 4,   # like ARPACK's ncv=4: >= 4 matvecs per solve
         "local_eig_backend": None,   # None: device Lanczos; 'SCIPY': parity mode
         "local_eig_maxiter": None,
     }
@@ -254,7 +255,8 @@ class DMRG2:
             ncv, tol = min(n, 16), 1e-12
         return eigh_lanczos(Heff, v0, which=self.which, ncv=ncv, tol=tol,
                             maxiter=self.opts["local_eig_maxiter"],
-                            return_info=True, comm=comm)
+                            return_info=True, comm=comm,
+                            min_steps=self.opts["device_eig_min_steps"])
 
     def _update_local_state_2site(self, i, direction, max_bond=None,
                                   cutoff=1e-10, cutoff_mode="sum2",

@@ -13,9 +13,11 @@ process lives on the device here:
     kernels (``qb_multi_dot`` : h = V w,  ``qb_multi_axpy`` : w -= V^T h);
   * the images ``W_j = H v_j`` are kept, so the projected matrix
     ``V H V^T`` is one skinny contraction;
-  * two small device->host reads per restart cycle (the ncv x ncv projected
-    matrix, then the true residual norm |H x - theta x|); the tiny dense
-    eigenproblem is host control logic, as in ARPACK.
+  * one small device->host read per step (the new column of the projected
+    matrix and beta_{j+1}: <= 65 doubles) so the Ritz value and the Lanczos
+    residual estimate are monitored after every matvec, plus the true residual
+    norm |H x - theta x| once per cycle; the tiny dense eigenproblem is host
+    control logic, as in ARPACK.
 
 Convergence test as in ARPACK's dsaupd: ``resid <= tol * max(eps^(2/3),
 |theta|)``.  The basis size ``ncv`` is a free parameter of the device solver:
@@ -37,6 +39,7 @@ from .linalg import norm as _norm
 
 _J, _N = 0, 1
 _MD_WS = {}
+_NCV_MAX = 64
 
 
 def _md_ws(dev):
@@ -58,27 +61,47 @@ def _norm_c(x, comm):
     return ops.sqrt(n2)
 
 
-def _orthogonalise(V, j, w, h, comm=None):
-    """Two classical Gram-Schmidt passes of w against V[0..j] (in place).
-    With ``comm`` the vectors are row slabs: the m dot products are summed
-    over the ranks (one tiny all-reduce per pass)."""
+_MD_MAX = 16        # rows per call of the fused Krylov kernels (csrc: MD_MAX)
+
+
+def _combine(V, m, coeffs, out, alpha=1.0):
+    """out += alpha * sum_j coeffs[j] V[j]  (j < m), 16 basis rows per launch."""
+    lib = _lib.load()
+    n = out.numel()
+    st = _lib.stream_ptr()
+    for j0 in range(0, m, _MD_MAX):
+        mm = min(_MD_MAX, m - j0)
+        rc = lib.qb_multi_axpy(_lib.QB_F64, mm, n, V[j0].data_ptr(), V.stride(0),
+                               coeffs[j0:].data_ptr(), float(alpha), out.data_ptr(), st)
+        _lib.check(rc, "qb_multi_axpy")
+
+
+def _orthogonalise(V, j, w, h, comm=None, keep=None):
+    """Two classical Gram-Schmidt passes of w against V[0..j] (in place), each
+    pass = all inner products first, then the update (16 basis rows per
+    launch of the fused kernels).  With ``comm`` the vectors are row slabs:
+    the dot products are summed over the ranks (one tiny all-reduce per pass).
+    ``keep`` (device vector) receives the first-pass coefficients <V[i], w>:
+    for w = H V[j] that is column j of the projected matrix V^T H V."""
     lib = _lib.load()
     m, n = j + 1, w.numel()
     st = _lib.stream_ptr()
     ws = _md_ws(w.device).data_ptr()
-    for _ in range(2):
-        rc = lib.qb_multi_dot(_lib.QB_F64, m, n, V.data_ptr(), V.stride(0),
-                              w.data_ptr(), h.data_ptr(), ws, st)
-        _lib.check(rc, "qb_multi_dot")
+    for it in range(2):
+        for j0 in range(0, m, _MD_MAX):
+            mm = min(_MD_MAX, m - j0)
+            rc = lib.qb_multi_dot(_lib.QB_F64, mm, n, V[j0].data_ptr(), V.stride(0),
+                                  w.data_ptr(), h[j0:].data_ptr(), ws, st)
+            _lib.check(rc, "qb_multi_dot")
         if comm is not None:
-            comm.all_reduce_(h)
-        rc = lib.qb_multi_axpy(_lib.QB_F64, m, n, V.data_ptr(), V.stride(0),
-                               h.data_ptr(), -1.0, w.data_ptr(), st)
-        _lib.check(rc, "qb_multi_axpy")
+            comm.all_reduce_(h[:m])
+        if it == 0 and keep is not None:
+            keep[:m].copy_(h[:m])
+        _combine(V, m, h, w, -1.0)
 
 
 def eigh_lanczos(matvec, v0, which="SA", ncv=4, tol=1e-3, maxiter=None,
-                 return_info=False, comm=None):
+                 return_info=False, comm=None, min_steps=4):
     """Lowest ('SA') or highest ('LA') eigenpair of a Hermitian operator.
 
     Parameters
@@ -88,7 +111,13 @@ def eigh_lanczos(matvec, v0, which="SA", ncv=4, tol=1e-3, maxiter=None,
     v0 : Array
         Start vector (any shape, flattened).
     ncv : int
-        Krylov basis size between restarts (2 <= ncv <= 16).
+        Largest Krylov basis between restarts (2 <= ncv <= 64); a cycle ends
+        as soon as the Lanczos residual estimate meets ``tol``.
+    min_steps : int
+        Matvecs before the residual estimate may stop the solve.  ARPACK with
+        ``ncv=4`` (the reference's setting) always spends 4; stopping earlier
+        than that leaves the local states of a sweep visibly less converged
+        than the reference's at the same ``tol``.
     comm : object with ``all_reduce_(tensor)``, optional
         Row-sharded mode (quimb_b200.dist.BondShard): ``v0`` and every vector
         handed to / returned by ``matvec`` is this rank's slab; inner products
@@ -117,13 +146,13 @@ def eigh_lanczos(matvec, v0, which="SA", ncv=4, tol=1e-3, maxiter=None,
         raise NotImplementedError(f"eigh_lanczos: dtype {dt} is not implemented "
                                   "yet (float64 only; no fallback)")
     dev = v0.t.device
-    m = max(2, min(int(ncv), n, 16))
+    m = max(2, min(int(ncv), n, _NCV_MAX))
     if maxiter is None:
         maxiter = 1000
     V = torch.zeros((m, n), dtype=dt, device=dev)
     W = torch.empty((m, n), dtype=dt, device=dev)
     w = torch.empty((n,), dtype=dt, device=dev)
-    h = torch.zeros((16,), dtype=dt, device=dev)
+    h = torch.zeros((_NCV_MAX,), dtype=dt, device=dev)
     eps23 = np.finfo(np.float64).eps ** (2.0 / 3.0)
     sign = 1.0 if which in ("SA", "SR") else -1.0
 
@@ -136,43 +165,51 @@ def eigh_lanczos(matvec, v0, which="SA", ncv=4, tol=1e-3, maxiter=None,
     info = {"restarts": 0, "converged": False}
     x = Array(V[0])
     mmax = m
+    min_steps = min(int(min_steps), n)
+    col = torch.zeros((_NCV_MAX + 1,), dtype=dt, device=dev)
     for cycle in range(maxiter):
-        # adaptive basis: a short first cycle (an already good v0 converges
-        # in ~3 matvecs, like ARPACK's ncv=4), longer ones for hard problems
-        m = min(mmax, 4 << min(cycle, 4))
+        # The projected matrix is assembled column by column on the host from
+        # the Gram-Schmidt coefficients (ONE small device->host read per step),
+        # so the Ritz value and the Lanczos residual estimate
+        # |beta_{j+1} y_j| are known after every matvec and the cycle stops as
+        # soon as it has converged: an already good v0 costs ~3 matvecs (like
+        # ARPACK's ncv = 4), a hard problem uses the whole basis without
+        # paying for restarts it does not need.
+        m = mmax
+        Hh = np.zeros((m, m))
+        meff = m
         for j in range(m):
             if not (j == 0 and have_w0):
                 Wj = matvec(Array(V[j]))
                 nmv += 1
                 W[j].copy_(ops.materialize(Wj).t.reshape(-1))
-            if j + 1 < m:
-                w.copy_(W[j])
-                _orthogonalise(V, j, w, h, comm)
-                bnorm = _norm_c(Array(w), comm)
-                V[j + 1].copy_(w)
-                ops.scale_(Array(V[j + 1]), 1.0, div_by=bnorm)
-        # projected matrix (m x m): host read #1 of the cycle
-        Hm = contract_pair(V[:m], [_J, _N], W[:m], [2, _N], [_J, 2])
-        if comm is not None:
-            comm.all_reduce_(Hm)
-        Hh = Hm.cpu().numpy()
-        Hh = 0.5 * (Hh + Hh.T)
-        evals, evecs = np.linalg.eigh(sign * Hh)
-        theta = sign * evals[0]
-        y = evecs[:, 0]
-        yd = torch.zeros(16, dtype=dt)
+            w.copy_(W[j])
+            _orthogonalise(V, j, w, h, comm, keep=col)
+            bnorm = _norm_c(Array(w), comm)
+            col[j + 1].copy_(bnorm.t)
+            c = col[:j + 2].cpu().numpy()
+            Hh[:j + 1, j] = c[:j + 1]
+            Hh[j, :j + 1] = c[:j + 1]
+            beta = float(c[j + 1])
+            evals, evecs = np.linalg.eigh(sign * Hh[:j + 1, :j + 1])
+            theta = sign * evals[0]
+            y = evecs[:, 0]
+            est = abs(beta * y[-1])
+            conv = est <= tol * max(eps23, abs(theta)) and nmv >= min_steps
+            if (conv or j + 1 == m or not np.isfinite(est)
+                    or beta <= 1e-14 * max(1.0, abs(theta))):
+                meff = j + 1
+                break
+            V[j + 1].copy_(w)
+            ops.scale_(Array(V[j + 1]), 1.0, div_by=bnorm)
+        m = meff
+        yd = torch.zeros(_NCV_MAX, dtype=dt)
         yd[:m] = torch.as_tensor(y, dtype=dt)
         yd = yd.to(dev)
-        lib = _lib.load()
         xnew = torch.zeros((n,), dtype=dt, device=dev)
         hx = torch.zeros((n,), dtype=dt, device=dev)
-        st = _lib.stream_ptr()
-        _lib.check(lib.qb_multi_axpy(_lib.QB_F64, m, n, V.data_ptr(), V.stride(0),
-                                     yd.data_ptr(), 1.0, xnew.data_ptr(), st),
-                   "qb_multi_axpy")
-        _lib.check(lib.qb_multi_axpy(_lib.QB_F64, m, n, W.data_ptr(), W.stride(0),
-                                     yd.data_ptr(), 1.0, hx.data_ptr(), st),
-                   "qb_multi_axpy")
+        _combine(V, m, yd, xnew)
+        _combine(W, m, yd, hx)
         # true residual |H x - theta x| (robust to Krylov breakdown):
         # host read #2
         w.copy_(hx)

@@ -190,3 +190,61 @@ def test_two_ended_mps_norm_gloo_world2():
         p.join(timeout=240)
         assert p.exitcode == 0
     assert ret[0] and ret[1]
+
+
+def _sharded_lanczos_worker(rank, world, port, ret):
+    """Row-sharded device Lanczos (the bond-sharded DMRG eigensolve's solver)
+    on gloo: every rank holds a row slab of the operator and of all Krylov
+    vectors; inner products are all-reduced, all ranks take the same decisions
+    and agree with the dense eigenvalue.  Host layer on the ABI emulator."""
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from tests.abi_emulator import emulated_abi
+    import quimb_b200 as qb
+    from quimb_b200.dist import BondShard
+    ok = True
+    with emulated_abi():
+        sh = BondShard()
+        rng = np.random.default_rng(4)
+        n = 301                                      # ragged slabs
+        A = rng.standard_normal((n, n))
+        H = A + A.T + np.diag(np.linspace(-40, 40, n))
+        lo, hi = sh.slab(n)
+        Hloc = qb.asarray(H[lo:hi].copy())
+        v0 = rng.standard_normal(n)
+
+        def matvec(v_local):
+            full = sh.all_gather_rows(v_local.t.reshape(-1, 1), n).reshape(-1)
+            return qb.tensordot(Hloc, qb.asarray(full), axes=((1,), (0,)))
+
+        for ncv, tol in ((8, 1e-8), (40, 1e-10)):
+            theta, x, info = qb.eigh_lanczos(matvec, qb.asarray(v0[lo:hi].copy()), ncv=ncv,
+                                             tol=tol, return_info=True, comm=sh)
+            ref = np.linalg.eigvalsh(H)[0]
+            ok = ok and abs(theta - ref) < 1e-7 and info["converged"]
+            allinfo = [None] * world
+            dist.all_gather_object(allinfo, (round(theta, 12), info["nmatvec"], info["restarts"]))
+            ok = ok and allinfo[0] == allinfo[1]
+            # the local slabs assemble to a normalised eigenvector
+            full = sh.all_gather_rows(x.t.reshape(-1, 1), n).reshape(-1).numpy()
+            ok = ok and abs(np.linalg.norm(full) - 1) < 1e-10
+            ok = ok and np.linalg.norm(H @ full - theta * full) < 1e-5
+    ret[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+def test_sharded_lanczos_gloo_world2():
+    mp.set_start_method("spawn", force=True)
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = 37500 + (os.getpid() % 2000)
+    procs = [mp.Process(target=_sharded_lanczos_worker, args=(r, 2, port, ret))
+             for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=240)
+        assert p.exitcode == 0
+    assert ret[0] and ret[1]
