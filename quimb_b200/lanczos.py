@@ -7,8 +7,9 @@ and every iteration calls back into ``TNLinearOperator._matvec``.  With a
 device matvec that would cross PCIe twice per iteration, so the whole Krylov
 process lives on the device here:
 
-  * restarted Lanczos (thick restart with the Ritz vector, whose image H x is
-    known, so a restart costs no matvec), full re-orthogonalisation by
+  * thick-restart Lanczos (the lowest few Ritz vectors are kept together with
+    their images H x, which are known, so a restart costs no matvec and loses
+    little of the Krylov space), full re-orthogonalisation by
     classical Gram-Schmidt applied twice, each pass = two fused HBM-bound
     kernels (``qb_multi_dot`` : h = V w,  ``qb_multi_axpy`` : w -= V^T h);
   * the images ``W_j = H v_j`` are kept, so the projected matrix
@@ -159,7 +160,6 @@ def eigh_lanczos(matvec, v0, which="SA", ncv=4, tol=1e-3, maxiter=None,
     nrm = _norm_c(v0, comm)
     V[0].copy_(v0.t)
     ops.scale_(Array(V[0]), 1.0, div_by=nrm)
-    have_w0 = False
     nmv = 0
     theta, resid = None, None
     info = {"restarts": 0, "converged": False}
@@ -167,6 +167,13 @@ def eigh_lanczos(matvec, v0, which="SA", ncv=4, tol=1e-3, maxiter=None,
     mmax = m
     min_steps = min(int(min_steps), n)
     col = torch.zeros((_NCV_MAX + 1,), dtype=dt, device=dev)
+    # thick restart: the k lowest Ritz vectors (and their known images) are
+    # kept, followed by the last residual direction -- close to unrestarted
+    # Lanczos in matvecs at a bounded basis (Wu & Simon's TRLan scheme)
+    keep_max = max(1, min(mmax // 4, 8))
+    Vk = Wk = None
+    jstart = 0
+    Hh = np.zeros((mmax, mmax))
     for cycle in range(maxiter):
         # The projected matrix is assembled column by column on the host from
         # the Gram-Schmidt coefficients (ONE small device->host read per step),
@@ -176,13 +183,11 @@ def eigh_lanczos(matvec, v0, which="SA", ncv=4, tol=1e-3, maxiter=None,
         # ARPACK's ncv = 4), a hard problem uses the whole basis without
         # paying for restarts it does not need.
         m = mmax
-        Hh = np.zeros((m, m))
         meff = m
-        for j in range(m):
-            if not (j == 0 and have_w0):
-                Wj = matvec(Array(V[j]))
-                nmv += 1
-                W[j].copy_(ops.materialize(Wj).t.reshape(-1))
+        for j in range(jstart, m):
+            Wj = matvec(Array(V[j]))
+            nmv += 1
+            W[j].copy_(ops.materialize(Wj).t.reshape(-1))
             w.copy_(W[j])
             _orthogonalise(V, j, w, h, comm, keep=col)
             bnorm = _norm_c(Array(w), comm)
@@ -203,31 +208,58 @@ def eigh_lanczos(matvec, v0, which="SA", ncv=4, tol=1e-3, maxiter=None,
             V[j + 1].copy_(w)
             ops.scale_(Array(V[j + 1]), 1.0, div_by=bnorm)
         m = meff
-        yd = torch.zeros(_NCV_MAX, dtype=dt)
-        yd[:m] = torch.as_tensor(y, dtype=dt)
-        yd = yd.to(dev)
-        xnew = torch.zeros((n,), dtype=dt, device=dev)
-        hx = torch.zeros((n,), dtype=dt, device=dev)
-        _combine(V, m, yd, xnew)
-        _combine(W, m, yd, hx)
-        # true residual |H x - theta x| (robust to Krylov breakdown):
-        # host read #2
-        w.copy_(hx)
-        ops.axpby(-theta, Array(xnew), 1.0, Array(w))
-        resid = float(_norm_c(Array(w), comm).item())
+
+        def ritz(yvec, out_v, out_w):
+            yd = torch.zeros(_NCV_MAX, dtype=dt)
+            yd[:m] = torch.as_tensor(np.ascontiguousarray(yvec), dtype=dt)
+            yd = yd.to(dev)
+            out_v.zero_()
+            out_w.zero_()
+            _combine(V, m, yd, out_v)
+            _combine(W, m, yd, out_w)
+
+        xnew = torch.empty((n,), dtype=dt, device=dev)
+        hx = torch.empty((n,), dtype=dt, device=dev)
+        ritz(y, xnew, hx)
+        # true residual |H x - theta x| (robust to Krylov breakdown): one more
+        # host read per cycle.  `w` still holds the last residual direction,
+        # so the check uses its own buffer.
+        rchk = hx.clone()
+        ops.axpby(-theta, Array(xnew), 1.0, Array(rchk))
+        resid = float(_norm_c(Array(rchk), comm).item())
         info["restarts"] = cycle
         if resid <= tol * max(eps23, abs(theta)) or not np.isfinite(resid):
             info["converged"] = bool(np.isfinite(resid))
             x = Array(xnew)
             break
-        # restart from the Ritz vector; its image is known
-        xn = _norm_c(Array(xnew), comm)
-        V[0].copy_(xnew)
-        ops.scale_(Array(V[0]), 1.0, div_by=xn)
-        W[0].copy_(hx)
-        ops.scale_(Array(W[0]), 1.0, div_by=xn)
-        have_w0 = True
-        x = Array(V[0].clone())
+        x = Array(xnew)
+        # ---- thick restart ------------------------------------------------
+        k = max(1, min(keep_max, m - 1))
+        if Vk is None:
+            Vk = torch.empty((keep_max, n), dtype=dt, device=dev)
+            Wk = torch.empty((keep_max, n), dtype=dt, device=dev)
+        ritz(y, Vk[0], Wk[0])                       # == (xnew, hx)
+        for i in range(1, k):
+            ritz(evecs[:, i], Vk[i], Wk[i])
+        usable = beta > 1e-14 * max(1.0, abs(theta)) and np.isfinite(beta)
+        V[:k].copy_(Vk[:k])
+        W[:k].copy_(Wk[:k])
+        Hh[:] = 0.0
+        Hh[np.arange(k), np.arange(k)] = sign * evals[:k]
+        if usable and k < mmax:
+            # next basis vector: the residual direction shared by all Ritz pairs
+            V[k].copy_(w)
+            ops.scale_(Array(V[k]), 1.0, div_by=bnorm)
+            jstart = k
+        else:
+            # invariant subspace reached without convergence of the true
+            # residual (rounding): continue from the best Ritz vector alone
+            k = 1
+            Hh[:] = 0.0
+            jstart = 0
+        if jstart == 0:
+            xn = _norm_c(Array(V[0]), comm)
+            ops.scale_(Array(V[0]), 1.0, div_by=xn)
     # normalise the Ritz vector
     xn = _norm_c(x, comm)
     x = ops.scale_(ops.materialize(x, force=True), 1.0, div_by=xn)

@@ -215,3 +215,39 @@ def test_environments_and_moving_environment_vs_oracle():
             val = np.einsum("xwa,apm,mqb,wvPp,vuQq,xPn,nQy,yub->", Le, A, B, mpo[i],
                             mpo[i + 1], A.conj(), B.conj(), Re, optimize=True)
             assert abs(val - expec) <= 1e-10 * abs(expec), (begin, i)
+
+
+@pytest.mark.parametrize("ncv", [2, 3, 4, 8, 20, 64])
+def test_lanczos_thick_restart_all_basis_sizes(ncv):
+    """Thick-restart Lanczos with per-step residual monitoring: every basis
+    size converges to the dense answer ('SA' and 'LA'), clustered spectra
+    included; the residual reported is the true |H x - theta x|."""
+    rng = np.random.default_rng(ncv)
+    n = 400
+    q, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    # close (but, for the 2- and 3-vector bases, not pathological) low cluster
+    low = [-5.0, -4.999, -4.99] if ncv >= 8 else [-5.0, -4.5, -4.2]
+    lam = np.concatenate([low, np.linspace(-4, 6, n - 3)])
+    H = (q * lam) @ q.T
+    Hd = qb.asarray(H)
+    count = [0]
+
+    def mv(v):
+        count[0] += 1
+        return qb.tensordot(Hd, v, axes=((1,), (0,)))
+
+    v0 = qb.asarray(rng.standard_normal(n))
+    for which, ref in (("SA", lam.min()), ("LA", lam.max())):
+        count[0] = 0
+        theta, x, info = qb.eigh_lanczos(mv, v0, which=which, ncv=ncv, tol=1e-9,
+                                         maxiter=4000, return_info=True)
+        assert info["converged"] and info["nmatvec"] == count[0]
+        assert abs(theta - ref) < 1e-8, (which, ncv, theta, ref)
+        xv = x.to_numpy()
+        assert abs(np.linalg.norm(xv) - 1) < 1e-12
+        assert np.linalg.norm(H @ xv - theta * xv) <= 2e-9 * max(1, abs(theta))
+    # a converged start vector stops after the ARPACK-like minimum of matvecs
+    count[0] = 0
+    theta, x, info = qb.eigh_lanczos(mv, qb.asarray(q[:, 0].copy()), ncv=max(ncv, 4), tol=1e-6,
+                                     return_info=True)
+    assert abs(theta - lam[0]) < 1e-9 and info["nmatvec"] <= 4
