@@ -251,3 +251,20 @@ def test_lanczos_thick_restart_all_basis_sizes(ncv):
     theta, x, info = qb.eigh_lanczos(mv, qb.asarray(q[:, 0].copy()), ncv=max(ncv, 4), tol=1e-6,
                                      return_info=True)
     assert abs(theta - lam[0]) < 1e-9 and info["nmatvec"] <= 4
+
+
+@pytest.mark.parametrize("method,tol", [("svd:eig", 1e-8), ("svd:rand", 1e-5)])
+def test_dmrg2_other_bond_compress_methods(method, tol):
+    """bond_compress_method (dmrg.py:84-102 opts): the Gram-matrix SVD gives
+    the same energies as the Jacobi SVD; the randomized range finder is an
+    approximation near the cut (GEMM-bound alternative at large chi)."""
+    mpo = dm.mpo_heis(14)
+    ref = qb.DMRG2(mpo, [8, 16, 32], cutoffs=1e-10, mpo_shape="lrdu", seed=2)
+    ref.solve(tol=1e-7, max_sweeps=8)
+    d = qb.DMRG2(mpo, [8, 16, 32], cutoffs=1e-10, mpo_shape="lrdu", seed=2)
+    d.opts["bond_compress_method"] = method
+    d.solve(tol=1e-7, max_sweeps=8)
+    assert abs(d.energy - ref.energy) < tol * abs(ref.energy)
+    with pytest.raises(ValueError):
+        d.opts["bond_compress_method"] = "cholesky"
+        d.sweep("R", max_bond=8, cutoff=0.0, method="cholesky")
