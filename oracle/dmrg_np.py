@@ -321,3 +321,134 @@ class DMRG2:
     @property
     def energy(self):
         return self.energies[-1]
+
+
+# ------------------------------------------------------------------ DMRG1 ---
+class EffHam1(spla.LinearOperator):
+    """One-site effective Hamiltonian L - W - R (dmrg.py:756-801)."""
+
+    def __init__(self, Lenv, W, Renv, dims):
+        self.L, self.W, self.R = Lenv, W, Renv
+        self.dims = dims  # (a, s, b)
+        n = int(np.prod(dims))
+        self.nmatvec = 0
+        super().__init__(dtype=Lenv.dtype, shape=(n, n))
+
+    def _matvec(self, v):
+        self.nmatvec += 1
+        x = v.reshape(self.dims)                                 # a s b
+        T = np.tensordot(self.L, x, axes=(2, 0))                 # a' w s b
+        T = np.tensordot(T, self.W, axes=((1, 2), (0, 3)))       # a' b w' s'
+        T = np.tensordot(T, self.R, axes=((2, 1), (1, 2)))       # a' s' b'
+        return T.reshape(-1)
+
+
+class DMRG1(DMRG2):
+    """quimb's DMRG1 = DMRG(bsz=1) (dmrg.py:756-801, 1100-1106, 1137-1156):
+    bonds are padded with noise of strength 1e-6 before every sweep
+    (expand_bond_dimension), each site is solved and the orthogonality centre
+    moved on by a stabilised QR / LQ."""
+
+    def __init__(self, mpo, bond_dims, cutoffs=1e-8, p0=None, seed=0):
+        super().__init__(mpo, bond_dims, cutoffs, p0=p0, seed=seed)
+        self._rng = np.random.default_rng(seed + 12345)
+
+    def expand(self, new_bond_dim, rand_strength=1e-6):
+        for i in range(self.L - 1):
+            cur = self.k[i].shape[2]
+            if cur >= new_bond_dim:
+                continue
+            ex = new_bond_dim - cur
+            a, b = self.k[i], self.k[i + 1]
+            pa = rand_strength * self._rng.standard_normal((a.shape[0], a.shape[1], ex))
+            pb = rand_strength * self._rng.standard_normal((ex, b.shape[1], b.shape[2]))
+            self.k[i] = np.concatenate([a, pa.astype(a.dtype)], axis=2)
+            self.k[i + 1] = np.concatenate([b, pb.astype(b.dtype)], axis=0)
+
+    def _init_right_envs(self):
+        dt = self.k[0].dtype
+        self.renv = {self.L - 1: np.ones((1, 1, 1), dtype=dt)}
+        for i in range(self.L - 1, 0, -1):
+            self.renv[i - 1] = env_step_right(self.renv[i], self.k[i], self.mpo[i])
+
+    def _init_left_envs(self):
+        dt = self.k[0].dtype
+        self.lenv = {0: np.ones((1, 1, 1), dtype=dt)}
+        for i in range(0, self.L - 1):
+            self.lenv[i + 1] = env_step_left(self.lenv[i], self.k[i], self.mpo[i])
+
+    def _update_1site(self, i, direction):
+        A = self.k[i]
+        dims = A.shape
+        Heff = EffHam1(self.lenv[i], self.mpo[i], self.renv[i], dims)
+        v0 = A.reshape(-1)
+        n = v0.size
+        if n < 800:
+            Hd = Heff @ np.eye(n)
+            Hd = 0.5 * (Hd + Hd.conj().T)
+            evals, evecs = np.linalg.eigh(Hd)
+            loc_en, x = evals[0], evecs[:, 0]
+        else:
+            lk, vk = spla.eigsh(Heff, k=1, which="SA", v0=v0, ncv=self.opts["local_eig_ncv"],
+                                tol=self.opts["local_eig_tol"])
+            loc_en, x = lk[0], vk[:, 0]
+        self.nmatvecs.append(Heff.nmatvec)
+        self.k[i] = x.reshape(dims)
+        tot_en = np.vdot(x, Heff._matvec(x))
+        if direction == "right" and i < self.L - 1:
+            a, d, r = dims
+            Q, _, R = dn.qr_stabilized(self.k[i].reshape(a * d, r).copy(), absorb=dn.get_U_sVH)
+            self.k[i] = Q.reshape(a, d, -1)
+            self.k[i + 1] = np.tensordot(R, self.k[i + 1], axes=(1, 0))
+        elif direction == "left" and i > 0:
+            a, d, r = dims
+            Lf, _, Q = dn.qr_stabilized(self.k[i].reshape(a, d * r).copy(), absorb=dn.get_Us_VH)
+            self.k[i] = Q.reshape(-1, d, r)
+            self.k[i - 1] = np.tensordot(self.k[i - 1], Lf, axes=(2, 0))
+        return float(np.real(loc_en)), float(np.real(tot_en)), {}
+
+    def sweep(self, direction, canonize=True, max_bond=None, cutoff=0.0):
+        L = self.L
+        loc, tot = [], []
+        if direction == "R":
+            if canonize:
+                self.k = right_canonize(self.k)
+            self._init_right_envs()
+            self.lenv = {0: np.ones((1, 1, 1), dtype=self.k[0].dtype)}
+            for i in range(L):
+                if i > 0:
+                    self.lenv[i] = env_step_left(self.lenv[i - 1], self.k[i - 1],
+                                                 self.mpo[i - 1])
+                le, te, _ = self._update_1site(i, "right")
+                loc.append(le); tot.append(te)
+        else:
+            if canonize:
+                self.k = left_canonize(self.k)
+            self._init_left_envs()
+            self.renv = {L - 1: np.ones((1, 1, 1), dtype=self.k[0].dtype)}
+            for i in range(L - 1, -1, -1):
+                if i < L - 1:
+                    self.renv[i] = env_step_right(self.renv[i + 1], self.k[i + 1],
+                                                  self.mpo[i + 1])
+                le, te, _ = self._update_1site(i, "left")
+                loc.append(le); tot.append(te)
+        self.local_energies.append(tuple(loc))
+        self.total_energies.append(tuple(tot))
+        return tot[-1]
+
+    def solve(self, tol=1e-4, max_sweeps=10, sweep_sequence=None):
+        seq = sweep_sequence or self.opts["default_sweep_sequence"]
+        prev = "0"
+        for n in range(max_sweeps):
+            direction = seq[n % len(seq)]
+            idx = self._sweep_idx
+            max_bond = self.bond_dims[min(idx, len(self.bond_dims) - 1)]
+            self._sweep_idx += 1
+            canonize = (direction + prev) not in ("LR", "RL")
+            self.expand(max_bond)
+            en = self.sweep(direction, canonize=canonize)
+            self.energies.append(en)
+            if len(self.energies) >= 2 and abs(self.energies[-2] - self.energies[-1]) < tol:
+                return True
+            prev = direction
+        return False

@@ -488,6 +488,18 @@ def mps_dmrg_cases():
                      "converged": bool(conv), "energies": [float(e) for e in dm.energies],
                      "exact": exact, "max_bond": int(dm.state.max_bond())})
     meta["dmrg2_runs"] = runs
+    # DMRG1 of the reference (bond expansion noise is unseeded there: energies
+    # are compared at the convergence tolerance, not bit-wise)
+    runs1 = []
+    for L, bond_dims, tol in [(10, [4, 8, 16, 32], 1e-8), (16, [8, 16, 32], 1e-7)]:
+        Hm = qtn.MPO_ham_heis(L)
+        dm1 = qtn.DMRG1(Hm, bond_dims=bond_dims, cutoffs=1e-10)
+        conv = dm1.solve(tol=tol, max_sweeps=12, verbosity=0)
+        exact = float(qu.groundenergy(qu.ham_heis(L, cyclic=False, sparse=True)))
+        runs1.append({"L": L, "bond_dims": bond_dims, "tol": tol, "converged": bool(conv),
+                      "energies": [float(e) for e in dm1.energies], "exact": exact,
+                      "max_bond": int(dm1.state.max_bond())})
+    meta["dmrg1_runs"] = runs1
     meta["heisenberg_energy_100_periodic"] = float(qu.heisenberg_energy(100))
     np.savez_compressed(os.path.join(OUT, "mps_dmrg.npz"), **store)
     json.dump(meta, open(os.path.join(OUT, "mps_dmrg.json"), "w"), indent=1)

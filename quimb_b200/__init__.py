@@ -36,7 +36,7 @@ from .linop import TNLinearOperator  # noqa: F401
 from .tebd import TEBD, LocalHam1D, gate_split, gate_with_auto_swap  # noqa: F401
 from .boundary import (BoundaryContractor2D, contract_boundary,  # noqa: F401
                        contract_boundary_two_sided, peps_norm_tensors)
-from .dmrg import DMRG2  # noqa: F401
+from .dmrg import DMRG1, DMRG2  # noqa: F401
 from .integration import register_with_quimb  # noqa: F401
 
 __version__ = "0.1.0"

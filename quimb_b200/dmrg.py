@@ -53,6 +53,7 @@ def get_default_opts():
         "device_eig_min_steps": 4,   # like ARPACK's ncv=4: >= 4 matvecs per solve
         "local_eig_backend": None,   # None: device Lanczos; 'SCIPY': parity mode
         "local_eig_maxiter": None,
+        "bond_expand_rand_strength": 1e-6,
     }
 
 
@@ -229,15 +230,22 @@ class DMRG2:
         A = self._k[0]
         return ops.ones((1, 1, 1), dtype=A.dtype, device=A.device)
 
+    bsz = 2     # sites optimised at once (DMRG1 overrides)
+
     def _init_right_envs(self):
+        """renv[j]: everything to the right of site j."""
         self.renv = {self.L - 1: self._ones_env()}
-        for i in range(self.L - 1, 1, -1):
+        for i in range(self.L - 1, self.bsz - 1, -1):
             self.renv[i - 1] = env_right_step(self.renv[i], self._k[i], self.ham[i])
 
     def _init_left_envs(self):
+        """lenv[i]: everything to the left of site i."""
         self.lenv = {0: self._ones_env()}
-        for i in range(0, self.L - 2):
+        for i in range(0, self.L - self.bsz):
             self.lenv[i + 1] = env_left_step(self.lenv[i], self._k[i], self.ham[i])
+
+    def _update_local_state(self, i, direction, **update_opts):
+        return self._update_local_state_2site(i, direction, **update_opts)
 
     # ---- local update (dmrg.py:803-870) --------------------------------------
     def _eigs(self, Heff, v0, comm=None):
@@ -318,25 +326,26 @@ class DMRG2:
                 self.right_canonize()
             self._init_right_envs()
             self.lenv = {0: self._ones_env()}
-            for i in range(L - 1):
+            for i in range(L - self.bsz + 1):
                 if i > 0:
                     self.lenv[i] = env_left_step(self.lenv[i - 1], self._k[i - 1],
                                                  self.ham[i - 1])
                     self.lenv.pop(i - 1, None)
-                le, te = self._update_local_state_2site(i, "right", **update_opts)
-                self.renv.pop(i + 1, None)
+                le, te = self._update_local_state(i, "right", **update_opts)
+                self.renv.pop(i + self.bsz - 1, None)
                 loc.append(le); tot.append(te)
         elif direction == "L":
             if canonize:
                 self.left_canonize()
             self._init_left_envs()
             self.renv = {L - 1: self._ones_env()}
-            for i in range(L - 2, -1, -1):
-                if i < L - 2:
-                    self.renv[i + 1] = env_right_step(self.renv[i + 2],
-                                                      self._k[i + 2], self.ham[i + 2])
-                    self.renv.pop(i + 2, None)
-                le, te = self._update_local_state_2site(i, "left", **update_opts)
+            b = self.bsz
+            for i in range(L - b, -1, -1):
+                if i < L - b:
+                    self.renv[i + b - 1] = env_right_step(self.renv[i + b],
+                                                          self._k[i + b], self.ham[i + b])
+                    self.renv.pop(i + b, None)
+                le, te = self._update_local_state(i, "left", **update_opts)
                 self.lenv.pop(i, None)
                 loc.append(le); tot.append(te)
         else:
@@ -371,6 +380,10 @@ class DMRG2:
             direction, max_bond, cutoff = (next(directions), next(self._bond_dims),
                                            next(self._cutoffs))
             canonize = not (direction + previous in {"LR", "RL"})
+            if self.bsz == 1:
+                # one-site updates cannot grow a bond (dmrg.py:1100-1106)
+                self.expand_bond_dimension(
+                    max_bond, rand_strength=self.opts["bond_expand_rand_strength"])
             energy = self.sweep(direction, canonize=canonize, max_bond=max_bond,
                                 cutoff=cutoff,
                                 cutoff_mode=self.opts["bond_compress_cutoff_mode"],
@@ -384,6 +397,95 @@ class DMRG2:
                 break
             previous = direction
         return converged
+
+
+class EffHam1:
+    """One-site effective Hamiltonian L - W - R (dmrg.py:756-801 through
+    ``form_local_ops``): three launches of the contraction kernel,
+    2 w d chi^3 + 2 w^2 d^2 chi^2 + 2 w d chi^3 flops."""
+
+    def __init__(self, Lenv, W, Renv, dims):
+        self.L, self.W, self.R = Lenv, W, Renv
+        self.dims = tuple(dims)      # (a, s, b)
+        self.nmatvec = 0
+
+    def matvec(self, v):
+        self.nmatvec += 1
+        x = v.reshape(self.dims)
+        T = contract_pair(self.L.t, [LB_, W_, L_], x.t, [L_, S_, R_], [LB_, W_, S_, R_],
+                          conj_a=self.L.cj, conj_b=x.cj)
+        T = contract_pair(T, [LB_, W_, S_, R_], self.W.t, [W_, W1_, S_, SB_],
+                          [LB_, SB_, W1_, R_], conj_b=self.W.cj)
+        y = contract_pair(T, [LB_, SB_, W1_, R_], self.R.t, [RB_, W1_, R_],
+                          [LB_, SB_, RB_], conj_b=self.R.cj)
+        return Array(y).reshape(-1)
+
+    __call__ = matvec
+
+
+class DMRG1(DMRG2):
+    """One-site DMRG (quimb's ``DMRG1`` = ``DMRG(bsz=1)``, dmrg.py:1137-1156;
+    local update :756-801): the bond dimension is raised before every sweep
+    by padding the bonds with small noise (``expand_bond_dimension``,
+    tn1d/core.py:1523-1569; tensor_core.py:2369-2440), each site is solved with
+    the device Lanczos and the orthogonality centre moves on by a stabilised
+    QR / LQ (``_canonize_after_1site_update`` :617-624)."""
+
+    bsz = 1
+
+    def __init__(self, ham, bond_dims=None, cutoffs=1e-8, which="SA", p0=None, **kw):
+        if bond_dims is None:
+            bond_dims = range(10, 1001, 10)
+        self._expand_seed = kw.get("seed", None)
+        super().__init__(ham, bond_dims, cutoffs, which=which, p0=p0, **kw)
+        self._expand_calls = 0
+
+    def expand_bond_dimension(self, new_bond_dim, rand_strength=0.0):
+        """Pad every bond to at least ``new_bond_dim`` (zeros, or gaussian noise
+        of strength ``rand_strength``), in place."""
+        k = self._k
+        gen = None
+        for i in range(self.L - 1):
+            cur = k[i].shape[2]
+            if cur >= new_bond_dim:
+                continue
+            extra = new_bond_dim - cur
+            for which in (i, i + 1):
+                A = k[which].resolve()
+                shape = list(A.shape)
+                shape[2 if which == i else 0] = extra
+                if rand_strength:
+                    if gen is None:
+                        gen = torch.Generator(device=A.device)
+                        seed = 0 if self._expand_seed is None else int(self._expand_seed)
+                        gen.manual_seed(1000003 * (seed + 1) + self._expand_calls)
+                    rdt = A.real.dtype if A.dtype.is_complex else A.dtype
+                    pad = torch.randn(shape, generator=gen, dtype=rdt, device=A.device)
+                    pad = (pad * rand_strength).to(A.dtype)
+                else:
+                    pad = torch.zeros(shape, dtype=A.dtype, device=A.device)
+                k[which] = Array(torch.cat([A, pad], dim=2 if which == i else 0))
+        self._expand_calls += 1
+
+    def _update_local_state(self, i, direction, **update_opts):
+        return self._update_local_state_1site(i, direction, **update_opts)
+
+    def _update_local_state_1site(self, i, direction, **compress_opts):
+        from .tebd import left_canonize_site, right_canonize_site
+        A = self._k[i]
+        dims = A.shape
+        Heff = EffHam1(self.lenv[i], self.ham[i], self.renv[i], dims)
+        loc_en, loc_gs, info = self._eigs(Heff, ops.materialize(A, force=True))
+        x = ops.materialize(loc_gs).reshape(-1)
+        self._k[i] = x.reshape(*dims)
+        Hx = Heff.matvec(x)
+        tot_en = ops.vdot(x, Hx).item()
+        self.nmatvecs.append(Heff.nmatvec)
+        if direction == "right" and i < self.L - 1:
+            left_canonize_site(self._k, i)
+        elif direction == "left" and i > 0:
+            right_canonize_site(self._k, i)
+        return loc_en, float(np.real(tot_en))
 
 
 def _rand_mps(n, bond_dim, d, dtype, seed):

@@ -268,3 +268,27 @@ def test_dmrg2_other_bond_compress_methods(method, tol):
     with pytest.raises(ValueError):
         d.opts["bond_compress_method"] = "cholesky"
         d.sweep("R", max_bond=8, cutoff=0.0, method="cholesky")
+
+
+def test_dmrg1_matches_reference_and_oracle(golden_mps):
+    """One-site DMRG (quimb's DMRG1): energies of the reference's own runs
+    (tests/golden/mps_dmrg.json: dmrg1_runs), the numpy oracle and exact
+    diagonalisation; bonds grow only through expand_bond_dimension."""
+    from quimb_b200.dmrg import DMRG1
+    _, meta = golden_mps
+    for r in meta["dmrg1_runs"]:
+        mpo = dm.mpo_heis(r["L"])
+        d = DMRG1(mpo, r["bond_dims"], cutoffs=1e-10, mpo_shape="lrdu", seed=1)
+        assert d.solve(tol=r["tol"], max_sweeps=12)
+        assert abs(d.energy - r["energies"][-1]) < 50 * r["tol"]
+        assert abs(d.energy - r["exact"]) < 1e-6
+        assert d.max_bond() <= r["bond_dims"][-1]
+        o = dm.DMRG1(mpo, r["bond_dims"], cutoffs=1e-10, seed=1)
+        o.solve(tol=r["tol"], max_sweeps=12)
+        assert abs(d.energy - o.energy) < 50 * r["tol"]
+    # complex dtype is preserved, sweeps in both directions
+    mpo = dm.mpo_heis(8)
+    d = DMRG1(mpo, [4, 8, 16], cutoffs=1e-10, mpo_shape="lrdu", seed=3, dtype="complex128")
+    d.solve(tol=1e-8, max_sweeps=10, sweep_sequence="RL")
+    assert d.state[0].dtype == np.complex128
+    assert abs(d.energy - np.linalg.eigvalsh(dm.mpo_to_dense(mpo))[0]) < 1e-7

@@ -322,3 +322,15 @@ def test_tebd_oracle_matches_reference():
         assert max(a.shape[2] for a in t.sites) == r["max_bond"]
         np.testing.assert_allclose(dm.mps_to_dense(t.sites).reshape(-1),
                                    data[r["key"] + "__dense"], atol=1e-8)
+
+
+def test_dmrg1_oracle_matches_reference_energies(golden_mps):
+    """One-site DMRG: the reference pads bonds with unseeded noise, so runs are
+    compared at the convergence tolerance (and against exact diagonalisation)."""
+    _, meta = golden_mps
+    for r in meta["dmrg1_runs"]:
+        d = dm.DMRG1(dm.mpo_heis(r["L"]), r["bond_dims"], cutoffs=1e-10, seed=1)
+        assert d.solve(tol=r["tol"], max_sweeps=12)
+        assert abs(d.energy - r["energies"][-1]) < 50 * r["tol"]
+        assert abs(d.energy - r["exact"]) < 1e-6
+        assert abs(r["energies"][-1] - r["exact"]) < 1e-6     # the reference itself
