@@ -30,6 +30,8 @@ how the parity tests pin it (tests/golden/boundary.*).
 
 import itertools
 
+import numpy as np
+
 from . import ops
 from .array import Array
 from .split import tensor_canonize_bond, tensor_compress_bond
@@ -165,12 +167,25 @@ class BoundaryContractor2D:
     tensors : iterable of (array, inds, (i, j), layer)
         ``layer`` is a tag such as 'KET' / 'BRA' or None for flat networks.
     Lx, Ly : int
+    widen : bool
+        float32 / complex64 networks are held in double precision internally
+        (one conversion per input tensor).
     """
 
-    def __init__(self, tensors, Lx, Ly):
+    def __init__(self, tensors, Lx, Ly, widen=True):
         self.Lx, self.Ly = int(Lx), int(Ly)
         self.sites = {(i, j): [] for i in range(self.Lx) for j in range(self.Ly)}
         for data, inds, coo, layer in tensors:
+            data = ops.asarray(data)
+            if widen and data.dtype in (np.float32, np.complex64):
+                # single precision: widen ONCE here instead of around every
+                # contraction / factorisation (the fp64 engines would convert
+                # each operand and result on the fly: three extra HBM passes per
+                # step); the value is then at least as accurate as the
+                # reference's single-precision arithmetic
+                from .contract import _WIDE, convert
+                src = ops.materialize(data).t
+                data = Array(convert(src, _WIDE[src.dtype]))
             self.sites[tuple(coo)].append(LTensor(data, inds, layer))
         self.n_compress = 0
         self.max_bond_seen = 1
@@ -309,7 +324,8 @@ def contract_boundary(tensors, Lx, Ly, max_bond=None, **opts):
     """``TensorNetwork2D.contract_boundary`` for labelled device arrays; see
     :class:`BoundaryContractor2D`.  Returns a Python scalar for a closed
     network."""
-    return BoundaryContractor2D(tensors, Lx, Ly).contract_boundary(max_bond, **opts)
+    widen = opts.pop("widen", True)
+    return BoundaryContractor2D(tensors, Lx, Ly, widen=widen).contract_boundary(max_bond, **opts)
 
 
 def peps_norm_tensors(arrays, site_inds=None):
@@ -397,7 +413,7 @@ def contract_boundary_two_sided(tensors, Lx, Ly, max_bond=None, cutoff=1e-10,
     n_steps = max(L - 2, 0)
     n_min, n_max = (n_steps + 1) // 2, n_steps // 2
     tensors = list(tensors)
-    bc = BoundaryContractor2D(tensors, Lx, Ly)
+    bc = BoundaryContractor2D(tensors, Lx, Ly, widen=step_opts.pop("widen", True))
     other = (0, (Ly if plane == "x" else Lx) - 1)
 
     def run(side, count):
