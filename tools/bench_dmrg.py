@@ -26,6 +26,11 @@ def main():
     ap.add_argument("--chi", type=int, default=1024)
     ap.add_argument("--cpu-L", type=int, default=24)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--method", default="svd",
+                    help="bond_compress_method: svd | svd:eig | svd:rand")
+    ap.add_argument("--ncv", type=int, default=None, help="device_eig_ncv override")
+    ap.add_argument("--left-sweep", action="store_true",
+                    help="also time the following sweep_left(canonize=False)")
     ap.add_argument("--shard", action="store_true",
                     help="under torchrun: row-shard the local eigensolves over the ranks (NCCL)")
     args = ap.parse_args()
@@ -46,6 +51,11 @@ def main():
     out = {"L": args.L, "chi": args.chi, "dtype": "f64"}
     mpo = dm.mpo_heis(args.L)
     d = qb.DMRG2(mpo, args.chi, cutoffs=0.0, mpo_shape="lrdu", seed=2, shard=shard)
+    if args.ncv:
+        d.opts["device_eig_ncv"] = args.ncv
+    out["opts"] = {k: d.opts[k] for k in ("device_eig_ncv", "device_eig_min_steps",
+                                            "local_eig_tol")}
+    out["method"] = args.method
     if shard is not None:
         out["shard"] = {"world_size": shard.world_size, "backend": "nccl"}
     torch.cuda.synchronize()
@@ -61,9 +71,24 @@ def main():
     d._update_local_state_2site = timed
     n0 = qb.launch_count()
     t0 = time.perf_counter()
-    e = d.sweep_right(canonize=True, max_bond=args.chi, cutoff=0.0, cutoff_mode="sum2")
+    e = d.sweep_right(canonize=True, max_bond=args.chi, cutoff=0.0, cutoff_mode="sum2",
+                      method=args.method)
     torch.cuda.synchronize()
     t_sweep = time.perf_counter() - t0
+    if args.left_sweep:
+        n_first = len(site_t)
+        t1 = time.perf_counter()
+        e2 = d.sweep_left(canonize=False, max_bond=args.chi, cutoff=0.0, cutoff_mode="sum2",
+                          method=args.method)
+        torch.cuda.synchronize()
+        second = site_t[n_first:]
+        out["gpu_left_sweep"] = {
+            "sweep_s": time.perf_counter() - t1, "energy": e2,
+            "matvecs_per_site": float(np.mean([nmv for (_, _, nmv, _) in second])),
+            "s_per_site_full_chi": float(np.median([t for (_, t, _, k) in second
+                                                    if k == args.chi] or [0.0])),
+        }
+        site_t = site_t[:n_first]
     full = [t for (i, t, nmv, k) in site_t if k == args.chi]
     out["gpu"] = {
         "sweep_s": t_sweep, "energy": e, "launches": qb.launch_count() - n0,
