@@ -28,11 +28,24 @@ def main():
     ap.add_argument("--L", type=int, default=10)
     ap.add_argument("--chi", type=int, default=24)
     ap.add_argument("--dtype", default="float64")
+    ap.add_argument("--emulate", action="store_true",
+                    help="CPU tier: host layer on tests/abi_emulator.py (no device)")
     args = ap.parse_args()
     rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"])
-    local = 0 if args.same_gpu else int(os.environ.get("LOCAL_RANK", rank))
-    torch.cuda.set_device(local)
+    import contextlib
+    ctx = contextlib.nullcontext()
+    if args.emulate:
+        from tests.abi_emulator import emulated_abi
+        ctx = emulated_abi()
+    else:
+        local = 0 if args.same_gpu else int(os.environ.get("LOCAL_RANK", rank))
+        torch.cuda.set_device(local)
     dist.init_process_group(args.backend, rank=rank, world_size=world)
+    with ctx:
+        run(args, rank, world)
+
+
+def run(args, rank, world):
     import quimb_b200 as qb
     from quimb_b200.dist import BondShard
     from oracle import dmrg_np as dm
