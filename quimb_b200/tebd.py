@@ -350,3 +350,56 @@ class TEBD:
         for t in ts:
             self.update_to(t, dt=dt, tol=tol, order=order)
             yield self.pt
+
+
+# ------------------------------------------------------- MPS circuit driver ---
+def gate_single(sites, G, i):
+    """Apply a one-site gate G[out, in] to site i (MatrixProductState.gate with
+    contract=True, tn1d/core.py:2132-2217): one launch, isometries preserved
+    for unitary G."""
+    A = sites[i]
+    G = ops.asarray(G)
+    if A.dtype != G.dtype:
+        dt = np.result_type(A.dtype, G.dtype)
+        A, G = A.astype(dt, copy=False), G.astype(dt, copy=False)
+    sites[i] = Array(contract_pair(A.t, [0, 1, 2], G.t, [3, 1], [0, 3, 2],
+                                   conj_a=A.cj, conj_b=G.cj))
+
+
+def mps_zero_state(n, d=2, dtype="complex128"):
+    """|00...0> as bond-dimension-1 (l, p, r) site arrays on the device."""
+    out = []
+    for _ in range(n):
+        x = np.zeros((1, d, 1), dtype=dtype)
+        x[0, 0, 0] = 1.0
+        out.append(ops.asarray(x))
+    return out
+
+
+def apply_circuit(sites, gates, **compress_opts):
+    """Run a gate list on an MPS in place, the way quimb's ``CircuitMPS`` does
+    (quimb/tensor/circuit/mps.py): one-qubit gates are contracted into their
+    site, two-qubit gates go through ``gate_with_auto_swap`` (swap to
+    adjacency, canonicalise, contract + truncated split, swap back).
+
+    ``gates``: iterable of ``(G, (i,))`` or ``(G, (i, j))`` with ``G`` a
+    (2, 2) / (4, 4) or (2, 2, 2, 2) array, index order (out..., in...)."""
+    compress_opts.setdefault("cutoff", 1e-10)
+    for G, where in gates:
+        where = tuple(where)
+        if len(where) == 1:
+            gate_single(sites, G, where[0])
+        elif len(where) == 2:
+            gate_with_auto_swap(sites, G, where, **compress_opts)
+        else:
+            raise ValueError("apply_circuit: only one- and two-qubit gates")
+    return sites
+
+
+def mps_amplitude(sites, bits):
+    """<bits|psi>: the chain of selected (chi x chi) matrices, left to right."""
+    v = None
+    for A, b in zip(sites, bits):
+        M = Array(A.t[:, int(b), :], A.cj)
+        v = M if v is None else ops.tensordot(v, M, axes=((v.ndim - 1,), (0,)))
+    return v.reshape(()).item()
