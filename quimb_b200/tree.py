@@ -232,6 +232,99 @@ def _greedy_ssa(inputs, output, size_dict):
     return ssa
 
 
+def _greedy_heap_ssa(inputs, output, size_dict, costmod=1.0, temperature=0.0, rng=None):
+    """Heap-based greedy with optional Boltzmann (Gumbel) noise: the trial
+    generator of the 'random-greedy' strategy (the approach of opt_einsum's /
+    cotengra's RandomGreedy).  Pair score = size(result) - costmod * (size(a) +
+    size(b)), compared on a signed-log scale with noise ``temperature``."""
+    import heapq
+    inds = {i: frozenset(t) for i, t in enumerate(inputs)}
+    order = {i: tuple(t) for i, t in enumerate(inputs)}
+    where = {}
+    for i, t in inds.items():
+        for ix in t:
+            where.setdefault(ix, set()).add(i)
+    out_set = set(output)
+    log2 = math.log2
+
+    def lsize(t):
+        return sum(log2(size_dict[ix]) for ix in t)
+
+    def result(a, b):
+        keep = [ix for ix in dict.fromkeys(order[a] + order[b])
+                if ix in out_set or (where[ix] - {a, b})]
+        return tuple(keep)
+
+    def score(a, b):
+        res = result(a, b)
+        c = 2.0 ** lsize(res) - costmod * (2.0 ** lsize(inds[a]) + 2.0 ** lsize(inds[b]))
+        sc = math.copysign(math.log1p(abs(c)), c)
+        if temperature > 0.0:
+            u = rng.random()
+            sc -= temperature * (-math.log(-math.log(u + 1e-300) + 1e-300))
+        return sc
+
+    heap = []
+    seen = set()
+    for ix, ts in where.items():
+        tl = sorted(ts)
+        for x in range(len(tl)):
+            for y in range(x + 1, len(tl)):
+                key = (tl[x], tl[y])
+                if key not in seen:
+                    seen.add(key)
+                    heapq.heappush(heap, (score(*key), key[0], key[1]))
+    ssa, nxt = [], len(inputs)
+    while len(inds) > 1:
+        a = b = None
+        while heap:
+            _, x, y = heapq.heappop(heap)
+            if x in inds and y in inds:
+                a, b = x, y
+                break
+        if a is None:
+            # disconnected components: outer product of the two smallest
+            ks = sorted(inds, key=lambda k: (lsize(inds[k]), k))[:2]
+            a, b = ks
+        res = result(a, b)
+        ssa.append((a, b))
+        for k in (a, b):
+            for ix in inds[k]:
+                where[ix].discard(k)
+            del inds[k], order[k]
+        inds[nxt], order[nxt] = frozenset(res), res
+        nbrs = set()
+        for ix in res:
+            nbrs.update(where.setdefault(ix, set()))
+            where[ix].add(nxt)
+        for k in nbrs:
+            if k != nxt:
+                heapq.heappush(heap, (score(k, nxt), k, nxt))
+        nxt += 1
+    return ssa
+
+
+def _random_greedy_ssa(inputs, output, size_dict, trials=32, seed=0, minimize="flops"):
+    """Best of a deterministic greedy run and ``trials`` noisy ones (fixed
+    seed: reproducible), judged by total cost then width."""
+    import random
+    rng = random.Random(seed)
+    best = None
+    for t in range(trials + 1):
+        if t == 0:
+            ssa = _greedy_heap_ssa(inputs, output, size_dict)
+        else:
+            costmod = math.exp(rng.uniform(math.log(0.1), math.log(4.0)))
+            temp = math.exp(rng.uniform(math.log(1e-3), math.log(1.0)))
+            ssa = _greedy_heap_ssa(inputs, output, size_dict, costmod, temp, rng)
+        tr = Tree(inputs, output, size_dict, ssa)
+        key = ((tr.contraction_cost(), tr.contraction_width()) if minimize == "flops"
+               else (tr.contraction_width(), tr.contraction_cost()))
+        if best is None or key < best[0]:
+            best = (key, ssa)
+    return best[1]
+
+
 def _optimal_ssa(inputs, output, size_dict):
     """Exact minimum-flop tree by dynamic programming over subsets."""
     n = len(inputs)
@@ -297,9 +390,14 @@ def find_tree(inputs, output, size_dict, optimize="auto"):
     elif n <= 1:
         ssa = []
     elif optimize in ("optimal", "dp") or (
-            optimize in ("auto", "auto-hq", None) and n <= 9):
+            optimize in ("auto", "auto-hq", "random-greedy", None) and n <= 9):
         ssa = _optimal_ssa(inputs, output, size_dict)
-    elif optimize in ("greedy", "auto", "auto-hq", None):
+    elif optimize in ("random-greedy", "auto-hq"):
+        ssa = _random_greedy_ssa(inputs, output, size_dict,
+                                 trials=128 if optimize == "auto-hq" else 32)
+    elif optimize in ("auto", None):
+        ssa = _random_greedy_ssa(inputs, output, size_dict, trials=8)
+    elif optimize == "greedy":
         ssa = _greedy_ssa(inputs, output, size_dict)
     else:
         raise ValueError(f"unknown optimize strategy {optimize!r}")

@@ -186,3 +186,47 @@ def test_find_slices_reduces_width_and_partitions_the_sum():
         total += complex(cn.array_contract(sub, red, output, "greedy"))
     assert abs(total - amp) < 1e-10
     assert tree.find_slices(tr) == ((), 1, w0, tr.contraction_cost())
+
+
+def _run_tree_numpy(tr, arrays):
+    """Execute a quimb_b200 Tree with the oracle's pairwise numpy contraction."""
+    nodes = dict(enumerate(arrays))
+    inds = dict(enumerate(tr.inputs))
+    for i, j, k, res in tr.steps:
+        nodes[k] = cn.contract_pair(nodes.pop(i), inds[i], nodes.pop(j), inds[j], res)
+        inds[k] = res
+    (out,) = nodes.values()
+    return out
+
+
+def test_random_greedy_finder_is_valid_and_not_worse():
+    from tests.circuit_util import random_grid_circuit_amplitude, random_circuit_amplitude
+    for arrays, inputs, output, amp in (random_grid_circuit_amplitude(3, 3, 8, seed=2),
+                                        random_circuit_amplitude(9, 6, 4)):
+        sz = {ix: 2 for t in inputs for ix in t}
+        g = tree.find_tree(inputs, output, sz, "greedy")
+        r = tree.find_tree(inputs, output, sz, "random-greedy")
+        r2 = tree.find_tree(inputs, output, sz, "random-greedy")
+        assert r.steps == r2.steps                       # fixed seed: reproducible
+        assert len(r.steps) == len(arrays) - 1
+        assert r.contraction_cost() <= g.contraction_cost() * 1.5
+        val = complex(_run_tree_numpy(r, arrays))
+        assert abs(val - amp) < 1e-10
+    # larger grid: the noisy trials find a markedly cheaper tree than plain greedy
+    arrays, inputs, output, _ = random_grid_circuit_amplitude(4, 4, 12, dense=False)
+    sz = {ix: 2 for t in inputs for ix in t}
+    g = tree.find_tree(inputs, output, sz, "greedy")
+    r = tree.find_tree(inputs, output, sz, "random-greedy")
+    assert r.contraction_cost() <= g.contraction_cost()
+    # disconnected networks and open outputs
+    ins = [("a", "b"), ("b", "c"), ("x", "y"), ("y",)]
+    t = tree.find_tree(ins, ("a", "c", "x"), dict(a=2, b=3, c=4, x=5, y=6), "random-greedy")
+    rng = np.random.default_rng(0)
+    arrs = [rng.standard_normal((2, 3)), rng.standard_normal((3, 4)),
+            rng.standard_normal((5, 6)), rng.standard_normal(6)]
+    if len(ins) > 9:
+        pass
+    ref = np.einsum("ab,bc,xy,y->acx", *arrs)
+    t = tree.Tree(ins, ("a", "c", "x"), dict(a=2, b=3, c=4, x=5, y=6),
+                  tree._greedy_heap_ssa(ins, ("a", "c", "x"), dict(a=2, b=3, c=4, x=5, y=6)))
+    np.testing.assert_allclose(_run_tree_numpy(t, arrs), ref, atol=1e-12)
