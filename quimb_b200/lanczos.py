@@ -14,11 +14,14 @@ process lives on the device here:
     kernels (``qb_multi_dot`` : h = V w,  ``qb_multi_axpy`` : w -= V^T h);
   * the images ``W_j = H v_j`` are kept, so the projected matrix
     ``V H V^T`` is one skinny contraction;
-  * one small device->host read per step (the new column of the projected
-    matrix and beta_{j+1}: <= 65 doubles) so the Ritz value and the Lanczos
-    residual estimate are monitored after every matvec, plus the true residual
-    norm |H x - theta x| once per cycle; the tiny dense eigenproblem is host
-    control logic, as in ARPACK.
+  * the projected matrix is assembled on the host from the Gram-Schmidt
+    coefficients (small device->host reads of <= 65 doubles per step), so the
+    Ritz value and the Lanczos residual estimate are monitored as the basis
+    grows and a solve stops the moment it has converged; while the estimate is
+    still far above the threshold up to two steps are queued before the next
+    read, so the device is not idle while the host decides.  The true residual
+    norm |H x - theta x| is checked once per cycle; the tiny dense
+    eigenproblem is host control logic, as in ARPACK.
 
 Convergence test as in ARPACK's dsaupd: ``resid <= tol * max(eps^(2/3),
 |theta|)``.  The basis size ``ncv`` is a free parameter of the device solver:
@@ -29,6 +32,7 @@ driving the device matvec).
 """
 
 import ctypes
+import math
 
 import numpy as np
 import torch
@@ -166,7 +170,9 @@ def eigh_lanczos(matvec, v0, which="SA", ncv=4, tol=1e-3, maxiter=None,
     x = Array(V[0])
     mmax = m
     min_steps = min(int(min_steps), n)
-    col = torch.zeros((_NCV_MAX + 1,), dtype=dt, device=dev)
+    colbuf = torch.zeros((mmax, _NCV_MAX + 1), dtype=dt, device=dev)
+    betas = np.zeros(mmax)
+    info["host_reads"] = 0
     # thick restart: the k lowest Ritz vectors (and their known images) are
     # kept, followed by the last residual direction -- close to unrestarted
     # Lanczos in matvecs at a bounded basis (Wu & Simon's TRLan scheme)
@@ -184,27 +190,60 @@ def eigh_lanczos(matvec, v0, which="SA", ncv=4, tol=1e-3, maxiter=None,
         # paying for restarts it does not need.
         m = mmax
         meff = m
+        pending = jstart          # first projected-matrix column not yet on the host
+        skip = 0
+        est_prev = None
         for j in range(jstart, m):
             Wj = matvec(Array(V[j]))
             nmv += 1
             W[j].copy_(ops.materialize(Wj).t.reshape(-1))
             w.copy_(W[j])
-            _orthogonalise(V, j, w, h, comm, keep=col)
+            _orthogonalise(V, j, w, h, comm, keep=colbuf[j])
             bnorm = _norm_c(Array(w), comm)
-            col[j + 1].copy_(bnorm.t)
-            c = col[:j + 2].cpu().numpy()
-            Hh[:j + 1, j] = c[:j + 1]
-            Hh[j, :j + 1] = c[:j + 1]
-            beta = float(c[j + 1])
+            colbuf[j, j + 1].copy_(bnorm.t)
+            if skip > 0 and j + 1 < m:
+                # far from convergence (see below): keep the device busy, the
+                # columns of these steps are read together with the next one
+                skip -= 1
+                V[j + 1].copy_(w)
+                ops.scale_(Array(V[j + 1]), 1.0, div_by=bnorm)
+                continue
+            rows = colbuf[pending:j + 1, :j + 2].cpu().numpy()
+            info["host_reads"] += 1
+            for jj in range(pending, j + 1):
+                c = rows[jj - pending]
+                Hh[:jj + 1, jj] = c[:jj + 1]
+                Hh[jj, :jj + 1] = c[:jj + 1]
+                betas[jj] = c[jj + 1]
+            if pending < j and j >= 1:
+                # residual estimate of the previous step, for the rate below
+                ev, evc = np.linalg.eigh(sign * Hh[:j, :j])
+                est_prev = abs(betas[j - 1] * evc[-1, 0])
+            pending = j + 1
+            beta = float(betas[j])
             evals, evecs = np.linalg.eigh(sign * Hh[:j + 1, :j + 1])
             theta = sign * evals[0]
             y = evecs[:, 0]
             est = abs(beta * y[-1])
-            conv = est <= tol * max(eps23, abs(theta)) and nmv >= min_steps
+            thresh = tol * max(eps23, abs(theta))
+            conv = est <= thresh and nmv >= min_steps
             if (conv or j + 1 == m or not np.isfinite(est)
                     or beta <= 1e-14 * max(1.0, abs(theta))):
                 meff = j + 1
                 break
+            # How many steps can run before the next look?  With the observed
+            # contraction rate r the estimate reaches 10 x the threshold after
+            # log(est / 10 thresh) / log(1 / r) steps; never more than 2 ahead
+            # (Lanczos converges superlinearly), never while a decision --
+            # convergence or breakdown -- could be near.
+            skip = 0
+            if est > 10.0 * thresh:
+                r = 0.3 if not est_prev or est_prev <= est else max(est / est_prev, 0.05)
+                if r < 1.0:
+                    skip = int(min(2, math.log(est / (10.0 * thresh)) / -math.log(r)))
+                if nmv + skip + 1 < min_steps:
+                    skip = max(skip, min(2, min_steps - nmv - 2))
+            est_prev = est
             V[j + 1].copy_(w)
             ops.scale_(Array(V[j + 1]), 1.0, div_by=bnorm)
         m = meff
