@@ -230,3 +230,67 @@ def test_random_greedy_finder_is_valid_and_not_worse():
     t = tree.Tree(ins, ("a", "c", "x"), dict(a=2, b=3, c=4, x=5, y=6),
                   tree._greedy_heap_ssa(ins, ("a", "c", "x"), dict(a=2, b=3, c=4, x=5, y=6)))
     np.testing.assert_allclose(_run_tree_numpy(t, arrs), ref, atol=1e-12)
+
+
+def test_planner_randomised_signatures():
+    """The C++ planner (host code of the product) on 300 random signatures:
+    batch / contracted / free / summed-out labels, size-1 modes, permuted and
+    padded strides.  M, N, K and batch must equal the products the einsum
+    semantics define; invalid signatures must be rejected, not planned."""
+    rng = np.random.default_rng(7)
+    letters = list(range(12))
+    n_ok = 0
+    for trial in range(300):
+        sizes = {l: int(rng.choice([1, 2, 3, 4, 5, 7])) for l in letters}
+        ra, rb = int(rng.integers(0, 5)), int(rng.integers(0, 5))
+        la = [int(x) for x in rng.choice(letters, size=ra, replace=False)]
+        lb = [int(x) for x in rng.choice(letters, size=rb, replace=False)]
+        cand = list(dict.fromkeys(la + lb))
+        keep = [l for l in cand if rng.random() < 0.6]
+        lc = [int(x) for x in rng.permutation(keep)] if keep else []
+
+        def shape_strides(ls, pad):
+            shape = [sizes[l] for l in ls]
+            order = list(rng.permutation(len(ls)))        # arbitrary memory order
+            st, acc = [0] * len(ls), 1
+            for ax in order:
+                st[ax] = acc
+                acc *= shape[ax] + (pad if rng.random() < 0.3 else 0)
+            return shape, st
+        sa, sta = shape_strides(la, 1)
+        sb, stb = shape_strides(lb, 2)
+        sc, stc = shape_strides(lc, 0)
+        plan = qb.plan_pair(sa, sta, la, sb, stb, lb, sc, stc, lc)
+        inA, inB, inC = set(la), set(lb), set(lc)
+        prod = lambda ls: int(np.prod([sizes[l] for l in ls])) if ls else 1  # noqa: E731
+        batch = [l for l in cand if l in inA and l in inB and l in inC]
+        m = [l for l in cand if l in inA and l not in inB and l in inC]
+        n = [l for l in cand if l in inB and l not in inA and l in inC]
+        k = [l for l in cand if l not in inC]
+        assert plan["batch"] == prod(batch), (la, lb, lc)
+        assert plan["M"] == prod(m), (la, lb, lc)
+        assert plan["N"] == prod(n), (la, lb, lc)
+        assert plan["K"] == prod(k), (la, lb, lc)
+        n_ok += 1
+    assert n_ok == 300
+    # a label of C that is in neither input / mismatched extents are rejected
+    with pytest.raises(ValueError):
+        qb.plan_pair([2, 3], [3, 1], [0, 1], [3, 4], [4, 1], [1, 2], [2, 5], [5, 1], [0, 9])
+    with pytest.raises(ValueError):
+        qb.plan_pair([2, 3], [3, 1], [0, 1], [4, 4], [4, 1], [1, 2], [2, 4], [4, 1], [0, 2])
+
+
+def test_planner_diagonal_and_summed_labels():
+    # trace-like: A[i, i, j] B[j, k] -> C[i, k]: the repeated label is ONE mode
+    plan = qb.plan_pair([4, 4, 3], [12, 3, 1], [0, 0, 1], [3, 5], [5, 1], [1, 2],
+                        [4, 5], [5, 1], [0, 2])
+    assert (plan["M"], plan["N"], plan["K"], plan["batch"]) == (4, 5, 3, 1)
+    # full trace against a scalar operand
+    plan = qb.plan_pair([6, 6], [6, 1], [0, 0], [], [], [], [], [], [])
+    assert plan["M"] * plan["N"] * plan["batch"] == 1 and plan["K"] == 6
+    # label only in A and not in C: summed over
+    plan = qb.plan_pair([3, 7], [7, 1], [0, 1], [3, 2], [2, 1], [0, 2], [2], [1], [2])
+    assert plan["K"] == 21 and plan["N"] == 2 and plan["M"] == 1
+    # repeated label with different extents is an error
+    with pytest.raises(ValueError):
+        qb.plan_pair([4, 5], [5, 1], [0, 0], [], [], [], [4], [1], [0])
