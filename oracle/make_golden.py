@@ -450,6 +450,40 @@ def tebd_cases():
     json.dump(meta, open(os.path.join(OUT, "tebd.json"), "w"), indent=1)
 
 
+def mps_ops_cases():
+    """MPS compression / addition / MPO application / overlap of the reference."""
+    store, meta = {}, {}
+    p = qtn.MPS_rand_state(7, 6, seed=31, dtype="complex128")
+    q = qtn.MPS_rand_state(7, 3, seed=32, dtype="float64")
+    H = qtn.MPO_ham_heis(7)
+    for i in range(7):
+        store[f"p__{i}"] = np.asarray(p[i].data)
+        store[f"q__{i}"] = np.asarray(q[i].data)
+        store[f"H__{i}"] = np.asarray(H[i].data)
+    meta["p_inds"] = [list(map(str, p[i].inds)) for i in range(7)]
+    meta["H_inds"] = [list(map(str, H[i].inds)) for i in range(7)]
+    meta["overlap_pq"] = [float(np.real(p.H @ q)), float(np.imag(p.H @ q))]
+    store["p_dense"] = np.asarray(p.to_dense()).reshape(-1)
+    store["add_dense"] = np.asarray((p + q).to_dense()).reshape(-1)
+    Hp = H.apply(p)
+    store["Hp_dense"] = np.asarray(Hp.to_dense()).reshape(-1)
+    meta["Hp_bonds"] = [int(Hp.bond_size(i, i + 1)) for i in range(6)]
+    cases = []
+    for kw in [dict(form="right", max_bond=3, cutoff=0.0), dict(form="left", max_bond=3, cutoff=0.0),
+               dict(form=2, max_bond=4, cutoff=0.0), dict(form=5, cutoff=1e-2),
+               dict(form="flat", max_bond=3, cutoff=0.0), dict(cutoff=1e-1, cutoff_mode="rel"),
+               dict(form="left", max_bond=2, cutoff=0.0, method="svd:eig")]:
+        c = Hp.copy()
+        c.compress(**kw)
+        key = f"cmp__{len(cases)}"
+        store[key + "__dense"] = np.asarray(c.to_dense()).reshape(-1)
+        cases.append({"key": key, "kw": kw,
+                      "bonds": [int(c.bond_size(i, i + 1)) for i in range(6)]})
+    meta["compress"] = cases
+    np.savez_compressed(os.path.join(OUT, "mps_ops.npz"), **store)
+    json.dump(meta, open(os.path.join(OUT, "mps_ops.json"), "w"), indent=1)
+
+
 def mps_dmrg_cases():
     store, meta = {}, {}
     # Heisenberg MPO of the reference, as arrays (lrud layout) + dense check
@@ -507,7 +541,7 @@ def mps_dmrg_cases():
 
 if __name__ == "__main__":
     only = set(sys.argv[1:])
-    for fn in (contract_cases, decomp_cases, decomp2_cases, boundary_cases, tebd_cases,
+    for fn in (contract_cases, decomp_cases, decomp2_cases, boundary_cases, tebd_cases, mps_ops_cases,
                mps_dmrg_cases):
         if not only or fn.__name__ in only:
             fn()

@@ -105,7 +105,17 @@ def qr(x, stabilized=False, want_q=True, want_r=True):
     m, n = x.shape
     k = min(m, n)
     if x.t.dtype == torch.complex128:
-        Qe, Re = qr(Array(_embed(x)), stabilized=True, want_q=want_q, want_r=want_r)
+        Qe, Re = qr(Array(_embed(x)), stabilized=True, want_q=want_q, want_r=True)
+        # The real QR of the embedding is the embedding of the complex QR only
+        # through uniqueness, i.e. for full column rank; its deviation from the
+        # embedded structure grows like eps * cond(x).  The diagonal of R
+        # (k doubles, one host read) tells: ill-conditioned or rank-deficient
+        # input (redundant MPS bonds, products of thin factors, ...) takes the
+        # SVD route, which is accurate there.
+        d = Re.t.diagonal()[0:2 * k:2].abs()
+        dh = d.cpu().numpy() if k else np.ones(1)
+        if dh.size and dh.min() <= _QR_COMPLEX_COND * dh.max():
+            return _qr_complex_via_svd(x, want_q, want_r)
         Q = Array(_extract(Qe.t, m, k, 2)) if want_q else None
         R = Array(_extract(Re.t, k, n, 2)) if want_r else None
         return Q, R
@@ -164,6 +174,25 @@ def _tsqr(x, stabilized, want_q, want_r):
         blk = ops.tensordot(q, Array(q2.t[b * n:(b + 1) * n]), axes=((1,), (0,)))
         Q[lo:lo + q.shape[0]] = blk.t
     return Array(Q), r
+
+
+# relative size of the smallest diagonal entry of R below which the complex
+# QR leaves the embedding route (structure error ~ eps / this value)
+_QR_COMPLEX_COND = 1e-4
+
+
+def _qr_complex_via_svd(x, want_q, want_r):
+    """x = Q R for (numerically) rank-deficient or ill-conditioned complex x:
+    Q = U (a complete isometry: the Jacobi kernel accumulates U as a product of
+    rotations, also across zero singular values), R = diag(s) V^H.  R is then
+    not triangular -- the factorisation is not unique in this regime and no
+    caller on the path needs triangularity (canonisation only needs x = Q R
+    with isometric Q); for well-conditioned input the embedding route returns
+    the unique stabilised QR."""
+    from .split import _ldmul
+    U, s, VH = svd(x)
+    R = Array(_ldmul(s.t, ops.materialize(VH, force=True).t)) if want_r else None
+    return (U if want_q else None), R
 
 
 def _select_complex_pairs(s_host, gram_fn):

@@ -403,3 +403,139 @@ def mps_amplitude(sites, bits):
         M = Array(A.t[:, int(b), :], A.cj)
         v = M if v is None else ops.tensordot(v, M, axes=((v.ndim - 1,), (0,)))
     return v.reshape(()).item()
+
+
+# ------------------------------------------------------ MPS compression etc. ---
+def left_compress_site(sites, i, **compress_opts):
+    """Truncate the bond (i, i+1) leaving site i left-isometric
+    (tn1d/core.py:1194-1224: tensor_compress_bond with absorb='right',
+    reduced='left'), in place."""
+    from .split import tensor_compress_bond
+    set_default_compress_mode(compress_opts)
+    compress_opts.setdefault("absorb", "right")
+    compress_opts.setdefault("reduced", "left")
+    sites[i], sites[i + 1] = tensor_compress_bond(
+        sites[i], ("l", "p", "x"), sites[i + 1], ("x", "q", "r"), **compress_opts)
+
+
+def right_compress_site(sites, i, **compress_opts):
+    """Truncate the bond (i-1, i) leaving site i right-isometric
+    (tn1d/core.py:1226-1256), in place."""
+    from .split import tensor_compress_bond
+    set_default_compress_mode(compress_opts)
+    compress_opts.setdefault("absorb", "left")
+    compress_opts.setdefault("reduced", "right")
+    sites[i - 1], sites[i] = tensor_compress_bond(
+        sites[i - 1], ("l", "p", "x"), sites[i], ("x", "q", "r"), **compress_opts)
+
+
+def left_compress(sites, start=None, stop=None, **compress_opts):
+    start = 0 if start is None else start
+    stop = len(sites) - 1 if stop is None else stop
+    for i in range(start, stop):
+        left_compress_site(sites, i, **compress_opts)
+
+
+def right_compress(sites, start=None, stop=None, **compress_opts):
+    start = len(sites) - 1 if start is None else start
+    stop = 0 if stop is None else stop
+    for i in range(start, stop, -1):
+        right_compress_site(sites, i, **compress_opts)
+
+
+def mps_compress(sites, form=None, **compress_opts):
+    """``MatrixProductState.compress`` (tn1d/core.py:1330-1390): canonise one
+    way, sweep truncated SVDs back the other way.  ``form``: 'right' (default,
+    centre at site 0), 'left', an integer centre, or 'flat'."""
+    import numbers
+    n = len(sites)
+    if form is None:
+        form = "right"
+    if isinstance(form, numbers.Integral):
+        if form < n // 2:
+            left_canonize(sites)
+            right_compress(sites, **compress_opts)
+            left_canonize(sites, stop=form)
+        else:
+            right_canonize(sites)
+            left_compress(sites, **compress_opts)
+            right_canonize(sites, stop=form)
+    elif form == "left":
+        right_canonize(sites)
+        left_compress(sites, **compress_opts)
+    elif form == "right":
+        left_canonize(sites)
+        right_compress(sites, **compress_opts)
+    elif form == "flat":
+        compress_opts["absorb"] = "both"
+        right_compress(sites, stop=n // 2, **compress_opts)
+        left_compress(sites, stop=n // 2, **compress_opts)
+    else:
+        raise ValueError(f"Form specifier {form} not understood, should be either "
+                         "'left', 'right', 'flat' or an int specifiying a new orthog "
+                         "center.")
+    return sites
+
+
+def mps_overlap(bra, ket):
+    """<bra|ket> of two (l, p, r) MPS with matching physical dimensions: two
+    launches per site, the bra conjugated on load."""
+    E = None
+    for A, B in zip(bra, ket):
+        if E is None:
+            E = ops.ones((A.shape[0], B.shape[0]), dtype=np.result_type(A.dtype, B.dtype),
+                         device=B.device)
+        if A.dtype != B.dtype or E.dtype != B.dtype:
+            dt = np.result_type(A.dtype, B.dtype, E.dtype)
+            A, B, E = A.astype(dt, copy=False), B.astype(dt, copy=False), E.astype(dt, copy=False)
+        T = contract_pair(E.t, [0, 1], B.t, [1, 2, 3], [0, 2, 3], conj_a=E.cj, conj_b=B.cj)
+        E = Array(contract_pair(A.t, [0, 2, 4], T, [0, 2, 3], [4, 3], conj_a=not A.cj))
+    return E.reshape(()).item()
+
+
+def mps_add(a, b):
+    """|a> + |b> as an MPS with bond dimensions added (block-diagonal bonds;
+    MatrixProductState.add_MPS, tn1d/core.py): pure data placement."""
+    import torch
+    n = len(a)
+    out = []
+    for i, (x, y) in enumerate(zip(a, b)):
+        xt, yt = x.resolve(), y.resolve()
+        if xt.dtype != yt.dtype:
+            dt = torch.promote_types(xt.dtype, yt.dtype)
+            xt, yt = xt.to(dt), yt.to(dt)
+        if n == 1:
+            out.append(Array(xt + yt))
+        elif i == 0:
+            out.append(Array(torch.cat([xt, yt], dim=2)))          # row vector of blocks
+        elif i == n - 1:
+            out.append(Array(torch.cat([xt, yt], dim=0)))          # column vector
+        else:
+            (l1, d, r1), (l2, _, r2) = xt.shape, yt.shape
+            z = torch.zeros((l1 + l2, d, r1 + r2), dtype=xt.dtype, device=xt.device)
+            z[:l1, :, :r1] = xt
+            z[l1:, :, r1:] = yt
+            out.append(Array(z))
+    return out
+
+
+def mpo_apply(mpo, sites, mpo_shape="lrud", compress=False, **compress_opts):
+    """H|psi> as an MPS: new_site[(l, wl), d, (r, wr)] = sum_u A[l, u, r]
+    W[wl, wr, u, d] (one launch per site; bond dimensions multiply), optionally
+    followed by :func:`mps_compress` (MatrixProductOperator.apply,
+    tn1d/core.py)."""
+    from .mps import mpo_lrud
+    n = len(sites)
+    out = []
+    for i, A in enumerate(sites):
+        W = mpo_lrud(mpo[i], mpo_shape, i, n)
+        if W.dtype != A.dtype:
+            dt = np.result_type(W.dtype, A.dtype)
+            W, A = W.astype(dt, copy=False), A.astype(dt, copy=False)
+        T = Array(contract_pair(A.t, [0, 1, 2], W.t, [3, 4, 1, 5], [0, 3, 5, 2, 4],
+                                conj_a=A.cj, conj_b=W.cj))
+        l, wl, d, r, wr = T.shape
+        out.append(T.reshape(l * wl, d, r * wr))
+    if compress:
+        mps_compress(out, **compress_opts)
+    return out

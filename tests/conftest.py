@@ -64,3 +64,8 @@ def golden_boundary():
 @pytest.fixture(scope="session")
 def golden_tebd():
     return load_golden("tebd")
+
+
+@pytest.fixture(scope="session")
+def golden_mps_ops():
+    return load_golden("mps_ops")

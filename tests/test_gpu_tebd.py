@@ -146,3 +146,35 @@ def test_mps_circuit_simulation_matches_statevector():
     assert max(a.shape[2] for a in s2) <= 4
     ov = abs(np.vdot(psi.reshape(-1), _dense(s2)))
     assert 0.3 < ov <= 1.0 + 1e-12
+
+
+def test_mps_compress_add_apply_overlap_match_reference(golden_mps_ops):
+    """MatrixProductState.compress (all forms) / add_MPS / MPO.apply / overlap
+    of the reference (tests/golden/mps_ops.*): dense states and bond dims."""
+    data, meta = golden_mps_ops
+    n = 7
+    p = _fresh([data[f"p__{i}"] for i in range(n)])
+    q = _fresh([data[f"q__{i}"] for i in range(n)])
+    H = [data[f"H__{i}"] for i in range(n)]
+    np.testing.assert_allclose(_dense(p), data["p_dense"], atol=1e-13)
+    ov = tb.mps_overlap(p, q)
+    assert abs(ov - complex(*meta["overlap_pq"])) < 1e-12
+    np.testing.assert_allclose(_dense(tb.mps_add(p, q)), data["add_dense"], atol=1e-12)
+    Hp = tb.mpo_apply(H, p, mpo_shape="lrud")
+    assert [a.shape[2] for a in Hp[:-1]] == meta["Hp_bonds"]
+    np.testing.assert_allclose(_dense(Hp), data["Hp_dense"], atol=1e-12)
+    for c in meta["compress"]:
+        s = [a.copy() for a in Hp]
+        tb.mps_compress(s, **c["kw"])
+        assert [a.shape[2] for a in s[:-1]] == c["bonds"], c
+        tol = 1e-7 if c["kw"].get("method") == "svd:eig" else 1e-10
+        np.testing.assert_allclose(_dense(s), data[c["key"] + "__dense"], atol=tol,
+                                   err_msg=str(c))
+    # canonical forms: 'right' leaves every site but the first right-isometric
+    s = [a.copy() for a in Hp]
+    tb.mps_compress(s, form="right", max_bond=5, cutoff=0.0)
+    for a in s[1:]:
+        m = a.to_numpy().reshape(a.shape[0], -1)
+        np.testing.assert_allclose(m @ m.conj().T, np.eye(m.shape[0]), atol=1e-11)
+    with pytest.raises(ValueError):
+        tb.mps_compress(s, form="up")
