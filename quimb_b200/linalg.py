@@ -218,18 +218,22 @@ def _select_complex_pairs(s_host, gram_fn):
             sel.append(i)
         else:
             G = gram_fn(i, j)  # complex Gram of the candidates, host (size x size)
+            # d independent candidates by pivoted Cholesky of the Gram matrix
+            # (always the candidate with the largest remaining component: the
+            # 2d candidates span exactly a d-dimensional complex space)
+            resid = np.real(np.diag(G)).copy()
+            Lc = np.zeros((size, d), dtype=G.dtype)
             chosen = []
-            for c in range(size):
-                if len(chosen) == d:
+            for t in range(d):
+                c = int(np.argmax(resid))
+                if resid[c] <= 1e-12:
                     break
-                if chosen:
-                    gs = G[np.ix_(chosen, [c])]
-                    GS = G[np.ix_(chosen, chosen)]
-                    res = (G[c, c] - (gs.conj().T @ np.linalg.solve(GS, gs))[0, 0]).real
-                else:
-                    res = G[c, c].real
-                if res > 0.25:
-                    chosen.append(c)
+                chosen.append(c)
+                col = G[:, c] - Lc[:, :t] @ Lc[c, :t].conj()
+                Lc[:, t] = col / np.sqrt(resid[c])
+                resid = resid - np.abs(Lc[:, t]) ** 2
+                resid[chosen] = -1.0
+            chosen.sort()
             Gs = G[np.ix_(chosen, chosen)]
             T = np.linalg.inv(np.linalg.cholesky(Gs)).conj().T
             blocks.append((len(sel), len(chosen), T))

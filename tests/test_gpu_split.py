@@ -246,11 +246,13 @@ def test_complex_qr_rank_deficient(m, n, r):
     l, rt = _np(left), _np(right)
     np.testing.assert_allclose(l @ rt, x, atol=1e-11 * scale)
     np.testing.assert_allclose(rt @ rt.conj().T, np.eye(k), atol=1e-11)
-    # ill-conditioned but full rank (cond 1e8): still an accurate isometry
+    # ill-conditioned but full rank (cond 1e8): still an isometry (to the
+    # accuracy of the singular subspaces of the tiniest values: 1e-8 covers a
+    # LAPACK-grade SVD; the Jacobi kernel is relatively accurate and far better)
     u, _ = np.linalg.qr(rng.standard_normal((m, k)) + 1j * rng.standard_normal((m, k)))
     v, _ = np.linalg.qr(rng.standard_normal((n, k)) + 1j * rng.standard_normal((n, k)))
     y = (u * np.logspace(0, -8, k)) @ v.conj().T
     Q, R = qb.linalg.qr(qb.asarray(y), stabilized=True)
     q, rr = _np(Q), _np(R)
-    np.testing.assert_allclose(q.conj().T @ q, np.eye(k), atol=1e-11)
+    np.testing.assert_allclose(q.conj().T @ q, np.eye(k), atol=1e-8)
     np.testing.assert_allclose(q @ rr, y, atol=1e-12)
