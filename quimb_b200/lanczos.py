@@ -69,6 +69,13 @@ def _norm_c(x, comm):
 _MD_MAX = 16        # rows per call of the fused Krylov kernels (csrc: MD_MAX)
 
 
+def _safe(nrm):
+    """Divisor for a normalisation queued before the host has seen the norm:
+    an exact Krylov breakdown (norm 0: the vector is exactly zero) must give
+    a zero vector, not NaNs; the host drops everything behind that step."""
+    return Array(torch.clamp_min(nrm.t, 1e-300))
+
+
 def _combine(V, m, coeffs, out, alpha=1.0):
     """out += alpha * sum_j coeffs[j] V[j]  (j < m), 16 basis rows per launch."""
     lib = _lib.load()
@@ -192,7 +199,7 @@ def eigh_lanczos(matvec, v0, which="SA", ncv=4, tol=1e-3, maxiter=None,
         meff = m
         pending = jstart          # first projected-matrix column not yet on the host
         skip = 0
-        est_prev = None
+        est_prev = est = None
         for j in range(jstart, m):
             Wj = matvec(Array(V[j]))
             nmv += 1
@@ -206,30 +213,37 @@ def eigh_lanczos(matvec, v0, which="SA", ncv=4, tol=1e-3, maxiter=None,
                 # columns of these steps are read together with the next one
                 skip -= 1
                 V[j + 1].copy_(w)
-                ops.scale_(Array(V[j + 1]), 1.0, div_by=bnorm)
+                ops.scale_(Array(V[j + 1]), 1.0, div_by=_safe(bnorm))
                 continue
             rows = colbuf[pending:j + 1, :j + 2].cpu().numpy()
             info["host_reads"] += 1
+            # the steps read now are examined in order: the first one that has
+            # converged, broken down (invariant subspace: beta = 0) or filled
+            # the basis ends the cycle -- steps queued behind it are dropped
+            hit = None
             for jj in range(pending, j + 1):
                 c = rows[jj - pending]
                 Hh[:jj + 1, jj] = c[:jj + 1]
                 Hh[jj, :jj + 1] = c[:jj + 1]
-                betas[jj] = c[jj + 1]
-            if pending < j and j >= 1:
-                # residual estimate of the previous step, for the rate below
-                ev, evc = np.linalg.eigh(sign * Hh[:j, :j])
-                est_prev = abs(betas[j - 1] * evc[-1, 0])
+                betas[jj] = beta = float(c[jj + 1])
+                evals, evecs = np.linalg.eigh(sign * Hh[:jj + 1, :jj + 1])
+                theta = sign * evals[0]
+                y = evecs[:, 0]
+                est_prev, est = est, abs(beta * y[-1])
+                thresh = tol * max(eps23, abs(theta))
+                conv = est <= thresh and nmv - (j - jj) >= min_steps
+                if (conv or jj + 1 == m or not np.isfinite(est)
+                        or beta <= 1e-14 * max(1.0, abs(theta))):
+                    hit = jj
+                    break
             pending = j + 1
-            beta = float(betas[j])
-            evals, evecs = np.linalg.eigh(sign * Hh[:j + 1, :j + 1])
-            theta = sign * evals[0]
-            y = evecs[:, 0]
-            est = abs(beta * y[-1])
-            thresh = tol * max(eps23, abs(theta))
-            conv = est <= thresh and nmv >= min_steps
-            if (conv or j + 1 == m or not np.isfinite(est)
-                    or beta <= 1e-14 * max(1.0, abs(theta))):
-                meff = j + 1
+            if hit is not None:
+                meff = hit + 1
+                if hit < j:
+                    # restore the residual direction of step `hit` for the
+                    # restart: w of that step was overwritten by later ones
+                    w.copy_(V[hit + 1])
+                    bnorm = Array(torch.ones((), dtype=dt, device=dev))
                 break
             # How many steps can run before the next look?  With the observed
             # contraction rate r the estimate reaches 10 x the threshold after
@@ -243,9 +257,8 @@ def eigh_lanczos(matvec, v0, which="SA", ncv=4, tol=1e-3, maxiter=None,
                     skip = int(min(2, math.log(est / (10.0 * thresh)) / -math.log(r)))
                 if nmv + skip + 1 < min_steps:
                     skip = max(skip, min(2, min_steps - nmv - 2))
-            est_prev = est
             V[j + 1].copy_(w)
-            ops.scale_(Array(V[j + 1]), 1.0, div_by=bnorm)
+            ops.scale_(Array(V[j + 1]), 1.0, div_by=_safe(bnorm))
         m = meff
 
         def ritz(yvec, out_v, out_w):

@@ -178,3 +178,26 @@ def test_mps_compress_add_apply_overlap_match_reference(golden_mps_ops):
         np.testing.assert_allclose(m @ m.conj().T, np.eye(m.shape[0]), atol=1e-11)
     with pytest.raises(ValueError):
         tb.mps_compress(s, form="up")
+
+
+def test_compress_and_canonize_complex_mps_with_redundant_bonds():
+    """Zero-padded (rank-deficient) complex bonds: canonisation keeps the
+    state and compression finds the true bond dimensions (the complex QR takes
+    its SVD route on such input)."""
+    a = dm.mps_rand(6, 3, seed=5, dtype="complex128")
+    pad = []
+    for i, x in enumerate(a):
+        l, d, r = x.shape
+        y = np.zeros((l if i == 0 else l + 4, d, r if i == 5 else r + 4), dtype=complex)
+        y[:l, :, :r] = x
+        pad.append(y)
+    ref = dm.mps_to_dense(a).reshape(-1)
+    true_bonds = [x.shape[2] for x in a]
+    for form in ("right", "left", 3, "flat"):
+        s = [qb.asarray(x) for x in pad]
+        tb.mps_compress(s, form=form, cutoff=1e-12)
+        np.testing.assert_allclose(_dense(s), ref, atol=1e-12)
+        assert [x.shape[2] for x in s] == true_bonds
+    s = [qb.asarray(x) for x in pad]
+    tb.canonicalize(s, 2)
+    np.testing.assert_allclose(_dense(s), ref, atol=1e-12)
