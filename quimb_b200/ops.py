@@ -256,12 +256,41 @@ def matmul(a, b):
         if a.ndim == 0 or b.ndim == 0:
             raise ValueError("matmul: scalar operands")
         return tensordot(a, b, axes=((a.ndim - 1,), (0,)))
-    # broadcast batched matmul via einsum labels
-    nb = max(a.ndim, b.ndim) - 2
+    # broadcast batched matmul via einsum labels (numpy.matmul semantics:
+    # 1-d operands are promoted, size-1 batch dims broadcast)
+    if a.dtype != b.dtype:
+        dt = np.result_type(a.dtype, b.dtype)
+        a, b = a.astype(dt, copy=False), b.astype(dt, copy=False)
+    vec_a, vec_b = a.ndim == 1, b.ndim == 1
+    if vec_a:
+        a = expand_dims(a, 0)
+    if vec_b:
+        b = expand_dims(b, b.ndim)
+    nb = builtins.max(a.ndim, b.ndim) - 2
     la = list(range(nb - (a.ndim - 2), nb)) + [100, 101]
     lb = list(range(nb - (b.ndim - 2), nb)) + [101, 102]
     lc = list(range(nb)) + [100, 102]
-    return Array(contract_pair(a.t, la, b.t, lb, lc, conj_a=a.cj, conj_b=b.cj))
+    # a size-1 batch dim facing a larger one is summed over (extent 1) under a
+    # private label instead of being a batch label: that is the broadcast
+    fresh = 200
+    for pos in range(nb):
+        ia, ib = pos - (nb - (a.ndim - 2)), pos - (nb - (b.ndim - 2))
+        sa = a.shape[ia] if ia >= 0 else None
+        sb = b.shape[ib] if ib >= 0 else None
+        if sa is not None and sb is not None and sa != sb:
+            if sa == 1:
+                la[ia] = fresh
+            elif sb == 1:
+                lb[ib] = fresh
+            else:
+                raise ValueError(f"matmul: batch dims {sa} and {sb} do not broadcast")
+            fresh += 1
+    out = Array(contract_pair(a.t, la, b.t, lb, lc, conj_a=a.cj, conj_b=b.cj))
+    if vec_a:
+        out = out.squeeze(out.ndim - 2)
+    if vec_b:
+        out = out.squeeze(out.ndim - 1)
+    return out
 
 
 def dot(a, b):

@@ -239,7 +239,9 @@ def _safe_inverse(s, cutoff):
     is a 0-d / 1-element device tensor.  Stays on the device (no sync)."""
     xmax = s.max()
     xmax = torch.where(xmax > 0.0, xmax, torch.ones_like(xmax))
-    c = cutoff / xmax
+    # (an all-zero spectrum makes cutoff = 0: keep the damping finite so that
+    # zeros map to zero instead of 0 / 0)
+    c = torch.clamp_min(cutoff / xmax, float(torch.finfo(s.dtype).tiny) ** 0.5)
     y = s / xmax
     return y / ((y * y + c * c) * xmax)
 

@@ -31,6 +31,7 @@ _SKIP = {
     "test_gpu_boundary": set(),
     "test_gpu_tebd": set(),
     "test_gpu_linop": set(),
+    "test_gpu_zz_edge_cases": set(),
 }
 
 

@@ -292,33 +292,3 @@ def test_dmrg1_matches_reference_and_oracle(golden_mps):
     d.solve(tol=1e-8, max_sweeps=10, sweep_sequence="RL")
     assert d.state[0].dtype == np.complex128
     assert abs(d.energy - np.linalg.eigvalsh(dm.mpo_to_dense(mpo))[0]) < 1e-7
-
-
-@pytest.mark.parametrize("dtype", ["float64", "complex128"])
-def test_dmrg2_from_product_state_krylov_breakdown(dtype):
-    """A product state start makes the local Krylov spaces tiny: the Lanczos
-    basis breaks down exactly (beta = 0) -- also inside the steps queued ahead
-    of the host reads -- and must end cleanly at the invariant subspace."""
-    L = 8
-    mpo = dm.mpo_heis(L)
-    p0 = [np.zeros((1, 2, 1), dtype=dtype) for _ in range(L)]
-    for i in range(L):
-        p0[i][0, i % 2, 0] = 1.0
-    d = qb.DMRG2(mpo, [4, 8, 16], cutoffs=1e-10, mpo_shape="lrdu", p0=p0, mps_shape="lpr")
-    d.solve(tol=1e-8, max_sweeps=8)
-    assert d.state[0].dtype == np.dtype(dtype)
-    assert abs(d.energy - np.linalg.eigvalsh(dm.mpo_to_dense(mpo))[0]) < 1e-7
-    # exact eigenvector as the start vector: immediate breakdown, no NaNs
-    rng = np.random.default_rng(0)
-    q, _ = np.linalg.qr(rng.standard_normal((50, 50)))
-    lam = np.linspace(-3, 3, 50)
-    H = qb.asarray((q * lam) @ q.T)
-    theta, x, info = qb.eigh_lanczos(lambda v: qb.tensordot(H, v, axes=((1,), (0,))),
-                                     qb.asarray(q[:, 0].copy()), ncv=16, tol=1e-12,
-                                     return_info=True)
-    assert abs(theta - lam[0]) < 1e-12 and np.all(np.isfinite(x.to_numpy()))
-    # start vector inside a 3-dimensional invariant subspace
-    v0 = q[:, [0, 7, 20]] @ np.array([0.2, 1.0, -0.5])
-    theta, x, info = qb.eigh_lanczos(lambda v: qb.tensordot(H, v, axes=((1,), (0,))),
-                                     qb.asarray(v0), ncv=16, tol=1e-12, return_info=True)
-    assert abs(theta - lam[0]) < 1e-10 and info["nmatvec"] <= 8

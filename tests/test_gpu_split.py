@@ -223,36 +223,3 @@ def test_complex64_split_preserves_dtype():
     sref = np.linalg.svd(x.astype(np.complex128), compute_uv=False)
     err = np.linalg.norm(left.to_numpy().astype(np.complex128) @ right.to_numpy().astype(np.complex128) - x)
     assert err == pytest.approx(np.sqrt(np.sum(sref[8:] ** 2)), rel=1e-4)
-
-
-@pytest.mark.parametrize("m,n,r", [(60, 30, 8), (32, 30, 18), (20, 40, 5), (96, 96, 40)])
-def test_complex_qr_rank_deficient(m, n, r):
-    """Complex QR of numerically rank-deficient input (redundant MPS bonds,
-    products of thin factors): the real-embedding route is only valid through
-    uniqueness of the full-rank QR, so such input takes the SVD route: x = Q R
-    with a complete isometry Q (R is then not triangular)."""
-    rng = np.random.default_rng(m + n + r)
-    x = ((rng.standard_normal((m, r)) + 1j * rng.standard_normal((m, r)))
-         @ (rng.standard_normal((r, n)) + 1j * rng.standard_normal((r, n))))
-    Q, R = qb.linalg.qr(qb.asarray(x), stabilized=True)
-    q, rr = _np(Q), _np(R)
-    k = min(m, n)
-    assert q.shape == (m, k) and rr.shape == (k, n)
-    scale = np.linalg.norm(x, 2)
-    np.testing.assert_allclose(q.conj().T @ q, np.eye(k), atol=1e-11)
-    np.testing.assert_allclose(q @ rr, x, atol=1e-11 * scale)
-    # the LQ family and the split driver inherit it
-    left, _, right = qb.qr_stabilized(qb.asarray(x), absorb="left")
-    l, rt = _np(left), _np(right)
-    np.testing.assert_allclose(l @ rt, x, atol=1e-11 * scale)
-    np.testing.assert_allclose(rt @ rt.conj().T, np.eye(k), atol=1e-11)
-    # ill-conditioned but full rank (cond 1e8): still an isometry (to the
-    # accuracy of the singular subspaces of the tiniest values: 1e-8 covers a
-    # LAPACK-grade SVD; the Jacobi kernel is relatively accurate and far better)
-    u, _ = np.linalg.qr(rng.standard_normal((m, k)) + 1j * rng.standard_normal((m, k)))
-    v, _ = np.linalg.qr(rng.standard_normal((n, k)) + 1j * rng.standard_normal((n, k)))
-    y = (u * np.logspace(0, -8, k)) @ v.conj().T
-    Q, R = qb.linalg.qr(qb.asarray(y), stabilized=True)
-    q, rr = _np(Q), _np(R)
-    np.testing.assert_allclose(q.conj().T @ q, np.eye(k), atol=1e-8)
-    np.testing.assert_allclose(q @ rr, y, atol=1e-12)

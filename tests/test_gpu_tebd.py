@@ -113,91 +113,3 @@ def test_local_ham_single_site_terms_and_tebd_vs_oracle(golden_tebd):
     exact = sla.expm(-0.2j * ref) @ psi0
     v = _dense(t.pt)
     assert abs(np.vdot(exact, v)) / (np.linalg.norm(exact) * np.linalg.norm(v)) > 1 - 1e-4
-
-
-def test_mps_circuit_simulation_matches_statevector():
-    """CircuitMPS-style run (quimb/tensor/circuit/mps.py): one-qubit gates
-    contracted in, two-qubit gates (incl. long-range ones) by swap + split;
-    amplitudes against a dense state-vector simulation."""
-    from tests.circuit_util import _rand_u2, _rand_u4
-    rng = np.random.default_rng(12)
-    n, depth = 7, 5
-    gates = []
-    psi = np.zeros([2] * n, dtype=np.complex128)
-    psi[(0,) * n] = 1.0
-    for layer in range(depth):
-        for q in range(n):
-            u = _rand_u2(rng)
-            gates.append((u, (q,)))
-            psi = np.moveaxis(np.tensordot(u, psi, axes=(1, q)), 0, q)
-        pairs = [(0, 1), (2, 5), (6, 3)] if layer % 2 == 0 else [(1, 2), (4, 0), (5, 6)]
-        for a, b in pairs:
-            g = _rand_u4(rng)
-            gates.append((g.reshape(4, 4), (a, b)))
-            psi = np.moveaxis(np.tensordot(g, psi, axes=((2, 3), (a, b))), (0, 1), (a, b))
-    sites = tb.mps_zero_state(n)
-    tb.apply_circuit(sites, gates, cutoff=1e-14)
-    np.testing.assert_allclose(_dense(sites), psi.reshape(-1), atol=1e-10)
-    for bits in ([0] * n, [1, 0, 1, 1, 0, 0, 1], rng.integers(0, 2, n).tolist()):
-        assert abs(tb.mps_amplitude(sites, bits) - psi[tuple(bits)]) < 1e-10
-    # truncated run stays normalised to the discarded weight
-    s2 = tb.mps_zero_state(n)
-    tb.apply_circuit(s2, gates, max_bond=4, cutoff=0.0)
-    assert max(a.shape[2] for a in s2) <= 4
-    ov = abs(np.vdot(psi.reshape(-1), _dense(s2)))
-    assert 0.3 < ov <= 1.0 + 1e-12
-
-
-def test_mps_compress_add_apply_overlap_match_reference(golden_mps_ops):
-    """MatrixProductState.compress (all forms) / add_MPS / MPO.apply / overlap
-    of the reference (tests/golden/mps_ops.*): dense states and bond dims."""
-    data, meta = golden_mps_ops
-    n = 7
-    p = _fresh([data[f"p__{i}"] for i in range(n)])
-    q = _fresh([data[f"q__{i}"] for i in range(n)])
-    H = [data[f"H__{i}"] for i in range(n)]
-    np.testing.assert_allclose(_dense(p), data["p_dense"], atol=1e-13)
-    ov = tb.mps_overlap(p, q)
-    assert abs(ov - complex(*meta["overlap_pq"])) < 1e-12
-    np.testing.assert_allclose(_dense(tb.mps_add(p, q)), data["add_dense"], atol=1e-12)
-    Hp = tb.mpo_apply(H, p, mpo_shape="lrud")
-    assert [a.shape[2] for a in Hp[:-1]] == meta["Hp_bonds"]
-    np.testing.assert_allclose(_dense(Hp), data["Hp_dense"], atol=1e-12)
-    for c in meta["compress"]:
-        s = [a.copy() for a in Hp]
-        tb.mps_compress(s, **c["kw"])
-        assert [a.shape[2] for a in s[:-1]] == c["bonds"], c
-        tol = 1e-7 if c["kw"].get("method") == "svd:eig" else 1e-10
-        np.testing.assert_allclose(_dense(s), data[c["key"] + "__dense"], atol=tol,
-                                   err_msg=str(c))
-    # canonical forms: 'right' leaves every site but the first right-isometric
-    s = [a.copy() for a in Hp]
-    tb.mps_compress(s, form="right", max_bond=5, cutoff=0.0)
-    for a in s[1:]:
-        m = a.to_numpy().reshape(a.shape[0], -1)
-        np.testing.assert_allclose(m @ m.conj().T, np.eye(m.shape[0]), atol=1e-11)
-    with pytest.raises(ValueError):
-        tb.mps_compress(s, form="up")
-
-
-def test_compress_and_canonize_complex_mps_with_redundant_bonds():
-    """Zero-padded (rank-deficient) complex bonds: canonisation keeps the
-    state and compression finds the true bond dimensions (the complex QR takes
-    its SVD route on such input)."""
-    a = dm.mps_rand(6, 3, seed=5, dtype="complex128")
-    pad = []
-    for i, x in enumerate(a):
-        l, d, r = x.shape
-        y = np.zeros((l if i == 0 else l + 4, d, r if i == 5 else r + 4), dtype=complex)
-        y[:l, :, :r] = x
-        pad.append(y)
-    ref = dm.mps_to_dense(a).reshape(-1)
-    true_bonds = [x.shape[2] for x in a]
-    for form in ("right", "left", 3, "flat"):
-        s = [qb.asarray(x) for x in pad]
-        tb.mps_compress(s, form=form, cutoff=1e-12)
-        np.testing.assert_allclose(_dense(s), ref, atol=1e-12)
-        assert [x.shape[2] for x in s] == true_bonds
-    s = [qb.asarray(x) for x in pad]
-    tb.canonicalize(s, 2)
-    np.testing.assert_allclose(_dense(s), ref, atol=1e-12)
