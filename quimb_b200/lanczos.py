@@ -149,14 +149,34 @@ def eigh_lanczos(matvec, v0, which="SA", ncv=4, tol=1e-3, maxiter=None,
 
         vr0 = Array(torch.view_as_real(v0.t).reshape(-1))
         theta, xr, info = eigh_lanczos(mv_real, vr0, which=which, ncv=ncv, tol=tol,
-                                       maxiter=maxiter, return_info=True, comm=comm)
+                                       maxiter=maxiter, return_info=True, comm=comm,
+                                       min_steps=min_steps)
         x = Array(torch.view_as_complex(xr.t.reshape(-1, 2)))
+        return (theta, x, info) if return_info else (theta, x)
+    if v0.t.dtype in (torch.float32, torch.complex64):
+        # single precision operator: the Krylov process runs in double (basis,
+        # inner products, projected matrix); only the vectors handed to / taken
+        # from ``matvec`` are rounded, so the operator keeps its own dtype
+        # (quimb preserves the dtype end to end, test_dmrg.py:290-300)
+        from .contract import convert
+        narrow = v0.t.dtype
+        wide = torch.float64 if narrow == torch.float32 else torch.complex128
+
+        def mv_wide(vw):
+            vn = Array(convert(ops.materialize(vw).t, narrow))
+            out = ops.materialize(matvec(vn)).t.reshape(-1)
+            return Array(convert(out, wide))
+
+        theta, xw, info = eigh_lanczos(mv_wide, Array(convert(v0.t, wide)), which=which,
+                                       ncv=ncv, tol=tol, maxiter=maxiter, return_info=True,
+                                       comm=comm, min_steps=min_steps)
+        x = Array(convert(ops.materialize(xw).t, narrow))
         return (theta, x, info) if return_info else (theta, x)
     n = v0.size
     dt = v0.t.dtype
     if dt != torch.float64:
         raise NotImplementedError(f"eigh_lanczos: dtype {dt} is not implemented "
-                                  "yet (float64 only; no fallback)")
+                                  "(float32/64, complex64/128; no fallback)")
     dev = v0.t.device
     m = max(2, min(int(ncv), n, _NCV_MAX))
     if maxiter is None:

@@ -303,3 +303,18 @@ def test_split_drivers_on_degenerate_matrices(kind, dtype):
                     rec = L @ (np.diag(s) @ R if s is not None else R)
                     etol = tol * max(1.0, np.abs(x).max()) * (1e3 if method == "svd:eig" else 1)
                     assert np.abs(rec - x).max() <= etol, (m, n, method, absorb)
+
+
+@pytest.mark.parametrize("dtype,tol", [("float32", 2e-5), ("float64", 1e-8),
+                                       ("complex64", 2e-5), ("complex128", 1e-8)])
+def test_dmrg2_all_four_dtypes_preserved(dtype, tol):
+    """The reference's test_dtypes (tests/test_tensor/test_tn1d/test_dmrg.py:
+    290-300): the state keeps the Hamiltonian's dtype for f32 / f64 / c64 /
+    c128; single precision runs its Krylov process in double."""
+    mpo = dm.mpo_heis(8)
+    e0 = np.linalg.eigvalsh(dm.mpo_to_dense(mpo))[0]
+    d = qb.DMRG2([w.astype(dtype) for w in mpo], [8, 16], cutoffs=1e-8, mpo_shape="lrdu",
+                 seed=1, dtype=dtype)
+    d.solve(max_sweeps=3)
+    assert {str(a.dtype) for a in d.state} == {dtype}
+    assert abs(d.energy - e0) < tol * abs(e0)
