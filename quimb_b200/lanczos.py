@@ -167,6 +167,9 @@ def eigh_lanczos(matvec, v0, which="SA", ncv=4, tol=1e-3, maxiter=None,
             out = ops.materialize(matvec(vn)).t.reshape(-1)
             return Array(convert(out, wide))
 
+        # the operator itself is only accurate to single precision: a tighter
+        # residual than that can never be met
+        tol = max(tol, 100 * float(torch.finfo(torch.float32).eps))
         theta, xw, info = eigh_lanczos(mv_wide, Array(convert(v0.t, wide)), which=which,
                                        ncv=ncv, tol=tol, maxiter=maxiter, return_info=True,
                                        comm=comm, min_steps=min_steps)
@@ -206,6 +209,7 @@ def eigh_lanczos(matvec, v0, which="SA", ncv=4, tol=1e-3, maxiter=None,
     keep_max = max(1, min(mmax // 4, 8))
     Vk = Wk = None
     jstart = 0
+    best_resid, best_cycle = np.inf, 0
     Hh = np.zeros((mmax, mmax))
     for cycle in range(maxiter):
         # The projected matrix is assembled column by column on the host from
@@ -305,6 +309,15 @@ def eigh_lanczos(matvec, v0, which="SA", ncv=4, tol=1e-3, maxiter=None,
             x = Array(xnew)
             break
         x = Array(xnew)
+        # stagnation guard: a residual that has not improved over many matvecs
+        # (>= 300 and >= 10 full bases) sits at the accuracy of the operator
+        # (rounding of the matvec); return the best Ritz pair instead of
+        # spinning to ``maxiter``
+        if resid < 0.99 * best_resid:
+            best_resid, best_cycle = resid, nmv
+        elif nmv - best_cycle >= max(300, 10 * mmax):
+            info["stagnated"] = True
+            break
         # ---- thick restart ------------------------------------------------
         k = max(1, min(keep_max, m - 1))
         if Vk is None:
