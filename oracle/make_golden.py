@@ -332,6 +332,129 @@ def decomp2_cases():
     json.dump(meta, open(os.path.join(OUT, "decomp2.json"), "w"), indent=1, default=str)
 
 
+def decomp3_cases():
+    """'cholesky', 'qr:cholesky' / 'lq:cholesky' and 'polar_right' / 'polar_left'
+    of the reference on its numpy backend (factors are unique: stored as is)."""
+    import warnings
+    rng = np.random.default_rng(23)
+    store, meta = {}, {}
+    ps = rng.standard_normal((16, 24))
+    hc = rng.standard_normal((12, 18)) + 1j * rng.standard_normal((12, 18))
+    big = rng.standard_normal((72, 90))
+    mats = {
+        "pd": ps @ ps.T / 24,
+        "hpd": hc @ hc.conj().T / 18,
+        "pd_big": big @ big.T / 90,
+        "tall": rng.standard_normal((24, 10)),
+        "wide": rng.standard_normal((9, 20)),
+        "square": rng.standard_normal((16, 16)),
+        "cplx": rng.standard_normal((12, 14)) + 1j * rng.standard_normal((12, 14)),
+        "ctall": rng.standard_normal((15, 7)) + 1j * rng.standard_normal((15, 7)),
+        "tall_big": rng.standard_normal((150, 70)),
+    }
+    for k, v in mats.items():
+        store[f"mat__{k}"] = v
+
+    def put(key, left, sv, right):
+        assert sv is None
+        if left is not None:
+            store[f"{key}__left"] = np.asarray(left)
+        if right is not None:
+            store[f"{key}__right"] = np.asarray(right)
+        return [left is not None, False, right is not None]
+
+    chol = []
+    for mname in ("pd", "hpd", "pd_big"):
+        for absorb in (0, -12, 12):
+            for shift in (True, False, "auto", 1e-3):
+                if mname == "pd_big" and (absorb, shift) not in ((-12, True), (12, False)):
+                    continue
+                key = f"chol__{len(chol)}"
+                has = put(key, *decomp.cholesky_regularized(mats[mname], absorb=absorb, shift=shift))
+                chol.append({"key": key, "mat": mname, "absorb": absorb, "shift": shift, "has": has})
+    meta["cholesky_cases"] = chol
+    qrc = []
+    for mname, absorbs in [("tall", (1, 10, 11)), ("wide", (-1, -10, -11)),
+                           ("square", (1, 10, 11, -1, -10, -11)), ("cplx", (-1, -10, -11)),
+                           ("ctall", (1, 10, 11)), ("tall_big", (11,))]:
+        for absorb in absorbs:
+            for st in (True, False):
+                if mname == "tall_big" and not st:
+                    continue
+                key = f"qrc__{len(qrc)}"
+                has = put(key, *decomp.qr_via_cholesky(mats[mname], absorb=absorb,
+                                                       solve_triangular=st))
+                qrc.append({"key": key, "mat": mname, "absorb": absorb,
+                            "solve_triangular": st, "has": has})
+    meta["qr_cholesky_cases"] = qrc
+    pol = []
+    for mname in ("tall", "wide", "square", "cplx", "ctall"):
+        for side in ("right", "left"):
+            if (side == "right") != (mats[mname].shape[0] >= mats[mname].shape[1]) and \
+                    mats[mname].shape[0] != mats[mname].shape[1]:
+                continue    # P would be rank deficient and U not unique
+            key = f"polar__{len(pol)}"
+            fn = decomp.polar_right if side == "right" else decomp.polar_left
+            has = put(key, *fn(mats[mname]))
+            pol.append({"key": key, "mat": mname, "side": side, "has": has})
+    meta["polar_cases"] = pol
+    meta["parse_split_opts"] = []
+    for kw in [dict(method="cholesky"), dict(method="cholesky", absorb="lsqrt"),
+               dict(method="qr:cholesky"), dict(method="lq:cholesky"),
+               dict(method="qr:cholesky", absorb="rfactor"),
+               dict(method="polar_right"), dict(method="polar_left", max_bond=4)]:
+        method, opts = decomp.parse_split_opts(**kw)
+        meta["parse_split_opts"].append({"kw": kw, "method": method, "opts": opts})
+    # array_split end to end + error behaviour
+    arr = []
+    for mname, kw in [("pd", dict(method="cholesky")), ("tall", dict(method="qr:cholesky")),
+                      ("wide", dict(method="lq:cholesky")), ("square", dict(method="polar_right")),
+                      ("square", dict(method="polar_left"))]:
+        key = f"asplit__{len(arr)}"
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            has = put(key, *decomp.array_split(mats[mname], cutoff=0.0, **kw))
+        arr.append({"key": key, "mat": mname, "kw": kw, "has": has})
+    meta["array_split_cases"] = arr
+    errs = {}
+    indef = mats["square"] + mats["square"].T
+    store["mat__indef"] = indef
+    for shift in (False, True, "auto"):
+        try:
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                decomp.cholesky_regularized(indef, shift=shift)
+            errs[str(shift)] = None
+        except Exception as e:  # noqa: BLE001
+            errs[str(shift)] = type(e).__name__
+    try:
+        decomp.parse_split_opts(method="polar_right", absorb=None)
+        errs["polar_absorb_none"] = None
+    except Exception as e:  # noqa: BLE001
+        errs["polar_absorb_none"] = type(e).__name__
+    try:
+        decomp.cholesky_regularized(mats["pd"], absorb=1)
+        errs["chol_bad_absorb"] = None
+    except Exception as e:  # noqa: BLE001
+        errs["chol_bad_absorb"] = type(e).__name__
+    meta["errors"] = errs
+    # diagonal helpers
+    d = np.abs(rng.standard_normal(16)) + 0.1
+    d[3] = 0.0
+    z = rng.standard_normal(9) + 1j * rng.standard_normal(9)
+    z[2] = 0.0
+    store["helpers__d"] = d
+    store["helpers__z"] = z
+    store["helpers__rddiv"] = decomp.rddiv(mats["square"], d)
+    store["helpers__lddiv"] = decomp.lddiv(d, mats["square"])
+    store["helpers__sgn"] = decomp.sgn(z)
+    store["helpers__sgn_real"] = decomp.sgn(z.real)
+    store["helpers__safe_inverse"] = decomp.safe_inverse(d)
+    store["helpers__safe_inverse_sqrt"] = decomp.safe_inverse(d, cutoff=1e-3, power=0.5)
+    np.savez_compressed(os.path.join(OUT, "decomp3.npz"), **store)
+    json.dump(meta, open(os.path.join(OUT, "decomp3.json"), "w"), indent=1, default=str)
+
+
 def _dump_tn2d(tn, key, store):
     """Store every tensor of a 2D network: data, index names, site, layer."""
     recs = []
@@ -541,7 +664,7 @@ def mps_dmrg_cases():
 
 if __name__ == "__main__":
     only = set(sys.argv[1:])
-    for fn in (contract_cases, decomp_cases, decomp2_cases, boundary_cases, tebd_cases, mps_ops_cases,
+    for fn in (contract_cases, decomp_cases, decomp2_cases, decomp3_cases, boundary_cases, tebd_cases, mps_ops_cases,
                mps_dmrg_cases):
         if not only or fn.__name__ in only:
             fn()

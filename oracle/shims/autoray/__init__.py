@@ -156,7 +156,7 @@ class _Namespace:
         if name.startswith("__"):
             raise AttributeError(name)
         full = f"{self._prefix}{name}"
-        if name in ("linalg", "random", "fft"):
+        if name in ("linalg", "random", "fft", "scipy"):
             return _Namespace(self._backend, prefix=f"{full}.")
         fn = get_lib_fn(self._backend, full)
         return fn

@@ -125,14 +125,84 @@ def _strip(x):
     return x / xmax, float(np.log10(xmax))
 
 
+def _all_numpy(arrays):
+    return all(isinstance(a, (np.ndarray, np.generic, float, complex, int)) for a in arrays)
+
+
+def _dispatched_contract(arrays, inputs, output, path, size_dict, strip_exponent=False,
+                         backend=None):
+    """The pairwise loop as cotengra runs it for a non-numpy backend: every
+    node is ``do("tensordot")`` (+ ``do("transpose")``) when the pair is a
+    pure tensordot and ``do("einsum")`` otherwise, dispatched by autoray on
+    the array type (or ``backend``).  Used when the unmodified reference is
+    driven with device arrays as ``Tensor._data`` (tests/test_dropin_reference_cpu.py)."""
+    from autoray import do
+    arrays = list(arrays)
+    terms = [tuple(t) for t in inputs]
+    output = tuple(output)
+    expo = 0.0
+
+    def strip(x):
+        nonlocal expo
+        if not strip_exponent:
+            return x
+        f = do("max", do("abs", x, like=backend), like=backend)
+        f = float(f.item() if hasattr(f, "item") else f)
+        if f == 0.0:
+            return x
+        expo += math.log10(f)
+        return x / f
+
+    def single(x, t):
+        if t == output:
+            return x
+        if len(set(t)) == len(t) and set(t) == set(output):
+            return do("transpose", x, tuple(t.index(ix) for ix in output), like=backend)
+        sym = get_symbol_map([t])
+        return do("einsum", "".join(sym[i] for i in t) + "->" + "".join(sym[i] for i in output),
+                  x, like=backend)
+
+    if len(arrays) == 1:
+        res = strip(single(arrays[0], terms[0]))
+        return (res, expo) if strip_exponent else res
+    for i, j in path:
+        need = _cn._needed_elsewhere(terms, (i, j), output)
+        last = len(terms) == 2
+        iout = output if last else _cn._pair_result(terms[i], terms[j], need)
+        ia, ib = terms[i], terms[j]
+        sa, sb, so = set(ia), set(ib), set(iout)
+        pure = (len(sa) == len(ia) and len(sb) == len(ib) and not (sa & sb & so)
+                and (sa - sb) <= so and (sb - sa) <= so)
+        if pure:
+            shared = [ix for ix in ia if ix in sb]
+            res = do("tensordot", arrays[i], arrays[j],
+                     axes=([ia.index(ix) for ix in shared], [ib.index(ix) for ix in shared]),
+                     like=backend)
+            ires = tuple(ix for ix in ia if ix not in sb) + tuple(ix for ix in ib if ix not in sa)
+            if ires != tuple(iout):
+                res = do("transpose", res, tuple(ires.index(ix) for ix in iout), like=backend)
+        else:
+            sym = get_symbol_map([ia, ib, tuple(iout)])
+            eq = "{},{}->{}".format("".join(sym[x] for x in ia), "".join(sym[x] for x in ib),
+                                    "".join(sym[x] for x in iout))
+            res = do("einsum", eq, arrays[i], arrays[j], like=backend)
+        res = strip(res)
+        arrays = [x for k, x in enumerate(arrays) if k not in (i, j)] + [res]
+        terms = [t for k, t in enumerate(terms) if k not in (i, j)] + [tuple(iout)]
+    return (arrays[0], expo) if strip_exponent else arrays[0]
+
+
 def array_contract(arrays, inputs, output=None, optimize="auto", backend=None,
                    strip_exponent=False, cache_expression=True, **kwargs):
     inputs = tuple(tuple(t) for t in inputs)
-    shapes = [np.shape(a) for a in arrays]
+    shapes = [tuple(a.shape) if hasattr(a, "shape") else np.shape(a) for a in arrays]
     size_dict = _sizes(inputs, shapes)
     if output is None:
         output = _cn.gen_output_inds(ix for t in inputs for ix in t)
     path = _resolve(optimize, inputs, tuple(output), size_dict)
+    if not _all_numpy(arrays) or backend not in (None, "numpy"):
+        return _dispatched_contract(arrays, inputs, tuple(output), path, size_dict,
+                                    strip_exponent, backend)
     return _cn.array_contract(arrays, inputs, tuple(output), optimize=path,
                               size_dict=size_dict, strip_exponent=strip_exponent)
 
@@ -155,6 +225,8 @@ def array_contract_expression(inputs, output=None, size_dict=None, shapes=None,
             full[i] = c
         for i, a in zip(var_pos, arrays):
             full[i] = a
+        if not _all_numpy(full) or backend not in (None, "numpy"):
+            return _dispatched_contract(full, inputs, output, path, size_dict, False, backend)
         return _cn.array_contract(full, inputs, output, optimize=path,
                                   size_dict=size_dict)
 

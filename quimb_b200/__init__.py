@@ -22,22 +22,36 @@ from . import linalg  # noqa: F401
 from .contract import contract_batched, contract_pair, plan_pair  # noqa: F401
 from . import dist  # noqa: F401
 from .tree import (ContractExpression, GraphedContraction, Tree,  # noqa: F401
-                   array_contract, find_tree, gen_output_inds, tensor_contract)
+                   array_contract, find_sliced_tree, find_slices, find_tree,
+                   gen_output_inds, tensor_contract)
 from .mps import (MovingEnvironment, compute_left_environments,  # noqa: F401
                   compute_right_environments, env_left_step, env_right_step,
                   mps_expec, mps_norm, mps_norm2)
-from .split import (array_split, array_svals, eigh_truncated,  # noqa: F401
-                    qr_stabilized, svd_rand_truncated, svd_truncated,
+from .split import (array_split, array_svals, cholesky_regularized,  # noqa: F401
+                    eigh_truncated, lddiv, ldmul, polar_left, polar_right,
+                    qr_stabilized, qr_via_cholesky, rddiv, rdmul, safe_inverse, sgn, svd_rand_truncated, svd_truncated,
                     svd_via_eig, svd_via_eig_truncated, tensor_canonize_bond,
                     tensor_compress_bond, tensor_split)
 from .lanczos import eigh_lanczos  # noqa: F401
-from . import boundary, linop, tebd  # noqa: F401
+from . import boundary, linop, tebd, treeopt  # noqa: F401
 from .linop import TNLinearOperator  # noqa: F401
 from .tebd import TEBD, LocalHam1D, gate_split, gate_with_auto_swap  # noqa: F401
 from .boundary import (BoundaryContractor2D, contract_boundary,  # noqa: F401
                        contract_boundary_two_sided, peps_norm_tensors)
 from .dmrg import DMRG1, DMRG2  # noqa: F401
 from .integration import register_with_quimb  # noqa: F401
+
+
+
+class _Namespace:
+    """attribute bag so that dotted autoray names resolve
+    (``do("scipy.linalg.solve_triangular", like="quimb_b200")``)."""
+
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+
+scipy = _Namespace(linalg=_Namespace(solve_triangular=linalg.solve_triangular))
 
 __version__ = "0.1.0"
 

@@ -180,6 +180,11 @@ class Array:
             t = t.real
         return Array(t.to(td))
 
+    def toarray(self):
+        """quimb's ``qarray`` protocol (DMRG reads eigenvectors through
+        ``loc_gs.toarray()``, dmrg.py:841): already a plain array."""
+        return self
+
     def copy(self):
         from .ops import materialize
         return materialize(self, force=True)

@@ -78,10 +78,16 @@ def contract_sliced(arrays, inputs, output, sliced_inds=None, optimize="auto",
         for t, x in zip(inputs, arrays):
             for ix, d in zip(t, x.shape):
                 sd[ix] = int(d)
-        full_tree = find_tree(inputs, tuple(output), sd, optimize)
         if min_slices is None:
             min_slices = world()[1] if world_size is None else world_size
-        sliced_inds = find_slices(full_tree, target_width, min_slices)[0]
+        if optimize == "auto-hq" and target_width is not None:
+            # tree and slices searched together (tree of the sliced network)
+            from .tree import find_sliced_tree
+            optimize, sliced_inds = find_sliced_tree(inputs, tuple(output), sd,
+                                                     target_width, min_slices)
+        else:
+            full_tree = find_tree(inputs, tuple(output), sd, optimize)
+            sliced_inds = find_slices(full_tree, target_width, min_slices)[0]
     sliced = tuple(sliced_inds)
     if any(ix in output for ix in sliced):
         raise ValueError("cannot slice an output index")

@@ -53,12 +53,19 @@ def register_with_quimb():
 
     for nm, fn in (("svd_via_eig_truncated", _svd_via_eig_truncated),
                    ("svd_rand_truncated", split.svd_rand_truncated),
-                   ("eigh_truncated", split.eigh_truncated)):
+                   ("eigh_truncated", split.eigh_truncated),
+                   ("cholesky_regularized", split.cholesky_regularized),
+                   ("qr_via_cholesky", split.qr_via_cholesky),
+                   ("polar_right", split.polar_right),
+                   ("polar_left", split.polar_left),
+                   ("rddiv", split.rddiv), ("lddiv", split.lddiv),
+                   ("rdmul", split.rdmul), ("ldmul", split.ldmul),
+                   ("sgn", split.sgn)):
         if hasattr(decomp, nm) and hasattr(getattr(decomp, nm), "register"):
             getattr(decomp, nm).register(name)(fn)
             done.append(nm)
 
-    for nm in ("fuse", "unfuse"):
+    for nm in ("fuse", "unfuse", "multiply_diagonal", "align_axes"):
         fn = getattr(array_ops, nm, None)
         if fn is not None and hasattr(fn, "register"):
             fn.register(name)(getattr(ops, nm))
@@ -73,7 +80,56 @@ def register_with_quimb():
         done.append("norm_fro")
     ar.register_function(name, "to_numpy", ops.to_numpy)
     done.append("to_numpy")
+
+    # partial eigensolver backend: ``eigh(A, k=1, backend="quimb_b200")`` /
+    # ``dmrg.opts["local_eig_backend"] = "quimb_b200"`` (one dictionary entry
+    # next to "NUMPY" / "SCIPY" / "LOBPCG", quimb/linalg/base_linalg.py:70-77)
+    from quimb.linalg import base_linalg
+    base_linalg._EIGS_METHODS[name.upper()] = eigs_quimb_b200
+    done.append("eigs:QUIMB_B200")
     return done
+
+
+def eigs_quimb_b200(A, k=1, *, B=None, which="SA", return_vecs=True, sigma=None,
+                    isherm=True, ncv=None, sort=True, tol=None, v0=None,
+                    maxiter=None, **backend_opts):
+    """quimb partial-eigensolver backend (same contract as ``eigs_scipy``,
+    quimb/linalg/scipy_linalg.py:23-133: returns ``lk`` as a host array of
+    ``k`` values and ``vk`` with eigenvectors as columns) that keeps the
+    whole Krylov process on the device.  ``A`` is a quimb
+    ``TNLinearOperator`` over device arrays (its ``_matvec`` accepts and
+    returns device arrays, tensor_core.py:12393-12417) or a dense Hermitian
+    device array (DMRG's dense branch, dmrg.py:690-703)."""
+    import numpy as np
+    from . import linalg
+    from .lanczos import eigh_lanczos
+    if B is not None or sigma is not None or not isherm:
+        raise NotImplementedError("quimb_b200 eigensolver: standard Hermitian problems only")
+    if which not in ("SA", "LA"):
+        raise NotImplementedError(f"quimb_b200 eigensolver: which={which!r}")
+    if hasattr(A, "_matvec") and not isinstance(A, Array):
+        if k != 1:
+            raise NotImplementedError("quimb_b200 eigensolver: k=1 for linear operators")
+        n = A.shape[1]
+        if v0 is None:
+            v0 = np.random.default_rng(0).standard_normal(n).astype(
+                np.dtype(A.dtype), copy=False)
+        v0 = ops.asarray(v0)
+        theta, x = eigh_lanczos(lambda v: ops.asarray(A._matvec(v)), v0, which=which,
+                                ncv=max(2, min(64, ncv or 4)),
+                                tol=1e-3 if not tol else tol, maxiter=maxiter)
+        lk = np.array([theta])
+        if not return_vecs:
+            return lk
+        return lk, Array(x.resolve().reshape(-1, 1))
+    w, v = linalg.eigh(ops.asarray(A))
+    wt, vt = w.resolve(), v.resolve()
+    if which == "LA":
+        wt, vt = wt.flip(0), vt.flip(1)
+    lk = wt[:k].cpu().numpy()
+    if not return_vecs:
+        return lk
+    return lk, Array(vt[:, :k].contiguous())
 
 
 __all__ = ["register_with_quimb", "to_device", "Array"]

@@ -362,3 +362,108 @@ def eigh(x, host_below=None):
 
 _REAL_OF = {torch.float32: torch.float32, torch.float64: torch.float64,
             torch.complex64: torch.float32, torch.complex128: torch.float64}
+
+
+# ------------------------------------------------ Cholesky / pseudo-inverse --
+def _scale_rows(x, d, sqrt_d=False):
+    """x[i, :] *= d[i]^p in place on a contiguous matrix (``qb_scale_diag``)."""
+    rows, cols = x.shape
+    rc = _lib.load().qb_scale_diag(_lib.qb_dtype(x.dtype), rows, cols, x.data_ptr(),
+                                   d.data_ptr(), 0, int(sqrt_d), _lib.stream_ptr())
+    _lib.check(rc, "qb_scale_diag")
+    return x
+
+
+@_narrow
+def _cholesky_lower(x):
+    x = _as_matrix(x)
+    n = x.shape[0]
+    if x.shape[1] != n:
+        raise ValueError(f"cholesky: expected a square matrix, got shape {x.shape}")
+    if n == 0:
+        return (x,)
+    if x.t.dtype == torch.complex128:
+        # chol(embed(x)) = embed(chol(x)): the embedding of the complex factor
+        # is real lower triangular with a positive diagonal, and that
+        # factorisation is unique
+        (Le,) = _cholesky_lower(Array(_embed(x)))
+        return (Array(_extract(Le.t, n, n, 2)),)
+    w, v = eigh(x)
+    wh = w.t.detach().cpu().numpy()
+    tol = n * float(np.finfo(np.float64).eps) * float(np.abs(wh).max(initial=0.0))
+    if not np.all(np.isfinite(wh)) or wh.max(initial=0.0) <= 0.0 or wh.min() < -tol:
+        raise np.linalg.LinAlgError("Matrix is not positive definite")
+    sq = torch.clamp(w.t, min=0.0).contiguous()
+    B = ops.materialize(Array(v.t.transpose(0, 1), not v.cj), force=True).t   # V^H
+    _scale_rows(B, sq, sqrt_d=True)                                           # sqrt(w) V^H
+    _, R = qr(Array(B), stabilized=True, want_q=False)
+    return (ops.materialize(Array(R.t.transpose(0, 1))),)
+
+
+def cholesky(x, upper=False):
+    """Cholesky factor of a Hermitian positive-definite matrix, ``x = L L^H``
+    (``upper=True``: the factor ``L^H``), the ``xp.linalg.cholesky`` behind
+    quimb's ``cholesky_regularized`` (decomp.py:2245-2322).
+
+    No new device code: with ``x = V diag(w) V^H`` from the Jacobi ``eigh``,
+    the stabilised QR ``sqrt(w) V^H = Q R`` gives ``x = R^H R`` with
+    ``diag(R) > 0``, and the Cholesky factor is unique, so ``L = R^H``.  Not
+    positive definite (an eigenvalue below ``-n eps |w|_max``) raises
+    ``numpy.linalg.LinAlgError`` as LAPACK does; eigenvalues inside the
+    rounding band around zero are treated as zero.  Off the contraction hot
+    path (bond-environment gauging); ~10x the flops of a blocked potrf."""
+    (L,) = _cholesky_lower(x)
+    if upper:
+        return ops.materialize(Array(L.t.transpose(0, 1), True))
+    return L
+
+
+def pinv(x, rcond=None):
+    """Moore-Penrose pseudo-inverse through the device SVD (singular values
+    below ``rcond * s_max`` are dropped; default ``max(m, n) * eps`` like
+    ``numpy.linalg.pinv``'s ``rtol``)."""
+    x = ops.asarray(x)
+    U, s, VH = svd(x)
+    st = s.t
+    if rcond is None:
+        rcond = max(x.shape) * float(torch.finfo(st.dtype).eps)
+    smax = st.max() if st.numel() else st.new_zeros(())
+    keep = st > rcond * smax
+    sinv = torch.where(keep, 1.0 / torch.where(keep, st, torch.ones_like(st)),
+                       torch.zeros_like(st)).contiguous()
+    Vs = _scale_rows(ops.materialize(VH, force=True).t, sinv)        # s^-1 V^H
+    left = Array(Vs.transpose(0, 1), True)                           # V s^-1
+    right = Array(U.t.transpose(0, 1), not U.cj)                     # U^H
+    return ops.matmul(left, right)
+
+
+def inv(x):
+    """Dense inverse.  Library forward (torch / cuSOLVER getrf + getri): not on
+    the contraction hot path, listed in SURVEY 8(b) as forwardable."""
+    return Array(torch.linalg.inv(ops.asarray(x).resolve()))
+
+
+def solve(a, b):
+    """``a @ out = b``.  Library forward (torch / cuSOLVER), see :func:`inv`."""
+    return Array(torch.linalg.solve(ops.asarray(a).resolve(), ops.asarray(b).resolve()))
+
+
+def solve_triangular(a, b, lower=False, trans=0, unit_diagonal=False, **kwargs):
+    """``scipy.linalg.solve_triangular`` signature (used by quimb's
+    ``qr_via_cholesky``, decomp.py:2404).  Library forward (torch / cuBLAS
+    trsm), see :func:`inv`."""
+    A = ops.asarray(a).resolve()
+    B = ops.asarray(b).resolve()
+    if trans in (1, "T"):
+        A, lower = A.transpose(-2, -1), not lower
+    elif trans in (2, "C"):
+        A, lower = A.conj().transpose(-2, -1), not lower
+    vec = B.ndim == 1
+    if vec:
+        B = B[:, None]
+    out = torch.linalg.solve_triangular(A, B, upper=not lower, unitriangular=unit_diagonal)
+    return Array(out[:, 0] if vec else out)
+
+
+def eigvalsh(x):
+    return eigh(x)[0]

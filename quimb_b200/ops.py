@@ -29,7 +29,10 @@ def asarray(x, dtype=None, device=None):
     if isinstance(x, torch.Tensor):
         t = x
     else:
-        t = torch.as_tensor(np.asarray(x))
+        xn = np.asarray(x)
+        if not xn.flags.writeable:
+            xn = xn.copy()          # torch cannot wrap read-only host memory
+        t = torch.as_tensor(xn)
     dev = device or (t.device if t.device.type == "cuda" else default_device())
     if t.device != dev:
         if t.device.type == "cpu" and t.numel() * t.element_size() >= (1 << 20):
@@ -529,3 +532,77 @@ def scale_(x, alpha=1.0, div_by=None):
                       x.t.data_ptr(), _lib.stream_ptr())
     _lib.check(rc, "qb_scale")
     return x
+
+
+# --------------------------------- remaining names of the backend surface ---
+# (cold helpers quimb's drivers reach through ``do``; they
+# forward to torch on the wrapped tensor like the element-wise block above)
+log2 = _wrap(torch.log2)
+log10 = _wrap(torch.log10)
+argsort = _wrap(torch.argsort)
+
+
+def sort(x, axis=-1):
+    return Array(torch.sort(_t(asarray(x)), dim=axis).values)
+
+
+prod = _wrap(torch.prod)
+outer = _wrap(torch.outer)
+
+
+def dag(x):
+    """conjugate transpose of the last two axes (lazy flag + view)."""
+    x = asarray(x)
+    return swapaxes(conj(x), x.ndim - 2, x.ndim - 1)
+
+
+def identity(n, dtype="float64", device=None):
+    return eye(n, dtype=dtype, device=device)
+
+
+def full(shape, fill_value, dtype=None, device=None):
+    if dtype is None:
+        dtype = "complex128" if isinstance(fill_value, complex) else "float64"
+    if isinstance(shape, numbers.Integral):
+        shape = (shape,)
+    return Array(torch.full(tuple(shape), fill_value, dtype=torch_dtype(dtype),
+                            device=device or default_device()))
+
+
+def indices(dimensions, dtype="int64", device=None):
+    """numpy.indices: grid index arrays, shape (len(dimensions), *dimensions)."""
+    dev = device or default_device()
+    grids = torch.meshgrid(*[torch.arange(int(d), dtype=torch_dtype(dtype), device=dev)
+                             for d in dimensions], indexing="ij")
+    if not grids:
+        return Array(torch.empty((0,), dtype=torch_dtype(dtype), device=dev))
+    return Array(torch.stack(grids, dim=0))
+
+
+def finfo(dtype):
+    """numpy.finfo of a dtype given as a name, a numpy / torch dtype or an
+    Array (quimb's safe_inverse / diag shifts ask the backend for eps)."""
+    if isinstance(dtype, Array):
+        dtype = dtype.dtype
+    if isinstance(dtype, torch.dtype):
+        dtype = str(dtype).replace("torch.", "")
+    return np.finfo(np.dtype(dtype))
+
+
+def multiply_diagonal(x, v, axis, backend=None):
+    """x with the vector v multiplied in along ``axis`` as if contracting with
+    diag(v) (quimb/tensor/array_ops.py:226-231)."""
+    x = asarray(x)
+    shape = tuple(-1 if i == axis % x.ndim else 1 for i in range(x.ndim))
+    return x * reshape(asarray(v), shape)
+
+
+def align_axes(*arrays, axes, backend=None):
+    """dense arrays need no sector alignment (array_ops.py:234-243)."""
+    return arrays
+
+
+def norm_fro(x):
+    """Frobenius norm through the deterministic dot kernel (array_ops.py:255-262)."""
+    from .linalg import norm
+    return norm(x)

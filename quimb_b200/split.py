@@ -50,7 +50,9 @@ _QR_ABSORBS = {get_U_sVH, get_U, get_sVH, get_Us_VH, get_Us, get_VH}
 
 _DEFAULT_ABSORB = {"svd": get_Usq_sqVH, "svd:eig": get_Usq_sqVH,
                    "svd:rand": get_Usq_sqVH, "eigh": get_Usq_sqVH,
-                   "qr": get_U_sVH}
+                   "qr": get_U_sVH, "cholesky": get_Usq_sqVH,
+                   "qr:cholesky": get_U_sVH, "polar_right": get_U_sVH,
+                   "polar_left": get_Us_VH}
 # which options each driver takes (the reference inspects the signature of
 # _SPLIT_FNS[method], decomp.py:391-422)
 _METHOD_OPTS = {
@@ -59,6 +61,10 @@ _METHOD_OPTS = {
     "eigh": ("absorb", "max_bond", "cutoff", "cutoff_mode", "renorm"),
     "svd:rand": ("absorb", "max_bond"),
     "qr": ("absorb",),
+    "cholesky": ("absorb",),
+    "qr:cholesky": ("absorb",),
+    "polar_right": (),
+    "polar_left": (),
 }
 
 
@@ -86,7 +92,8 @@ def parse_method_absorb(method="auto", absorb="auto", truncation=True):
     if method not in _DEFAULT_ABSORB:
         raise ValueError(f"quimb_b200: split method {method!r} is not "
                          "implemented (available: 'svd', 'svd:eig', 'svd:rand', "
-                         "'eigh', 'qr', 'lq')")
+                         "'eigh', 'qr', 'lq', 'cholesky', 'qr:cholesky', "
+                         "'lq:cholesky', 'polar_right', 'polar_left')")
     if absorb == "auto":
         absorb = _DEFAULT_ABSORB[method]
     else:
@@ -104,8 +111,10 @@ def parse_split_opts(method="auto", absorb="auto", max_bond=None,
     truncation = (max_bond > 0) or (cutoff > 0.0)
     method, absorb = parse_method_absorb(method, absorb, truncation)
     takes = _METHOD_OPTS[method]
-    opts = {"absorb": absorb}
-    if method == "qr" and absorb is None:
+    opts = {}
+    if "absorb" in takes:
+        opts["absorb"] = absorb
+    if absorb is None and (method == "qr" or "absorb" not in takes):
         raise ValueError("You can't return the singular values separately when "
                          f"`method='{method}'`.")
     if "max_bond" in takes:
@@ -515,12 +524,162 @@ def qr_stabilized(x, absorb=get_U_sVH, stabilized=True):
     raise ValueError(f"Invalid absorb mode for qr_stabilized: {absorb}")
 
 
+# ------------------------------------------- Cholesky / polar split drivers --
+_ABSORB_TRANSPOSE_MAP = {get_U_sVH: get_Us_VH, get_U: get_VH, get_sVH: get_Us,
+                         get_Us_VH: get_U_sVH, get_VH: get_U, get_Us: get_sVH}
+
+
+def _cholesky_maybe_with_diag_shift(x, absorb, shift):
+    x = _with_diag_shift(x, shift)
+    if absorb == get_sqVH:
+        return None, None, linalg.cholesky(x, upper=True)
+    left = linalg.cholesky(x, upper=False)
+    if absorb == get_Usq:
+        return left, None, None
+    if absorb == get_Usq_sqVH:
+        return left, None, ops.materialize(Array(left.t.transpose(0, 1), True))
+    raise ValueError(
+        f"Invalid absorb={absorb} in cholesky_regularized. Should be one "
+        "of 'both'/'get_Usq_sqVH', 'lsqrt'/'get_Usq' or rsqrt'/'get_sqVH'.")
+
+
+def cholesky_regularized(x, absorb=get_Usq_sqVH, shift=True):
+    """``method='cholesky'`` (decomp.py:2269-2322): ``(L, None, L^H)`` of a
+    positive-definite matrix; ``shift`` = True (add eps * trace to the
+    diagonal), False, 'auto' (retry with the shift if the plain factorisation
+    fails) or a relative float."""
+    absorb = _ABSORB_MAP[absorb]
+    if isinstance(shift, str) and shift == "auto":
+        try:
+            return _cholesky_maybe_with_diag_shift(x, absorb, 0.0)
+        except Exception as e:  # noqa: BLE001  (the reference catches Exception)
+            import warnings
+            warnings.warn(
+                f"Cholesky decomposition failed with error: {e}. "
+                "retrying with small regularization added to the diagonal.")
+            return _cholesky_maybe_with_diag_shift(x, absorb, -1.0)
+    shift = {False: 0.0, True: -1.0}.get(shift, shift)
+    return _cholesky_maybe_with_diag_shift(x, absorb, shift)
+
+
+def qr_via_cholesky(x, absorb=get_Us_VH, shift=True, solve_triangular=True):
+    """``method='qr:cholesky'`` / ``'lq:cholesky'`` (decomp.py:2359-2424):
+    QR- or LQ-like split from the Cholesky factor of the Gram matrix (a
+    launch of the contraction kernel) and a triangular solve."""
+    absorb = _ABSORB_MAP[absorb]
+    if absorb in (get_U_sVH, get_U, get_sVH):
+        transposed = True
+    elif absorb in (get_Us_VH, get_Us, get_VH):
+        transposed = False
+    else:
+        raise ValueError(f"Invalid absorb mode for qr_via_cholesky: {absorb}")
+    x = ops.asarray(x)
+    if x.ndim != 2:
+        raise ValueError("qr_via_cholesky: only 2-d arrays are supported")
+    if transposed:
+        absorb = _ABSORB_TRANSPOSE_MAP[absorb]
+        xT = ops.transpose(x, (1, 0))
+        xx = ops.matmul(xT, ops.conj(x))
+        x = xT
+    else:
+        xx = ops.matmul(x, ops.conj(ops.transpose(x, (1, 0))))
+    m, n = x.shape
+    if m > n:
+        import warnings
+        warnings.warn(f"qr_via_cholesky not well-defined for tall matrices ({m} > {n}).")
+    L, _, _ = cholesky_regularized(xx, absorb=get_Usq, shift=shift)
+    if absorb != get_Us:
+        if solve_triangular:
+            right = linalg.solve_triangular(L, x, lower=True)
+        else:
+            right = linalg.solve(L, x)
+    else:
+        right = None
+    left = L if absorb != get_VH else None
+    if transposed:
+        RT, QT = left, right
+        left = None if QT is None else ops.materialize(ops.transpose(QT, (1, 0)))
+        right = None if RT is None else ops.materialize(ops.transpose(RT, (1, 0)))
+    return left, None, right
+
+
+def polar_right(x):
+    """``x = U P`` with U isometric and P positive semi-definite
+    (decomp.py:2673-2700): from the device SVD, ``U = W V^H``,
+    ``P = V s V^H``; two launches of the contraction kernel."""
+    W, s, VH = linalg.svd(x)
+    U = ops.matmul(W, VH)
+    sV = Array(_ldmul(s.t, ops.materialize(VH, force=True).t))
+    P = ops.matmul(_dag(VH), sV)
+    return U, None, P
+
+
+def polar_left(x):
+    """``x = P U`` (decomp.py:2703-2730): ``P = W s W^H``, ``U = W V^H``."""
+    W, s, VH = linalg.svd(x)
+    U = ops.matmul(W, VH)
+    Ws = Array(_rdmul(ops.materialize(W, force=True).t, s.t))
+    P = ops.matmul(Ws, _dag(W))
+    return P, None, U
+
+
+# ------------------------------------ diagonal helpers (decomp.py:580-656) --
+def rdmul(x, d):
+    """x @ diag(d)"""
+    return ops.asarray(x) * ops.asarray(d)[None, :]
+
+
+def ldmul(d, x):
+    """diag(d) @ x"""
+    return ops.asarray(x) * ops.asarray(d)[:, None]
+
+
+def safe_inverse(x, cutoff=None, power=1.0):
+    """decomp.py:501-551: ``x**-power`` with entries at or below ``cutoff``
+    (default ``eps * max(x)``) damped to zero:
+    ``y / ((y**q + c**q) * xmax**power)``, y = x / xmax, q = power + 1."""
+    t = ops.asarray(x).resolve()
+    if t.ndim == 1:
+        xmax = t.max() if t.numel() else t.new_ones(())
+    else:
+        xmax = t.max(dim=-1, keepdim=True).values
+    xmax = torch.where(xmax > 0.0, xmax, torch.ones_like(xmax))
+    if cutoff is None:
+        c = float(torch.finfo(t.dtype).eps)
+    else:
+        c = cutoff / xmax
+    y = t / xmax
+    q = power + 1.0
+    return Array(y / ((y ** q + c ** q) * xmax ** power))
+
+
+def rddiv(x, d):
+    """x @ diag(d)^-1 with the reference's safe inverse (decomp.py:591-604)."""
+    return rdmul(x, safe_inverse(d))
+
+
+def lddiv(d, x):
+    """diag(d)^-1 @ x (decomp.py:618-631)."""
+    return ldmul(safe_inverse(d), x)
+
+
+def sgn(x):
+    """x / |x| with sgn(0) = 1 (decomp.py:634-648)."""
+    t = ops.asarray(x).resolve()
+    x0 = (t == 0.0).to(t.dtype)
+    return Array((t + x0) / (t.abs() + (x0.real if t.is_complex() else x0)))
+
+
 _SPLIT_FNS = {
     "svd": svd_truncated,
     "svd:eig": svd_via_eig_truncated,
     "svd:rand": svd_rand_truncated,
     "eigh": eigh_truncated,
     "qr": qr_stabilized,
+    "cholesky": cholesky_regularized,
+    "qr:cholesky": qr_via_cholesky,
+    "polar_right": polar_right,
+    "polar_left": polar_left,
 }
 _SPLIT_VALUES_FNS = {"svd": svdvals, "svd:eig": svdvals_eig}
 

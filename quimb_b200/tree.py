@@ -379,6 +379,69 @@ def _optimal_ssa(inputs, output, size_dict):
     return ssa
 
 
+def _hq_candidates(inputs, output, size_dict, trials=64, subtree_size=8):
+    """Refined candidate trees over the rank-simplified network: noisy greedy
+    (good for shallow / tree-like networks) and the spectral sweep (good for
+    deep circuits and strips), each polished by subtree reconfiguration.
+    Yields ``(log2 cost, log2 width, ssa over the ORIGINAL inputs)``."""
+    from . import treeopt
+    n = len(inputs)
+    prefix, red, ids = treeopt.simplify_inputs(inputs, output, size_dict)
+    if len(red) < 3:
+        sub = [(0, 1)] if len(red) == 2 else []
+        full = treeopt.compose_ssa(prefix, n, ids, sub)
+        yield treeopt.tree_stats(inputs, output, size_dict, full) + (full,)
+        return
+    starts = [_random_greedy_ssa(red, output, size_dict, trials=trials),
+              treeopt.spectral_ssa(red, output, size_dict)]
+    for sub in starts:
+        sub = treeopt.reconfigure(red, output, size_dict, sub, subtree_size=6)
+        sub = treeopt.reconfigure(red, output, size_dict, sub, subtree_size=subtree_size)
+        c, w = treeopt.tree_stats(red, output, size_dict, sub)
+        yield c, w, treeopt.compose_ssa(prefix, n, ids, sub)
+
+
+def _hq_ssa(inputs, output, size_dict):
+    return min(_hq_candidates(inputs, output, size_dict), key=lambda t: t[:2])[2]
+
+
+def find_sliced_tree(inputs, output, size_dict, target_width, min_slices=None,
+                     optimize="auto-hq", subtree_size=8):
+    """Tree + sliced indices found TOGETHER for a memory target (the job of
+    cotengra's ``slicing_reconf_opts``): candidates from ``optimize`` are each
+    sliced index by index with the tree of the sliced network re-optimised
+    after every cut, and the cheapest total (cost per slice x slices) wins.
+    Returns ``(Tree over the sliced inputs, sliced_inds)``; ``min_slices``
+    (e.g. the world size) adds slices with :func:`find_slices` when the width
+    target alone gives fewer.  Host-only."""
+    from . import treeopt
+    inputs = [tuple(t) for t in inputs]
+    output = tuple(output)
+    if optimize == "auto-hq":
+        cands = [c[2] for c in _hq_candidates(inputs, output, size_dict, subtree_size=subtree_size)]
+    else:
+        cands = [[(i, j) for i, j, _, _ in find_tree(inputs, output, size_dict, optimize).steps]]
+    best = None
+    for ssa in cands:
+        ssa2, sl = treeopt.slice_and_reconfigure(inputs, output, size_dict, ssa,
+                                                 target_width, subtree_size=subtree_size)
+        s = set(sl)
+        red = [tuple(ix for ix in t if ix not in s) for t in inputs]
+        c, w = treeopt.tree_stats(red, output, size_dict, ssa2)
+        tot = c + sum(math.log2(size_dict[ix]) for ix in sl)
+        if best is None or (w > target_width, tot) < best[0]:
+            best = ((w > target_width, tot), ssa2, sl, red)
+    _, ssa, sl, red = best
+    tr = Tree(red, output, size_dict, ssa)
+    if min_slices is not None and math.prod(size_dict[ix] for ix in sl) < min_slices:
+        more = find_slices(tr, None, -(-min_slices // math.prod(size_dict[ix] for ix in sl)))[0]
+        sl = tuple(sl) + tuple(more)
+        s = set(sl)
+        red = [tuple(ix for ix in t if ix not in s) for t in inputs]
+        tr = Tree(red, output, size_dict, ssa)
+    return tr, tuple(sl)
+
+
 def find_tree(inputs, output, size_dict, optimize="auto"):
     n = len(inputs)
     if hasattr(optimize, "get_path"):          # cotengra.ContractionTree
@@ -392,9 +455,13 @@ def find_tree(inputs, output, size_dict, optimize="auto"):
     elif optimize in ("optimal", "dp") or (
             optimize in ("auto", "auto-hq", "random-greedy", None) and n <= 9):
         ssa = _optimal_ssa(inputs, output, size_dict)
-    elif optimize in ("random-greedy", "auto-hq"):
-        ssa = _random_greedy_ssa(inputs, output, size_dict,
-                                 trials=128 if optimize == "auto-hq" else 32)
+    elif optimize == "auto-hq":
+        ssa = _hq_ssa(inputs, output, size_dict)
+    elif optimize == "spectral":
+        from . import treeopt
+        ssa = treeopt.spectral_ssa(inputs, output, size_dict)
+    elif optimize == "random-greedy":
+        ssa = _random_greedy_ssa(inputs, output, size_dict, trials=32)
     elif optimize in ("auto", None):
         ssa = _random_greedy_ssa(inputs, output, size_dict, trials=8)
     elif optimize == "greedy":

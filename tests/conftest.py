@@ -69,3 +69,8 @@ def golden_tebd():
 @pytest.fixture(scope="session")
 def golden_mps_ops():
     return load_golden("mps_ops")
+
+
+@pytest.fixture(scope="session")
+def golden_decomp3():
+    return load_golden("decomp3")
