@@ -167,3 +167,74 @@ def test_reference_dmrg2_runs_on_device_arrays(env, dense):
     exact = qu.groundenergy(qu.ham_heis(L, cyclic=False, sparse=True))
     assert abs(float(dm.energy) - exact) < 1e-6
     assert [dm.state[i].shape for i in range(L)] == [ref.state[i].shape for i in range(L)]
+
+
+def test_reference_callers_either_side_of_the_path(env):
+    """The reference's own drivers around the hot path (boundary
+    contraction, circuits, TEBD, DMRG1, MPS gates / arithmetic, rank
+    simplification) on device arrays, against their numpy runs."""
+    import quimb as qu
+    qtn, qb, _ = env
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        # PEPS norm by boundary-MPS contraction (tn2d/core.py:2528-2543)
+        peps = qtn.PEPS.rand(4, 4, bond_dim=2, seed=1, dtype="complex128")
+        norm = peps.make_norm()
+        ref = norm.contract_boundary(max_bond=8, cutoff=0.0, layer_tags=("KET", "BRA"))
+        out = _dev(norm, qb).contract_boundary(max_bond=8, cutoff=0.0, layer_tags=("KET", "BRA"))
+        assert abs(complex(out) - complex(ref)) < 1e-10 * abs(ref)
+        ising = qtn.TN2D_classical_ising_partition_function(4, 4, beta=0.3)
+        assert abs(float(_dev(ising, qb).contract_boundary(max_bond=8))
+                   - float(ising.contract_boundary(max_bond=8))) < 1e-6
+
+        # circuit amplitude with to_backend (circuit/exact.py:90-98)
+        def build(**kw):
+            rng = np.random.default_rng(0)
+            circ = qtn.Circuit(5, **kw)
+            for d in range(4):
+                for q in range(5):
+                    circ.apply_gate("U3", *rng.uniform(0, 6, 3), q)
+                for q in range(d % 2, 4, 2):
+                    circ.apply_gate("CZ", q, q + 1)
+            return circ
+        assert abs(complex(build(to_backend=qb.asarray).amplitude("01001"))
+                   - complex(build().amplitude("01001"))) < 1e-12
+        tn = build().amplitude_tn("00000")
+        assert abs(complex(_dev(tn, qb).full_simplify() ^ all) - complex(tn.full_simplify() ^ all)) < 1e-12
+
+        # TEBD (tn1d/tebd.py)
+        ham = qtn.ham_1d_heis(6)
+        psi0 = qtn.MPS_neel_state(6)
+        t0 = qtn.TEBD(psi0.copy(), ham, progbar=False)
+        t0.update_to(0.2, dt=0.05, order=2)
+        t1 = qtn.TEBD(_dev(psi0, qb), ham, progbar=False)
+        t1.update_to(0.2, dt=0.05, order=2)
+        assert isinstance(t1.pt[2].data, qb.Array)
+        host = t1.pt.copy()
+        host.apply_to_arrays(lambda x: x.to_numpy())
+        assert abs(abs(complex(t0.pt.H @ host)) - abs(complex(t0.pt.H @ t0.pt))) < 1e-10
+
+        # DMRG1 with the device eigensolver backend
+        H = qtn.MPO_ham_heis(8)
+        p0 = qtn.MPS_rand_state(8, 8, seed=3)
+        r = qtn.DMRG1(H.copy(), bond_dims=[8, 16], p0=p0.copy())
+        r.solve(tol=1e-8, max_sweeps=4, verbosity=0)
+        d = qtn.DMRG1(_dev(H, qb), bond_dims=[8, 16], p0=_dev(p0, qb))
+        d.opts["local_eig_backend"] = "quimb_b200"
+        d.solve(tol=1e-8, max_sweeps=4, verbosity=0)
+        assert abs(float(d.energy) - float(r.energy)) < 1e-7
+
+        # MPS gates, MPO application, addition, entropy, dense vector
+        p = qtn.MPS_rand_state(6, 4, seed=2)
+        G = qu.rand_uni(4, seed=1).reshape(2, 2, 2, 2)
+        for where, fn in (((2, 3), "gate_split"), ((0, 4), "gate_with_auto_swap")):
+            rr = getattr(p, fn)(G, where, cutoff=1e-12)
+            dd = getattr(_dev(p, qb), fn)(qb.asarray(G), where, cutoff=1e-12)
+            np.testing.assert_allclose(np.asarray(dd.to_dense()), rr.to_dense(), atol=1e-10)
+        Hh = qtn.MPO_ham_heis(6)
+        np.testing.assert_allclose(np.asarray(_dev(Hh, qb).apply(_dev(p, qb)).to_dense()),
+                                   Hh.apply(p).to_dense(), atol=1e-10)
+        q = qtn.MPS_rand_state(6, 3, seed=6)
+        np.testing.assert_allclose(np.asarray((_dev(p, qb) + _dev(q, qb)).to_dense()),
+                                   (p + q).to_dense(), atol=1e-12)
+        assert abs(float(_dev(p, qb).entropy(3)) - float(p.entropy(3))) < 1e-10
