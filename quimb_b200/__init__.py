@@ -51,7 +51,8 @@ class _Namespace:
         self.__dict__.update(kw)
 
 
-scipy = _Namespace(linalg=_Namespace(solve_triangular=linalg.solve_triangular))
+scipy = _Namespace(linalg=_Namespace(solve_triangular=linalg.solve_triangular,
+                                     expm=linalg.expm))
 
 __version__ = "0.1.0"
 

@@ -180,6 +180,27 @@ class Array:
             t = t.real
         return Array(t.to(td))
 
+    def diagonal(self, offset=0, axis1=0, axis2=1):
+        return Array(torch.diagonal(self.resolve(), offset, axis1, axis2))
+
+    # scipy's ``aslinearoperator`` accepts any object with ``shape`` and
+    # ``matvec``: with these a dense device matrix can be handed to
+    # ``scipy.sparse.linalg.eigsh`` / ``svds`` directly (what quimb's DMRG does
+    # with its dense effective Hamiltonian when no eigensolver backend is
+    # selected, dmrg.py:690-703 -> scipy_linalg.py:113-128): the Krylov vectors
+    # live on the host, the products run on the device.
+    def matvec(self, v):
+        from .ops import asarray, matmul
+        return matmul(self, asarray(np.asarray(v).astype(self.dtype, copy=False))).to_numpy()
+
+    def matmat(self, m):
+        return self.matvec(m)
+
+    def rmatvec(self, v):
+        from .ops import asarray, matmul
+        return matmul(self.conj().swapaxes(0, 1),
+                      asarray(np.asarray(v).astype(self.dtype, copy=False))).to_numpy()
+
     def toarray(self):
         """quimb's ``qarray`` protocol (DMRG reads eigenvectors through
         ``loc_gs.toarray()``, dmrg.py:841): already a plain array."""
@@ -238,10 +259,27 @@ class Array:
     def __neg__(self): return Array(-self.resolve())
     def __pos__(self): return self
     def __abs__(self): return Array(self.t.abs())
-    def __lt__(self, o): return self._bin(o, torch.lt)
-    def __le__(self, o): return self._bin(o, torch.le)
-    def __gt__(self, o): return self._bin(o, torch.gt)
-    def __ge__(self, o): return self._bin(o, torch.ge)
+    def _order(self, other, fn):
+        """ordering comparisons; complex operands compare lexicographically
+        (real part, then imaginary part) as numpy does -- torch has no complex
+        ordering, and quimb's drivers compare 0-d complex overlaps with floats
+        (``0.0 < psi.H @ psi < 1.0``)."""
+        def cmp(a, b):
+            ca = isinstance(a, complex) or (isinstance(a, torch.Tensor) and a.is_complex())
+            cb = isinstance(b, complex) or (isinstance(b, torch.Tensor) and b.is_complex())
+            if not (ca or cb):
+                return fn(torch.as_tensor(a) if not isinstance(a, torch.Tensor) else a, b)
+            dev = a.device if isinstance(a, torch.Tensor) else b.device
+            a = torch.as_tensor(a, device=dev).to(torch.complex128)
+            b = torch.as_tensor(b, device=dev).to(torch.complex128)
+            strict = torch.lt if fn in (torch.lt, torch.le) else torch.gt
+            return torch.where(a.real != b.real, strict(a.real, b.real), fn(a.imag, b.imag))
+        return self._bin(other, cmp)
+
+    def __lt__(self, o): return self._order(o, torch.lt)
+    def __le__(self, o): return self._order(o, torch.le)
+    def __gt__(self, o): return self._order(o, torch.gt)
+    def __ge__(self, o): return self._order(o, torch.ge)
     def __eq__(self, o): return self._bin(o, torch.eq)
     def __ne__(self, o): return self._bin(o, torch.ne)
     __hash__ = None

@@ -467,3 +467,10 @@ def solve_triangular(a, b, lower=False, trans=0, unit_diagonal=False, **kwargs):
 
 def eigvalsh(x):
     return eigh(x)[0]
+
+
+def expm(x):
+    """Matrix exponential.  Library forward (torch.linalg.matrix_exp): gate
+    construction (``isometrize(method="exp")``, Trotter terms), not on the
+    contraction hot path."""
+    return Array(torch.linalg.matrix_exp(ops.asarray(x).resolve()))

@@ -373,11 +373,9 @@ sin = _wrap(torch.sin)
 cos = _wrap(torch.cos)
 tanh = _wrap(torch.tanh)
 sign = _wrap(torch.sgn)
-cumsum = _wrap(torch.cumsum)
 count_nonzero = _wrap(torch.count_nonzero)
 where = _wrap(torch.where)
 clip = _wrap(torch.clamp)
-flip = _wrap(torch.flip)
 isfinite = _wrap(torch.isfinite)
 isnan = _wrap(torch.isnan)
 argmax = _wrap(torch.argmax)
@@ -389,9 +387,6 @@ multiply = _wrap(torch.mul)
 add = _wrap(torch.add)
 subtract = _wrap(torch.sub)
 divide = _wrap(torch.div)
-take = _wrap(torch.take)
-tril = _wrap(torch.tril)
-triu = _wrap(torch.triu)
 
 
 def abs(x):  # noqa: A001
@@ -606,3 +601,47 @@ def norm_fro(x):
     """Frobenius norm through the deterministic dot kernel (array_ops.py:255-262)."""
     from .linalg import norm
     return norm(x)
+
+
+# ---- numpy-signature versions of helpers whose torch signature differs ------
+def take(x, indices, axis=None):
+    """numpy.take: an integer index drops the axis, a sequence keeps it."""
+    t = _t(asarray(x))
+    if axis is None:
+        t, axis = t.reshape(-1), 0
+    if isinstance(indices, numbers.Integral):
+        return Array(t.select(axis, int(indices)))
+    idx = _t(indices) if isinstance(indices, Array) else torch.as_tensor(
+        np.asarray(indices), device=t.device)
+    idx = idx.to(torch.int64)
+    out = t.index_select(axis, idx.reshape(-1))
+    if idx.ndim != 1:
+        shape = list(t.shape)
+        out = out.reshape(shape[:axis] + list(idx.shape) + shape[axis + 1:])
+    return Array(out)
+
+
+def flip(x, axis=None):
+    t = _t(asarray(x))
+    if axis is None:
+        dims = tuple(range(t.ndim))
+    elif isinstance(axis, numbers.Integral):
+        dims = (int(axis),)
+    else:
+        dims = tuple(int(a) for a in axis)
+    return Array(torch.flip(t, dims))
+
+
+def cumsum(x, axis=None):
+    t = _t(asarray(x))
+    if axis is None:
+        t, axis = t.reshape(-1), 0
+    return Array(torch.cumsum(t, dim=axis))
+
+
+def tril(x, k=0):
+    return Array(torch.tril(_t(asarray(x)), diagonal=k))
+
+
+def triu(x, k=0):
+    return Array(torch.triu(_t(asarray(x)), diagonal=k))

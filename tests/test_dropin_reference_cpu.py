@@ -146,6 +146,25 @@ def test_canonize_compress_and_linear_operator(env):
     assert isinstance(out, qb.Array)
 
 
+def test_reference_dmrg2_default_eigensolver_path(env):
+    """No backend selected: quimb hands the dense effective Hamiltonian or the
+    TNLinearOperator to scipy ARPACK on the host (dmrg.py:626-645); the
+    products run on the device, the Krylov vectors cross the boundary."""
+    qtn, qb, _ = env
+    L = 8
+    H = qtn.MPO_ham_heis(L)
+    p0 = qtn.MPS_rand_state(L, 4, seed=3)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ref = qtn.DMRG2(H.copy(), bond_dims=[8, 16, 32], cutoffs=1e-10, p0=p0.copy())
+        ref.solve(tol=1e-8, max_sweeps=5, verbosity=0)
+        for dense in (None, False):
+            dm = qtn.DMRG2(_dev(H, qb), bond_dims=[8, 16, 32], cutoffs=1e-10, p0=_dev(p0, qb))
+            dm.opts["local_eig_ham_dense"] = dense
+            dm.solve(tol=1e-8, max_sweeps=5, verbosity=0)
+            assert abs(float(dm.energy) - float(ref.energy)) < 1e-6
+
+
 @pytest.mark.parametrize("dense", [True, False])
 def test_reference_dmrg2_runs_on_device_arrays(env, dense):
     qtn, qb, _ = env

@@ -188,3 +188,27 @@ def test_pinv_inv_solve_and_small_surface():
     np.testing.assert_allclose(float(qb.prod(qb.asarray(b[:, 0])).item()), np.prod(b[:, 0]))
     np.testing.assert_allclose(_np(qb.log10(qb.asarray(np.abs(b)))), np.log10(np.abs(b)))
     np.testing.assert_allclose(_np(qb.linalg.eigvalsh(qb.asarray(a + a.T))), np.linalg.eigvalsh(a + a.T), atol=1e-11)
+
+
+def test_numpy_signature_helpers():
+    """take / flip / cumsum / tril / triu / expm with numpy's signatures (found
+    by running the reference's own test-suite on device tensors)."""
+    rng = np.random.default_rng(4)
+    x = rng.standard_normal((3, 4, 5))
+    X = qb.asarray(x)
+    np.testing.assert_array_equal(_np(qb.take(X, 2, axis=1)), np.take(x, 2, axis=1))
+    np.testing.assert_array_equal(_np(qb.take(X, [3, 0], axis=2)), np.take(x, [3, 0], axis=2))
+    np.testing.assert_array_equal(_np(qb.take(X, 7)), np.take(x, 7))
+    np.testing.assert_array_equal(_np(qb.take(X, [[0, 1], [2, 2]], axis=0)), np.take(x, [[0, 1], [2, 2]], axis=0))
+    for ax in (None, 0, -1, (0, 2)):
+        np.testing.assert_array_equal(_np(qb.flip(X, axis=ax)), np.flip(x, axis=ax))
+    np.testing.assert_allclose(_np(qb.cumsum(X)), np.cumsum(x))
+    np.testing.assert_allclose(_np(qb.cumsum(X, axis=1)), np.cumsum(x, axis=1))
+    m = x[0]
+    for k in (-1, 0, 2):
+        np.testing.assert_array_equal(_np(qb.tril(qb.asarray(m), k=k)), np.tril(m, k=k))
+        np.testing.assert_array_equal(_np(qb.triu(qb.asarray(m), k=k)), np.triu(m, k=k))
+    import scipy.linalg as sla
+    a = rng.standard_normal((4, 4)) + 1j * rng.standard_normal((4, 4))
+    np.testing.assert_allclose(_np(qb.linalg.expm(qb.asarray(a))), sla.expm(a), atol=1e-12)
+    np.testing.assert_allclose(_np(qb.scipy.linalg.expm(qb.asarray(a.real))), sla.expm(a.real), atol=1e-12)
