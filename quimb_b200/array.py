@@ -308,6 +308,9 @@ class Array:
         from .ops import matmul
         return matmul(self, other)
 
+    def dot(self, other):
+        return self.__matmul__(other)
+
     def __rmatmul__(self, other):
         from .ops import matmul, asarray
         return matmul(asarray(other), self)

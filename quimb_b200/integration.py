@@ -81,6 +81,18 @@ def register_with_quimb():
     ar.register_function(name, "to_numpy", ops.to_numpy)
     done.append("to_numpy")
 
+    # singular-value-only drivers are plain (numba) functions in quimb, looked
+    # up by method name (decomp.py:474-493): wrap them so device arrays take
+    # the device routes and everything else still reaches the original
+    for method, fn in (("svd", split.svdvals), ("svd:eig", split.svdvals_eig)):
+        orig = decomp._SPLIT_VALUES_FNS.get(method)
+        if orig is not None and not getattr(orig, "_quimb_b200", False):
+            def _svals(x, *a, _orig=orig, _fn=fn, **kw):
+                return _fn(x) if isinstance(x, Array) else _orig(x, *a, **kw)
+            _svals._quimb_b200 = True
+            decomp._SPLIT_VALUES_FNS[method] = _svals
+            done.append(f"svals:{method}")
+
     # partial eigensolver backend: ``eigh(A, k=1, backend="quimb_b200")`` /
     # ``dmrg.opts["local_eig_backend"] = "quimb_b200"`` (one dictionary entry
     # next to "NUMPY" / "SCIPY" / "LOBPCG", quimb/linalg/base_linalg.py:70-77)
