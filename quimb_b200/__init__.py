@@ -51,6 +51,46 @@ class _Namespace:
         self.__dict__.update(kw)
 
 
+def _random_array(shape, dist="normal", dtype="float64", rng=None, seed=None,
+                  loc=0.0, scale=1.0, **kwargs):
+    """``xp.random.array`` as quimb's builders call it (tensor_builder.py:4129,
+    tn1d/compress.py:1283): values drawn on the host from a numpy Generator
+    (``rng`` / ``seed``: reproducible, same stream as the numpy backend) and
+    placed on the device."""
+    import numpy as _np
+    if rng is None:
+        rng = _np.random.default_rng(seed)
+    elif not isinstance(rng, _np.random.Generator):
+        rng = _np.random.default_rng(rng)
+    if isinstance(shape, int):
+        shape = (shape,)
+    dt = _np.dtype(dtype)
+
+    def draw():
+        if dist == "normal":
+            return rng.standard_normal(shape)
+        if dist == "uniform":
+            return rng.uniform(-1.0, 1.0, size=shape)
+        if dist == "rademacher":
+            return rng.choice([-1.0, 1.0], size=shape)
+        if dist == "exp":
+            return rng.exponential(size=shape)
+        raise ValueError(f"unknown distribution {dist!r}")
+    x = draw()
+    if dt.kind == "c":
+        x = (x + 1j * draw()) / 2 ** 0.5 if dist != "rademacher" else x + 0j
+    x = x * scale + loc
+    return asarray(_np.asarray(x, dtype=dt))  # noqa: F405
+
+
+random = _Namespace(
+    array=_random_array,
+    normal=lambda loc=0.0, scale=1.0, size=(), dtype="float64", **kw: _random_array(
+        size, "normal", dtype, loc=loc, scale=scale, **kw),
+    uniform=lambda low=0.0, high=1.0, size=(), dtype="float64", **kw: _random_array(
+        size, "uniform", dtype, loc=(low + high) / 2, scale=(high - low) / 2, **kw),
+)
+
 scipy = _Namespace(linalg=_Namespace(solve_triangular=linalg.solve_triangular,
                                      expm=linalg.expm))
 

@@ -28,7 +28,7 @@ _SKIP = {
     "test_gpu_mps_dmrg": {"test_bond_sharded_eigensolve_two_ranks_one_gpu"},
     "test_gpu_split": set(),
     "test_gpu_split2": set(),
-    "test_gpu_split3": set(),
+    "test_gpu_zzz_split3": set(),
     "test_gpu_boundary": set(),
     "test_gpu_tebd": set(),
     "test_gpu_linop": set(),
