@@ -382,7 +382,8 @@ def _optimal_ssa(inputs, output, size_dict):
 def _hq_candidates(inputs, output, size_dict, trials=64, subtree_size=8):
     """Refined candidate trees over the rank-simplified network: noisy greedy
     (good for shallow / tree-like networks) and the spectral sweep (good for
-    deep circuits and strips), each polished by subtree reconfiguration.
+    deep circuits and strips), each polished by simulated annealing over tree
+    rotations and exact subtree reconfiguration.
     Yields ``(log2 cost, log2 width, ssa over the ORIGINAL inputs)``."""
     from . import treeopt
     n = len(inputs)
@@ -394,8 +395,9 @@ def _hq_candidates(inputs, output, size_dict, trials=64, subtree_size=8):
         return
     starts = [_random_greedy_ssa(red, output, size_dict, trials=trials),
               treeopt.spectral_ssa(red, output, size_dict)]
-    for sub in starts:
+    for k, sub in enumerate(starts):
         sub = treeopt.reconfigure(red, output, size_dict, sub, subtree_size=6)
+        sub = treeopt.anneal(red, output, size_dict, sub, sweeps=300, seed=k)
         sub = treeopt.reconfigure(red, output, size_dict, sub, subtree_size=subtree_size)
         c, w = treeopt.tree_stats(red, output, size_dict, sub)
         yield c, w, treeopt.compose_ssa(prefix, n, ids, sub)

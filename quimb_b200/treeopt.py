@@ -22,7 +22,8 @@ Trees are exchanged as SSA step lists like everywhere in ``tree.py``.
 import math
 import random
 
-__all__ = ["reconfigure", "slice_and_reconfigure", "tree_stats"]
+__all__ = ["reconfigure", "anneal", "slice_and_reconfigure", "tree_stats",
+           "spectral_ssa", "growth_ssa", "simplify_inputs", "compose_ssa"]
 
 
 class _Bits:
@@ -359,16 +360,21 @@ def _greedy_slices(bt, target_width, fixed=(), max_new=None):
 
 def slice_and_reconfigure(inputs, output, size_dict, ssa, target_width,
                           subtree_size=8, step=1, minimize="flops", max_rounds=2,
-                          max_time=None):
-    """Interleave slicing with reconfiguration (the scheme of cotengra's
+                          anneal_sweeps=300, max_time=None):
+    """Interleave slicing with re-optimisation (the scheme of cotengra's
     ``slicing_reconfigure``): slice the ``step`` best indices for the current
-    tree, re-optimise the tree of the *sliced* network -- the one that is
-    executed once per slice -- and repeat until its largest intermediate has
-    at most ``2**target_width`` elements.  Returns ``(ssa, sliced_inds)``; the
-    tree is valid for the unsliced network as well (same leaves)."""
+    tree, then anneal + reconfigure the tree of the *sliced* network -- the one
+    that is executed once per slice -- with intermediates wider than the
+    target charged extra, and repeat until the largest intermediate has at
+    most ``2**target_width`` elements.  The width target of each round is
+    lowered one bit at a time (never below ``target_width``): annealing
+    against the final target from the start distorts the early rounds.
+    Returns ``(ssa, sliced_inds)``; the tree is valid for the unsliced network
+    as well (same leaves)."""
     import time
     t0 = time.time()
     sliced = []
+    wprev = None
     while True:
         sl = set(sliced)
         red_inputs = [tuple(ix for ix in t if ix not in sl) for t in inputs]
@@ -376,14 +382,16 @@ def slice_and_reconfigure(inputs, output, size_dict, ssa, target_width,
         bt = _BinTree(red_inputs, red_output, size_dict, ssa)
         if sliced:
             left = None if max_time is None else max(1.0, max_time - (time.time() - t0))
+            if anneal_sweeps and len(inputs) >= 4:
+                _anneal_bt(bt, anneal_sweeps, 0.5, 0.02, max(target_width, wprev - 1.0),
+                           seed=len(sliced), max_time=left)
             _reconfigure_bt(bt, subtree_size, max_rounds,
                             64.0 if minimize == "combo" else 0.0, None, left)
             ssa = bt.to_ssa()
             bt = _BinTree(red_inputs, red_output, size_dict, ssa)
-        width = bt.width()
+        width = wprev = bt.width()
         if width <= target_width + 1e-9:
             break
-        # one greedy step: lower the target by one index at a time
         bits, _, _ = _greedy_slices(bt, target_width, max_new=step)
         if not bits:
             break
@@ -561,3 +569,94 @@ def spectral_ssa(inputs, output, size_dict):
         cur = nxt
         nxt += 1
     return ssa
+
+
+# ------------------------------------------------------ simulated annealing --
+def _anneal_bt(bt, sweeps=200, t_start=1.0, t_end=0.02, target_width=None, seed=0,
+               max_time=None):
+    """Metropolis over local tree rotations (the move set of cotengra's
+    ``simulated_anneal_tree``): at a node p = (l, r) with l = (a, b) the
+    sibling r is exchanged with a or b, which changes only the contraction
+    that forms l.  Scores are log2 of the local cost; an intermediate wider
+    than ``target_width`` is charged 2^(excess) extra.  Keeps the best tree
+    seen.  In place; returns the best total cost."""
+    import time
+    rng = random.Random(seed)
+    lsize = bt.bits.lsize
+    t0 = time.time()
+
+    def step_cost(li, lj, legs_out):
+        c = lsize(li | lj)
+        if target_width is not None:
+            over = lsize(legs_out) - target_width
+            if over > 0:
+                c += 2.0 * over
+        return c
+
+    def tree_score():
+        tot = 0.0
+        for k, (i, j) in bt.children.items():
+            tot += 2.0 ** step_cost(bt.legs[i], bt.legs[j], bt.legs[k])
+        return tot
+
+    cur = tree_score()
+    best = cur
+    best_children = dict(bt.children)
+    nodes = [k for k in bt.children]
+    for s in range(sweeps):
+        T = t_start * (t_end / t_start) ** (s / max(1, sweeps - 1))
+        rng.shuffle(nodes)
+        for p in nodes:
+            l, r = bt.children[p]
+            if rng.random() < 0.5:
+                l, r = r, l
+            if l not in bt.children:
+                l, r = r, l
+                if l not in bt.children:
+                    continue
+            a, b = bt.children[l]
+            if rng.random() < 0.5:
+                a, b = b, a
+            # p = ((a, b), r)  ->  ((a, r), b)
+            la, lb, lr = bt.legs[a], bt.legs[b], bt.legs[r]
+            old_l = bt.legs[l]
+            new_l, new_h = bt._merged_legs(la, lr, bt.hcnt[a], bt.hcnt[r])
+            lp = bt.legs[p]
+            old = 2.0 ** step_cost(la, lb, old_l) + 2.0 ** step_cost(old_l, lr, lp)
+            new = 2.0 ** step_cost(la, lr, new_l) + 2.0 ** step_cost(new_l, lb, lp)
+            if new > old:
+                d = math.log2(new) - math.log2(old)
+                if rng.random() >= math.exp(-d / T):
+                    continue
+            bt.children[l] = (a, r)
+            bt.legs[l], bt.hcnt[l] = new_l, new_h
+            bt.children[p] = (l, b)
+            cur += new - old
+            if cur < best * (1.0 - 1e-12):
+                best = cur
+                best_children = dict(bt.children)
+        if max_time is not None and time.time() - t0 > max_time:
+            break
+    # restore the best tree and recompute its legs bottom-up
+    bt.children = best_children
+    order, stack = [], [bt.root]
+    while stack:
+        k = stack.pop()
+        if k in bt.children:
+            order.append(k)
+            stack.extend(bt.children[k])
+    for k in reversed(order):
+        i, j = bt.children[k]
+        bt.legs[k], bt.hcnt[k] = bt._merged_legs(bt.legs[i], bt.legs[j], bt.hcnt[i], bt.hcnt[j])
+    return best
+
+
+def anneal(inputs, output, size_dict, ssa, sweeps=200, t_start=1.0, t_end=0.02,
+           target_width=None, seed=0, max_time=None):
+    """Simulated annealing of an SSA tree (see :func:`_anneal_bt`), followed by
+    nothing else -- combine with :func:`reconfigure`.  Returns new SSA steps."""
+    if len(inputs) < 4:
+        return list(ssa)
+    bt = _BinTree(inputs, output, size_dict, ssa)
+    _anneal_bt(bt, sweeps, t_start, t_end, target_width, seed, max_time)
+    return bt.to_ssa()

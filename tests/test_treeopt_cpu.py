@@ -160,3 +160,34 @@ def test_find_sliced_tree_meets_the_width_and_sums_to_the_amplitude():
     sl0, n0, w0, cost0 = tree.find_slices(full, target_width=target)
     tr2, sl2 = tree.find_sliced_tree(inputs, output, sizes, target)
     assert tr2.contraction_cost() * 2 ** len(sl2) <= cost0 * n0 * 1.0001
+
+
+def test_anneal_keeps_value_and_repairs_a_bad_tree():
+    rng = np.random.default_rng(21)
+    for hyper in (False, True):
+        for trial in range(10):
+            n = int(rng.integers(5, 11))
+            arrays, inputs, output, sizes = _rand_network(rng, n, int(rng.integers(n, 2 * n)), hyper)
+            ref = _einsum_ref(arrays, inputs, output)
+            ssa0 = tree._greedy_ssa(inputs, output, sizes)
+            ssa = treeopt.anneal(inputs, output, sizes, ssa0, sweeps=40, seed=trial)
+            out, tr = _run_ssa(inputs, output, sizes, ssa, arrays)
+            np.testing.assert_allclose(out, ref, rtol=1e-10, atol=1e-10)
+            # the best tree seen is kept: never worse than the start
+            assert tr.contraction_cost() <= tree.Tree(inputs, output, sizes, ssa0).contraction_cost() * (1 + 1e-9)
+            ssa_w = treeopt.anneal(inputs, output, sizes, ssa0, sweeps=20, seed=1, target_width=3.0)
+            out, _ = _run_ssa(inputs, output, sizes, ssa_w, arrays)
+            np.testing.assert_allclose(out, ref, rtol=1e-10, atol=1e-10)
+    # a deep grid circuit from a deliberately poor start (plain greedy):
+    # annealing alone recovers most of the gap to the refined tree
+    arrays, inputs, output, amp = random_grid_circuit_amplitude(3, 3, 16, seed=3)
+    sizes = {ix: 2 for t in inputs for ix in t}
+    prefix, red, ids = treeopt.simplify_inputs(inputs, output, sizes)
+    bad = tree._greedy_ssa(red, output, sizes)
+    c_bad, _ = treeopt.tree_stats(red, output, sizes, bad)
+    good = treeopt.anneal(red, output, sizes, bad, sweeps=200, seed=0)
+    c_good, w_good = treeopt.tree_stats(red, output, sizes, good)
+    assert c_good <= c_bad and w_good <= 9 + 1e-9
+    full = treeopt.compose_ssa(prefix, len(inputs), ids, good)
+    out, _ = _run_ssa(inputs, output, sizes, full, arrays)
+    assert abs(complex(out) - amp) < 1e-10
