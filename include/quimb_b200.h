@@ -87,6 +87,10 @@ enum {
   QB_ENGINE_AUTO = 0, /* heuristic                                    */
   QB_ENGINE_DMMA = 1, /* native fp64 tensor-core path (DMMA)          */
   QB_ENGINE_OZAKI = 2, /* tcgen05 int8 error-free-split path (fp64)    */
+  QB_ENGINE_STREAM = 3, /* HBM-bound streaming path for small-operator
+                         * steps (N <= 16 and K <= 16 after mode grouping:
+                         * gate application); other shapes take the DMMA
+                         * path.  Opt-in until timed on a B200.          */
   /* OR-able flag: the caller guarantees that bytes [0, 1024) of `workspace`
    * (the stream-K flag words) were zero before its first use and are written
    * by this library only -- which always leaves them zero again -- so the
@@ -146,6 +150,18 @@ int qb_contract_pair_plan(const qb_tensor_t *A, const int32_t *labelsA,
                           const qb_tensor_t *B, const int32_t *labelsB,
                           const qb_tensor_t *C, const int32_t *labelsC,
                           int64_t *out16);
+
+/*
+ * TEST / debug entry, host pointers only: runs the streaming engine's row
+ * code (shared __host__ __device__ functions of contract_stream.cu) in a
+ * host loop so that its index bookkeeping can be checked without a device.
+ * Never called by the product; returns -9 for shapes the engine does not take.
+ */
+int qb_debug_contract_stream_host(const qb_tensor_t *A, const int32_t *labelsA,
+                                  const qb_tensor_t *B, const int32_t *labelsB,
+                                  qb_tensor_t *C, const int32_t *labelsC,
+                                  int conjA, int conjB, double alpha,
+                                  double beta);
 
 /*
  * Many independent same-signature contractions in one launch: A[i], B[i], C[i]

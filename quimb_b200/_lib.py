@@ -12,7 +12,7 @@ import torch
 
 QB_MAX_RANK = 32
 QB_F32, QB_F64, QB_C64, QB_C128 = 0, 1, 2, 3
-QB_ENGINE_AUTO, QB_ENGINE_DMMA, QB_ENGINE_OZAKI = 0, 1, 2
+QB_ENGINE_AUTO, QB_ENGINE_DMMA, QB_ENGINE_OZAKI, QB_ENGINE_STREAM = 0, 1, 2, 3
 QB_ENGINE_WS_ZEROED = 0x100
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -110,6 +110,8 @@ def load(build_if_missing=True):
                                   P(i64), dblp, dblp]),
         ("qb_measure_dmma_peak", ci, [dblp, vp]),
         ("qb_debug_trace_read", ci, [vp, i64]),
+        ("qb_debug_contract_stream_host", ci,
+         [T, I32P, T, I32P, T, I32P, ci, ci, ctypes.c_double, ctypes.c_double]),
     ):
         if hasattr(lib, name):
             sig(name, res, args)

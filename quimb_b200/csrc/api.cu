@@ -82,16 +82,26 @@ static int check_device_dtype(int dt) {
 
 using namespace qb;
 
-// engine policy: explicit request, or QB_ENGINE=ozaki|dmma in the environment
-static bool want_ozaki(int engine, const PairPlan &plan) {
-  static const int env_engine = [] {
+// engine policy: explicit request, or QB_ENGINE=ozaki|dmma|stream in the
+// environment
+static int env_engine() {
+  static const int v = [] {
     const char *e = getenv("QB_ENGINE");
     if (e && !strcmp(e, "ozaki")) return (int)QB_ENGINE_OZAKI;
     if (e && !strcmp(e, "dmma")) return (int)QB_ENGINE_DMMA;
+    if (e && !strcmp(e, "stream")) return (int)QB_ENGINE_STREAM;
     return (int)QB_ENGINE_AUTO;
   }();
-  if (engine == QB_ENGINE_AUTO) engine = env_engine;
+  return v;
+}
+static bool want_ozaki(int engine, const PairPlan &plan) {
+  if (engine == QB_ENGINE_AUTO) engine = env_engine();
   return engine == QB_ENGINE_OZAKI && ozaki_eligible(plan);
+}
+// streaming engine (contract_stream.cu): small-operator steps, N, K <= 16
+static bool want_stream(int engine, const PairPlan &plan) {
+  if (engine == QB_ENGINE_AUTO) engine = env_engine();
+  return engine == QB_ENGINE_STREAM && stream_eligible(plan);
 }
 
 
@@ -128,6 +138,24 @@ int64_t qb_contract_pair_workspace(const qb_tensor_t *A, const int32_t *la,
   if (want_ozaki(engine & 0xff, plan))
     need = std::max(need, ozaki_workspace_bytes(plan) + kWsHeaderBytes);
   return need;
+}
+
+int qb_debug_contract_stream_host(const qb_tensor_t *A, const int32_t *la,
+                                  const qb_tensor_t *B, const int32_t *lb,
+                                  qb_tensor_t *C, const int32_t *lc, int conjA,
+                                  int conjB, double alpha, double beta) {
+  PairPlan plan;
+  int rc = plan_pair(A, la, B, lb, C, lc, conjA, conjB, plan);
+  if (rc) return rc;
+  if (plan.empty_out) return 0;
+  if (plan.zero_fill) {
+    set_error("qb_debug_contract_stream_host: zero-extent contraction");
+    return -10;
+  }
+  plan.p.alpha = alpha; plan.p.beta = beta;
+  rc = contract_stream_host(plan);
+  if (rc) set_error("qb_debug_contract_stream_host: needs N, K <= 16 and f64 / c128");
+  return rc;
 }
 
 // QB_TRACE=1: device buffer the kernels stamp their phase times into
@@ -187,6 +215,7 @@ static int contract_pair_impl(const qb_tensor_t *A, const int32_t *la,
     }
     return launch_contract_ozaki(plan, static_cast<char *>(workspace) + kWsHeaderBytes, st);
   }
+  if (want_stream(engine, plan)) return launch_contract_stream(plan, st);
   int64_t need = plan_workspace_bytes(plan);
   if (need > 0) {
     if (!workspace || (int64_t)workspace_bytes < need) {

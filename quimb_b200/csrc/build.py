@@ -15,6 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SOURCES = [
     "api.cu",
     "contract_dmma.cu",
+    "contract_stream.cu",
     "elementwise.cu",
     "linalg.cu",
     "ozaki_tc.cu",

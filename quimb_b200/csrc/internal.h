@@ -14,6 +14,11 @@ bool ozaki_eligible(const PairPlan &plan);
 int64_t ozaki_workspace_bytes(const PairPlan &plan);
 int launch_contract_ozaki(const PairPlan &plan, void *workspace, cudaStream_t st);
 
+// streaming engine for small-operator steps (contract_stream.cu)
+bool stream_eligible(const PairPlan &plan);
+int launch_contract_stream(const PairPlan &plan, cudaStream_t st);
+int contract_stream_host(const PairPlan &plan);  // TEST: same row code on host pointers
+
 // C(MxN) = alpha * A(MxK) * B(KxN) + beta * C on strided fp64 matrices
 // (element strides; any of them may describe a transposed view).
 int gemm_f64(const double *A, int64_t a_rs, int64_t a_cs, const double *B,

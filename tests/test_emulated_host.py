@@ -29,6 +29,8 @@ _SKIP = {
     "test_gpu_split": set(),
     "test_gpu_split2": set(),
     "test_gpu_zzz_split3": set(),
+    # asserts the launch count of the real engine
+    "test_gpu_zzz_stream": {"test_stream_engine_gate_application"},
     "test_gpu_boundary": set(),
     "test_gpu_tebd": set(),
     "test_gpu_linop": set(),
