@@ -59,7 +59,13 @@ def _random_array(shape, dist="normal", dtype="float64", rng=None, seed=None,
     placed on the device."""
     import numpy as _np
     if rng is None:
+        if seed is None:
+            # follow numpy's global state like the numpy backend does, so that
+            # ``np.random.seed(...)`` makes quimb's randomized drivers repeatable
+            seed = int(_np.random.randint(0, 2 ** 31 - 1))
         rng = _np.random.default_rng(seed)
+    elif hasattr(rng, "_rng"):
+        rng = rng._rng                      # a _DeviceGenerator from random.default_rng
     elif not isinstance(rng, _np.random.Generator):
         rng = _np.random.default_rng(rng)
     if isinstance(shape, int):
@@ -83,7 +89,43 @@ def _random_array(shape, dist="normal", dtype="float64", rng=None, seed=None,
     return asarray(_np.asarray(x, dtype=dt))  # noqa: F405
 
 
+class _DeviceGenerator:
+    """``xp.random.default_rng(seed)`` as quimb's randomized drivers use it
+    (decomp.py:1796-1824, tn1d/compress.py:1768): a numpy Generator whose
+    draws are placed on the device."""
+
+    def __init__(self, seed=None):
+        import numpy as _np
+        if isinstance(seed, _np.random.Generator):
+            self._rng = seed
+        else:
+            if seed is None:
+                seed = int(_np.random.randint(0, 2 ** 31 - 1))
+            self._rng = _np.random.default_rng(seed)
+
+    def normal(self, loc=0.0, scale=1.0, size=None, dtype="float64"):
+        return _random_array(() if size is None else size, "normal", dtype, rng=self._rng,
+                             loc=loc, scale=scale)
+
+    def standard_normal(self, size=None, dtype="float64"):
+        return self.normal(size=size, dtype=dtype)
+
+    def uniform(self, low=0.0, high=1.0, size=None, dtype="float64"):
+        return _random_array(() if size is None else size, "uniform", dtype, rng=self._rng,
+                             loc=(low + high) / 2, scale=(high - low) / 2)
+
+    def random(self, size=None, dtype="float64"):
+        return self.uniform(0.0, 1.0, size, dtype)
+
+    def integers(self, *args, **kwargs):
+        return self._rng.integers(*args, **kwargs)
+
+    def choice(self, *args, **kwargs):
+        return self._rng.choice(*args, **kwargs)
+
+
 random = _Namespace(
+    default_rng=_DeviceGenerator,
     array=_random_array,
     normal=lambda loc=0.0, scale=1.0, size=(), dtype="float64", **kw: _random_array(
         size, "normal", dtype, loc=loc, scale=scale, **kw),

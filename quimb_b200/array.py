@@ -85,6 +85,8 @@ class Array:
         return self.t.device
 
     def __len__(self):
+        if self.t.dim() == 0:
+            raise TypeError("len() of unsized object")
         return self.t.shape[0]
 
     def __repr__(self):

@@ -50,7 +50,7 @@ def convert(t, dtype):
 
 
 def contract_pair(a, la, b, lb, lc, conj_a=False, conj_b=False, out=None,
-                  engine=0, alpha=1.0, beta=0.0):
+                  engine=0, alpha=1.0, beta=0.0, _regrouped=False):
     """``out[lc] = sum op(a)[la] * op(b)[lb]`` with integer mode labels.
 
     Parameters
@@ -101,6 +101,12 @@ def contract_pair(a, la, b, lb, lc, conj_a=False, conj_b=False, out=None,
     da, db, dc = _lib.desc(a), _lib.desc(b), _lib.desc(out)
     pla, plb, plc = _lib.labels(la), _lib.labels(lb), _lib.labels(lc)
     need = lib.qb_contract_pair_workspace(da, pla, db, plb, dc, plc, engine)
+    if need == -100 and not _regrouped and "non-mergeable" in _lib.last_error():
+        # more than 12 jointly non-mergeable modes in one group (high-rank
+        # operands whose axes interleave: boundary / compression drivers on
+        # tensors of rank > 12): regroup the operands once with the permute
+        # kernel so that every group is a single contiguous mode
+        return _contract_regrouped(a, la, b, lb, lc, conj_a, conj_b, out, engine, alpha, beta)
     if need < 0:
         _lib.check(int(need), "qb_contract_pair_workspace")
     ws_ptr, ws_n = None, 0
@@ -117,6 +123,79 @@ def contract_pair(a, la, b, lb, lc, conj_a=False, conj_b=False, out=None,
                                      float(alpha), float(beta), ws_ptr, ws_n,
                                      _lib.stream_ptr())
     _lib.check(rc, "qb_contract_pair")
+    return out
+
+
+_CHUNK = 5
+
+
+def permute_contiguous(t, order):
+    """Contiguous tensor whose axis k is axis ``order[k]`` of ``t``, for any
+    rank: the permute kernel takes up to 15 jointly non-mergeable modes, so a
+    general permutation of a high-rank tensor is done in passes that each move
+    ``_CHUNK`` axes behind the rest (<= 2 * _CHUNK + 2 modes per pass)."""
+    lib = _lib.load()
+
+    def one_pass(src, perm):
+        view = src.permute(tuple(perm))
+        dst = torch.empty(view.shape, dtype=src.dtype, device=src.device)
+        if dst.numel():
+            rc = lib.qb_permute(_lib.desc(view), _lib.desc(dst), 0, _lib.stream_ptr())
+            _lib.check(rc, "qb_permute")
+        return dst
+
+    order = list(order)
+    r = t.dim()
+    if r <= 2 * _CHUNK:
+        return one_pass(t, order)
+    # start from a copy laid out in the source's own stride order (few modes)
+    by_stride = sorted(range(r), key=lambda ax: (-abs(t.stride(ax)), ax))
+    cur = one_pass(t, by_stride)
+    names = list(by_stride)                   # names[k] = original axis held by cur's axis k
+    placed = 0
+    while placed < r:
+        chunk = order[max(0, r - placed - _CHUNK): r - placed]
+        tail = order[r - placed:]
+        rest = [ax for ax in names if ax not in chunk and ax not in tail]
+        new = rest + chunk + tail
+        if new != names:
+            cur = one_pass(cur, [names.index(ax) for ax in new])
+            names = new
+        placed += len(chunk)
+    return cur
+
+
+def _contract_regrouped(a, la, b, lb, lc, conj_a, conj_b, out, engine, alpha, beta):
+    la, lb, lc = list(la), list(lb), list(lc)
+    if len(set(la)) != len(la) or len(set(lb)) != len(lb):
+        raise ValueError("contract_pair: too many non-mergeable modes and a repeated "
+                         "label inside one operand; take the diagonal first")
+    sa, sb, sc = set(la), set(lb), set(lc)
+    batch = [l for l in lc if l in sa and l in sb]
+    free_a = [l for l in lc if l in sa and l not in sb]
+    free_b = [l for l in lc if l in sb and l not in sa]
+    k = [l for l in la if l in sb and l not in sc]
+    sum_a = [l for l in la if l not in sb and l not in sc]
+    sum_b = [l for l in lb if l not in sa and l not in sc]
+    la2 = batch + free_a + k + sum_a
+    lb2 = batch + k + sum_b + free_b
+    lc2 = batch + free_a + free_b
+    a2 = permute_contiguous(a, [la.index(l) for l in la2])
+    b2 = permute_contiguous(b, [lb.index(l) for l in lb2])
+    if out is None:
+        res = contract_pair(a2, la2, b2, lb2, lc2, conj_a, conj_b, None, engine, alpha, beta,
+                            _regrouped=True)
+        return res.permute(tuple(lc2.index(l) for l in lc))   # a view in the requested order
+    if beta != 0.0:
+        cur = permute_contiguous(out, [lc.index(l) for l in lc2])
+        res = contract_pair(a2, la2, b2, lb2, lc2, conj_a, conj_b, cur, engine, alpha, beta,
+                            _regrouped=True)
+    else:
+        res = contract_pair(a2, la2, b2, lb2, lc2, conj_a, conj_b, None, engine, alpha, 0.0,
+                            _regrouped=True)
+    final = permute_contiguous(res, [lc2.index(l) for l in lc])
+    rc = _lib.load().qb_permute(_lib.desc(final), _lib.desc(out), 0, _lib.stream_ptr())
+    _lib.check(rc, "qb_permute")
     return out
 
 

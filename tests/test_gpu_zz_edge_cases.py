@@ -318,3 +318,35 @@ def test_dmrg2_all_four_dtypes_preserved(dtype, tol):
     d.solve(max_sweeps=3)
     assert {str(a.dtype) for a in d.state} == {dtype}
     assert abs(d.energy - e0) < tol * abs(e0)
+
+
+def test_contraction_with_more_than_12_interleaved_modes_regroups():
+    """A pair whose free / contracted axes interleave so that a group keeps
+    more than 12 non-mergeable modes (rank-26 operands of compression drivers,
+    found by the reference's test_tn1d/test_compress.py on device tensors) is
+    regrouped once with the permute kernel instead of being refused."""
+    from quimb_b200.contract import contract_pair, permute_contiguous
+    rng = np.random.default_rng(5)
+    r = 26
+    x = rng.standard_normal((2,) * r)
+    y = rng.standard_normal((2,) * 14)
+    la = list(range(r))
+    k = list(range(0, r, 2))[:13]                  # every other axis of x is contracted
+    lb = k + [40]
+    lc = [l for l in la if l not in k] + [40]
+    perm = rng.permutation(len(lc))
+    lc = [lc[p] for p in perm]
+    ref = np.einsum(x, la, y, lb, lc, optimize=True)
+    out = contract_pair(qb.asarray(x).t, la, qb.asarray(y).t, lb, lc)
+    np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=1e-11, atol=1e-11)
+    # into a caller-provided output, accumulating
+    prev = rng.standard_normal(ref.shape)
+    o = qb.asarray(prev.copy()).t
+    contract_pair(qb.asarray(x).t, la, qb.asarray(y).t, lb, lc, out=o, alpha=2.0, beta=1.0)
+    np.testing.assert_allclose(o.cpu().numpy(), 2.0 * ref + prev, rtol=1e-11, atol=1e-11)
+    # the multi-pass permutation on its own
+    z = rng.standard_normal((2,) * 22)
+    order = [int(p) for p in rng.permutation(22)]
+    got = permute_contiguous(qb.asarray(z).t, order)
+    assert got.is_contiguous()
+    np.testing.assert_array_equal(got.cpu().numpy(), np.transpose(z, order))
