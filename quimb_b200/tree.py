@@ -379,7 +379,14 @@ def _optimal_ssa(inputs, output, size_dict):
     return ssa
 
 
-def _hq_candidates(inputs, output, size_dict, trials=64, subtree_size=8):
+# multiply-add equivalents charged per intermediate element by the 'combo'
+# objective of the device-targeted searches: a complex128 element written and
+# read back costs 2 x 16 B / (HBM bytes/s) against 8 flop / (fp64 flop/s) per
+# multiply-add, about 14 on a B200 (7.7 TB/s, 25-33 TFLOP/s measured)
+DEVICE_COMBO = ("combo", 16.0)
+
+
+def _hq_candidates(inputs, output, size_dict, trials=64, subtree_size=8, minimize="flops"):
     """Refined candidate trees over the rank-simplified network: noisy greedy
     (good for shallow / tree-like networks) and the spectral sweep (good for
     deep circuits and strips), each polished by simulated annealing over tree
@@ -396,9 +403,10 @@ def _hq_candidates(inputs, output, size_dict, trials=64, subtree_size=8):
     starts = [_random_greedy_ssa(red, output, size_dict, trials=trials),
               treeopt.spectral_ssa(red, output, size_dict)]
     for k, sub in enumerate(starts):
-        sub = treeopt.reconfigure(red, output, size_dict, sub, subtree_size=6)
-        sub = treeopt.anneal(red, output, size_dict, sub, sweeps=300, seed=k)
-        sub = treeopt.reconfigure(red, output, size_dict, sub, subtree_size=subtree_size)
+        sub = treeopt.reconfigure(red, output, size_dict, sub, subtree_size=6, minimize=minimize)
+        sub = treeopt.anneal(red, output, size_dict, sub, sweeps=300, seed=k, minimize=minimize)
+        sub = treeopt.reconfigure(red, output, size_dict, sub, subtree_size=subtree_size,
+                                  minimize=minimize)
         c, w = treeopt.tree_stats(red, output, size_dict, sub)
         yield c, w, treeopt.compose_ssa(prefix, n, ids, sub)
 
@@ -408,11 +416,13 @@ def _hq_ssa(inputs, output, size_dict):
 
 
 def find_sliced_tree(inputs, output, size_dict, target_width, min_slices=None,
-                     optimize="auto-hq", subtree_size=8):
+                     optimize="auto-hq", subtree_size=8, minimize=DEVICE_COMBO):
     """Tree + sliced indices found TOGETHER for a memory target (the job of
     cotengra's ``slicing_reconf_opts``): candidates from ``optimize`` are each
     sliced index by index with the tree of the sliced network re-optimised
     after every cut, and the cheapest total (cost per slice x slices) wins.
+    ``minimize`` defaults to the device-targeted objective (multiply-adds + 16 x
+    intermediate elements: most big steps of a circuit tree are HBM-bound).
     Returns ``(Tree over the sliced inputs, sliced_inds)``; ``min_slices``
     (e.g. the world size) adds slices with :func:`find_slices` when the width
     target alone gives fewer.  Host-only."""
@@ -420,16 +430,21 @@ def find_sliced_tree(inputs, output, size_dict, target_width, min_slices=None,
     inputs = [tuple(t) for t in inputs]
     output = tuple(output)
     if optimize == "auto-hq":
-        cands = [c[2] for c in _hq_candidates(inputs, output, size_dict, subtree_size=subtree_size)]
+        cands = [c[2] for c in _hq_candidates(inputs, output, size_dict, subtree_size=subtree_size,
+                                              minimize=minimize)]
     else:
         cands = [[(i, j) for i, j, _, _ in find_tree(inputs, output, size_dict, optimize).steps]]
     best = None
     for ssa in cands:
         ssa2, sl = treeopt.slice_and_reconfigure(inputs, output, size_dict, ssa,
-                                                 target_width, subtree_size=subtree_size)
+                                                 target_width, subtree_size=subtree_size,
+                                                 minimize=minimize)
         s = set(sl)
         red = [tuple(ix for ix in t if ix not in s) for t in inputs]
         c, w = treeopt.tree_stats(red, output, size_dict, ssa2)
+        sw = treeopt._size_weight(minimize)
+        if sw:
+            c = math.log2(2.0 ** c + sw * 2.0 ** treeopt.tree_traffic(red, output, size_dict, ssa2) / 3)
         tot = c + sum(math.log2(size_dict[ix]) for ix in sl)
         if best is None or (w > target_width, tot) < best[0]:
             best = ((w > target_width, tot), ssa2, sl, red)

@@ -22,7 +22,7 @@ Trees are exchanged as SSA step lists like everywhere in ``tree.py``.
 import math
 import random
 
-__all__ = ["reconfigure", "anneal", "slice_and_reconfigure", "tree_stats",
+__all__ = ["reconfigure", "anneal", "slice_and_reconfigure", "tree_stats", "tree_traffic",
            "spectral_ssa", "growth_ssa", "simplify_inputs", "compose_ssa"]
 
 
@@ -295,8 +295,7 @@ def reconfigure(inputs, output, size_dict, ssa, subtree_size=8, max_rounds=8,
     if len(inputs) < 3:
         return list(ssa)
     bt = _BinTree(inputs, output, size_dict, ssa)
-    sw = 64.0 if minimize == "combo" else 0.0
-    _reconfigure_bt(bt, subtree_size, max_rounds, sw, seed, max_time)
+    _reconfigure_bt(bt, subtree_size, max_rounds, _size_weight(minimize), seed, max_time)
     return bt.to_ssa()
 
 
@@ -305,6 +304,18 @@ def tree_stats(inputs, output, size_dict, ssa):
     bt = _BinTree(inputs, output, size_dict, ssa)
     c = bt.total_cost()
     return (math.log2(c) if c > 0 else 0.0), bt.width()
+
+
+def tree_traffic(inputs, output, size_dict, ssa):
+    """log2 of the elements moved by the pairwise executor: every node reads
+    its two operands and writes its result (the algorithmic bytes of a tree
+    are this times the item size)."""
+    bt = _BinTree(inputs, output, size_dict, ssa)
+    lsize = bt.bits.lsize
+    tot = 0.0
+    for k, (i, j) in bt.children.items():
+        tot += 2.0 ** lsize(bt.legs[i]) + 2.0 ** lsize(bt.legs[j]) + 2.0 ** lsize(bt.legs[k])
+    return math.log2(tot) if tot > 0 else 0.0
 
 
 def _greedy_slices(bt, target_width, fixed=(), max_new=None):
@@ -384,9 +395,8 @@ def slice_and_reconfigure(inputs, output, size_dict, ssa, target_width,
             left = None if max_time is None else max(1.0, max_time - (time.time() - t0))
             if anneal_sweeps and len(inputs) >= 4:
                 _anneal_bt(bt, anneal_sweeps, 0.5, 0.02, max(target_width, wprev - 1.0),
-                           seed=len(sliced), max_time=left)
-            _reconfigure_bt(bt, subtree_size, max_rounds,
-                            64.0 if minimize == "combo" else 0.0, None, left)
+                           seed=len(sliced), max_time=left, size_weight=_size_weight(minimize))
+            _reconfigure_bt(bt, subtree_size, max_rounds, _size_weight(minimize), None, left)
             ssa = bt.to_ssa()
             bt = _BinTree(red_inputs, red_output, size_dict, ssa)
         width = wprev = bt.width()
@@ -573,7 +583,7 @@ def spectral_ssa(inputs, output, size_dict):
 
 # ------------------------------------------------------ simulated annealing --
 def _anneal_bt(bt, sweeps=200, t_start=1.0, t_end=0.02, target_width=None, seed=0,
-               max_time=None):
+               max_time=None, size_weight=0.0):
     """Metropolis over local tree rotations (the move set of cotengra's
     ``simulated_anneal_tree``): at a node p = (l, r) with l = (a, b) the
     sibling r is exchanged with a or b, which changes only the contraction
@@ -586,17 +596,20 @@ def _anneal_bt(bt, sweeps=200, t_start=1.0, t_end=0.02, target_width=None, seed=
     t0 = time.time()
 
     def step_cost(li, lj, legs_out):
-        c = lsize(li | lj)
-        if target_width is not None:
-            over = lsize(legs_out) - target_width
-            if over > 0:
-                c += 2.0 * over
+        """linear cost of one contraction: multiply-adds + size_weight x the
+        elements of its result (written once, read once by its consumer)."""
+        c = 2.0 ** lsize(li | lj)
+        so = lsize(legs_out)
+        if size_weight:
+            c += size_weight * 2.0 ** so
+        if target_width is not None and so > target_width:
+            c *= 4.0 ** (so - target_width)
         return c
 
     def tree_score():
         tot = 0.0
         for k, (i, j) in bt.children.items():
-            tot += 2.0 ** step_cost(bt.legs[i], bt.legs[j], bt.legs[k])
+            tot += step_cost(bt.legs[i], bt.legs[j], bt.legs[k])
         return tot
 
     cur = tree_score()
@@ -622,8 +635,8 @@ def _anneal_bt(bt, sweeps=200, t_start=1.0, t_end=0.02, target_width=None, seed=
             old_l = bt.legs[l]
             new_l, new_h = bt._merged_legs(la, lr, bt.hcnt[a], bt.hcnt[r])
             lp = bt.legs[p]
-            old = 2.0 ** step_cost(la, lb, old_l) + 2.0 ** step_cost(old_l, lr, lp)
-            new = 2.0 ** step_cost(la, lr, new_l) + 2.0 ** step_cost(new_l, lb, lp)
+            old = step_cost(la, lb, old_l) + step_cost(old_l, lr, lp)
+            new = step_cost(la, lr, new_l) + step_cost(new_l, lb, lp)
             if new > old:
                 d = math.log2(new) - math.log2(old)
                 if rng.random() >= math.exp(-d / T):
@@ -651,12 +664,24 @@ def _anneal_bt(bt, sweeps=200, t_start=1.0, t_end=0.02, target_width=None, seed=
     return best
 
 
+def _size_weight(minimize):
+    """'flops' -> 0; 'combo' -> 64 (cotengra's convention: multiply-adds +
+    64 x intermediate elements); ('combo', w) -> w."""
+    if minimize in (None, "flops"):
+        return 0.0
+    if minimize == "combo":
+        return 64.0
+    if isinstance(minimize, (tuple, list)) and minimize[0] == "combo":
+        return float(minimize[1])
+    raise ValueError(f"unknown objective {minimize!r}")
+
+
 def anneal(inputs, output, size_dict, ssa, sweeps=200, t_start=1.0, t_end=0.02,
-           target_width=None, seed=0, max_time=None):
+           target_width=None, seed=0, max_time=None, minimize="flops"):
     """Simulated annealing of an SSA tree (see :func:`_anneal_bt`), followed by
     nothing else -- combine with :func:`reconfigure`.  Returns new SSA steps."""
     if len(inputs) < 4:
         return list(ssa)
     bt = _BinTree(inputs, output, size_dict, ssa)
-    _anneal_bt(bt, sweeps, t_start, t_end, target_width, seed, max_time)
+    _anneal_bt(bt, sweeps, t_start, t_end, target_width, seed, max_time, _size_weight(minimize))
     return bt.to_ssa()

@@ -7,7 +7,7 @@ import pytest
 
 import quimb_b200 as qb
 from oracle import contract_np as cn
-from tests.circuit_util import random_circuit_amplitude
+from tests.circuit_util import random_circuit_amplitude, random_grid_circuit_amplitude
 
 pytestmark = pytest.mark.gpu
 
@@ -68,3 +68,22 @@ def test_grid_circuit_amplitude_matches_statevector(Lx, Ly, depth, gate):
             Lx, Ly, depth, seed=3, bits=bits, gate=gate)
         out = qb.array_contract(arrays, inputs, output, optimize="greedy")
         assert abs(complex(out.item()) - amp) <= 1e-10 * max(1.0, abs(amp))
+
+
+def test_contract_sliced_with_tree_and_slices_found_together():
+    """dist.contract_sliced(optimize='auto-hq', target_width=...): tree and
+    sliced indices come from find_sliced_tree (slicing interleaved with
+    annealing / reconfiguration), every rank executes its share of the
+    slices with the tree of the sliced network; the parts sum to the
+    state-vector amplitude."""
+    from quimb_b200 import dist
+    arrays, inputs, output, amp = random_grid_circuit_amplitude(3, 3, 10, seed=7)
+    dev = [qb.asarray(a) for a in arrays]
+    total, seen = 0.0, []
+    for r in range(2):
+        part, mine = dist.contract_sliced(dev, inputs, output, optimize="auto-hq", target_width=6,
+                                          rank=r, world_size=2, reduce=False)
+        seen += list(mine)
+        total += complex(part.item())
+    assert sorted(seen) == list(range(len(seen))) and len(seen) >= 2
+    assert abs(total - amp) < 1e-12

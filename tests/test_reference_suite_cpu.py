@@ -110,16 +110,12 @@ def _run(tmp_path, rel, kexpr, deselect):
     dst = os.path.join("test_tensor", rel)
     cmd = [sys.executable, "-m", "pytest", str(dst), "-q", "-p", "no:cacheprovider",
            "--timeout", "300", "--tb=line", "-W", "ignore"]
-    if kexpr:
-        cmd += ["-k", kexpr]
+    # deselect by test-function name (the part after the last '::')
+    parts = [f"({kexpr})"] if kexpr else []
+    parts += [f"not {sfx.split('::')[-1]}" for sfx, _ in deselect]
+    if parts:
+        cmd += ["-k", " and ".join(parts)]
     env = dict(os.environ, PYTHONPATH="")
-    # collect once to resolve the deselect suffixes to node ids
-    if deselect:
-        out = subprocess.run(cmd + ["--collect-only"], cwd=work, env=env, capture_output=True,
-                             text=True, timeout=600).stdout
-        for line in out.splitlines():
-            if "::" in line and any(sfx in line for sfx, _ in deselect):
-                cmd += ["--deselect", line.strip()]
     return subprocess.run(cmd, cwd=work, env=env, capture_output=True, text=True, timeout=1500)
 
 
