@@ -4,7 +4,7 @@ complex128).  Not the driver's bench.py contract (that is configs[1]); run
 under gpurun:
 
   python tools/bench_circuit.py [--Lx 5] [--Ly 5] [--depth 16] [--target-width 28]
-                                [--max-slices 64] [--graph] [--out gpurun_out/x.json]
+                                [--max-slices 64] [--out gpurun_out/x.json]
   torchrun --nproc-per-node 8 tools/bench_circuit.py --Lx 6 --Ly 6 --depth 24 \\
            --target-width 32 --max-slices 64
 
@@ -36,7 +36,6 @@ def main():
     ap.add_argument("--target-width", type=int, default=28)
     ap.add_argument("--max-slices", type=int, default=64)
     ap.add_argument("--reps", type=int, default=1)
-    ap.add_argument("--graph", action="store_true", help="replay each slice from a CUDA graph")
     ap.add_argument("--out", default=None)
     args = ap.parse_args()
     import numpy as np
