@@ -88,6 +88,18 @@ def contract_sliced(arrays, inputs, output, sliced_inds=None, optimize="auto",
         else:
             full_tree = find_tree(inputs, tuple(output), sd, optimize)
             sliced_inds = find_slices(full_tree, target_width, min_slices)[0]
+    if (rank is None and world_size is None and torch.distributed.is_available()
+            and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1):
+        # every rank searched for itself (deterministically: tree.py canonicalises
+        # index names); rank 0's choice is nevertheless the one all ranks use
+        from .tree import Tree
+        steps = [(i, j) for i, j, _, _ in optimize.steps] if isinstance(optimize, Tree) else None
+        box = [(tuple(sliced_inds), steps)]
+        torch.distributed.broadcast_object_list(box, src=0)
+        sliced_inds, steps0 = box[0]
+        if steps0 is not None and isinstance(optimize, Tree) and steps0 != steps:
+            red = [tuple(ix for ix in t if ix not in set(sliced_inds)) for t in inputs]
+            optimize = Tree(red, tuple(output), optimize.size_dict, steps0)
     sliced = tuple(sliced_inds)
     if any(ix in output for ix in sliced):
         raise ValueError("cannot slice an output index")

@@ -427,8 +427,9 @@ def find_sliced_tree(inputs, output, size_dict, target_width, min_slices=None,
     (e.g. the world size) adds slices with :func:`find_slices` when the width
     target alone gives fewer.  Host-only."""
     from . import treeopt
-    inputs = [tuple(t) for t in inputs]
-    output = tuple(output)
+    orig_inputs = [tuple(t) for t in inputs]
+    orig_output, orig_sizes = tuple(output), size_dict
+    inputs, output, size_dict, names = _canonical(orig_inputs, orig_output, size_dict)
     if optimize == "auto-hq":
         cands = [c[2] for c in _hq_candidates(inputs, output, size_dict, subtree_size=subtree_size,
                                               minimize=minimize)]
@@ -453,14 +454,36 @@ def find_sliced_tree(inputs, output, size_dict, target_width, min_slices=None,
     if min_slices is not None and math.prod(size_dict[ix] for ix in sl) < min_slices:
         more = find_slices(tr, None, -(-min_slices // math.prod(size_dict[ix] for ix in sl)))[0]
         sl = tuple(sl) + tuple(more)
-        s = set(sl)
-        red = [tuple(ix for ix in t if ix not in s) for t in inputs]
-        tr = Tree(red, output, size_dict, ssa)
-    return tr, tuple(sl)
+    # back to the caller's index names
+    sl = tuple(names[ix] for ix in sl)
+    s = set(sl)
+    red = [tuple(ix for ix in t if ix not in s) for t in orig_inputs]
+    return Tree(red, orig_output, orig_sizes, ssa), sl
+
+
+def _canonical(inputs, output, size_dict):
+    """Index names -> integers in first-appearance order.  The finders keep
+    indices in sets; with string names their iteration order depends on the
+    process's hash seed, and the ranks of a multi-GPU run (which each find the
+    tree and the slices for themselves) must take identical decisions."""
+    table = {}
+    for t in inputs:
+        for ix in t:
+            table.setdefault(ix, len(table))
+    for ix in output:
+        table.setdefault(ix, len(table))
+    cin = [tuple(table[ix] for ix in t) for t in inputs]
+    cout = tuple(table[ix] for ix in output)
+    csz = {table[ix]: size_dict[ix] for ix in table}
+    names = list(table)
+    return cin, cout, csz, names
 
 
 def find_tree(inputs, output, size_dict, optimize="auto"):
     n = len(inputs)
+    orig = (inputs, output, size_dict)
+    if isinstance(optimize, (str, type(None))) and n > 1:
+        inputs, output, size_dict, _ = _canonical(inputs, output, size_dict)
     if hasattr(optimize, "get_path"):          # cotengra.ContractionTree
         ssa = linear_to_ssa(optimize.get_path(), n)
     elif isinstance(optimize, Tree):
@@ -485,7 +508,7 @@ def find_tree(inputs, output, size_dict, optimize="auto"):
         ssa = _greedy_ssa(inputs, output, size_dict)
     else:
         raise ValueError(f"unknown optimize strategy {optimize!r}")
-    return Tree(inputs, output, size_dict, ssa)
+    return Tree(orig[0], orig[1], orig[2], ssa)
 
 
 # --------------------------------------------------------------- executor ---

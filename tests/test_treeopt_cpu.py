@@ -191,3 +191,30 @@ def test_anneal_keeps_value_and_repairs_a_bad_tree():
     full = treeopt.compose_ssa(prefix, len(inputs), ids, good)
     out, _ = _run_ssa(inputs, output, sizes, full, arrays)
     assert abs(complex(out) - amp) < 1e-10
+
+
+def test_tree_search_does_not_depend_on_the_hash_seed():
+    """Ranks of a multi-GPU run each search for the tree and the slices; with
+    string index names kept in sets the result would follow PYTHONHASHSEED."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = "\n".join([
+        "import sys; sys.path.insert(0, %r)" % root,
+        "from tests.circuit_util import random_grid_circuit_amplitude",
+        "from quimb_b200 import tree",
+        "a, inputs, output, _ = random_grid_circuit_amplitude(3, 3, 10, seed=3, dense=False)",
+        "sd = {ix: 2 for t in inputs for ix in t}",
+        "tr, sl = tree.find_sliced_tree(inputs, output, sd, 6)",
+        "r = tree.find_tree(inputs, output, sd, 'random-greedy')",
+        "print(sl, repr(tr.steps), repr(r.steps))",
+    ])
+    outs = set()
+    for seed in ("0", "1", "12345"):
+        env = dict(os.environ, PYTHONHASHSEED=seed)
+        res = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True,
+                             timeout=600)
+        assert res.returncode == 0, res.stderr[-2000:]
+        outs.add(res.stdout)
+    assert len(outs) == 1
