@@ -31,3 +31,7 @@ QB_ENGINE=stream timeout 600 python tools/bench_circuit.py --Lx 5 --Ly 5 --depth
     --out $out/${tag}_circuit_5x5_d16_stream.json >> $out/${tag}_circuit.log 2>&1
 QB_ENGINE=stream timeout 900 python tools/bench_circuit.py --Lx 6 --Ly 6 --depth 24 --target-width 31 --max-slices 2 \
     --out $out/${tag}_circuit_6x6_d24_partial_stream.json >> $out/${tag}_circuit.log 2>&1
+# 6. the MPO steps of the DMRG matvec are (w d = 10)-deep, 10-wide contractions over 2^21 rows:
+#    same sweep with the streaming engine taking every eligible step
+QB_ENGINE=stream timeout 900 python tools/bench_dmrg.py --L 30 --chi 1024 --no-cpu --left-sweep > $out/${tag}_dmrg_L30_stream.log 2>&1
+tail -2 $out/${tag}_dmrg_L30.log $out/${tag}_dmrg_L30_stream.log
