@@ -101,8 +101,14 @@ class Array:
             return materialize(self).t
         return self.t
 
-    def item(self):
-        v = self.t.item()
+    def item(self, *args):
+        """numpy's ``item()`` / ``item(flat_index)`` / ``item(i, j, ...)``"""
+        t = self.t
+        if len(args) == 1 and not isinstance(args[0], tuple):
+            t = t.reshape(-1)[int(args[0])]
+        elif args:
+            t = t[tuple(args[0]) if len(args) == 1 else tuple(int(a) for a in args)]
+        v = t.item()
         return v.conjugate() if self.cj else v
 
     def __float__(self):
@@ -215,19 +221,36 @@ class Array:
     def clone(self):
         return self.copy()
 
+    @staticmethod
+    def _index(idx):
+        """unwrap device index arrays; numpy index arrays go as tensors"""
+        def one(i):
+            if isinstance(i, Array):
+                return i.t
+            if isinstance(i, np.ndarray):
+                return torch.as_tensor(np.ascontiguousarray(i))
+            return i
+        if isinstance(idx, tuple):
+            return tuple(one(i) for i in idx)
+        if isinstance(idx, list) and any(isinstance(i, (Array, np.ndarray)) for i in idx):
+            return tuple(one(i) for i in idx)
+        return one(idx)
+
     def __getitem__(self, idx):
-        if isinstance(idx, Array):
-            idx = idx.t
-        elif isinstance(idx, tuple):
-            idx = tuple(i.t if isinstance(i, Array) else i for i in idx)
-        return Array(self.t[idx], self.cj)
+        return Array(self.t[self._index(idx)], self.cj)
 
     def __setitem__(self, idx, val):
         if self.cj:
             raise ValueError("cannot assign into a lazily conjugated view")
         if isinstance(val, Array):
             val = val.resolve()
-        self.t[idx] = val
+        elif isinstance(val, np.ndarray):
+            val = torch.as_tensor(np.ascontiguousarray(val), device=self.t.device)
+        if isinstance(val, torch.Tensor) and val.dtype != self.t.dtype:
+            if val.is_complex() and not self.t.is_complex():
+                val = val.real                      # numpy: discards the imaginary part
+            val = val.to(self.t.dtype)
+        self.t[self._index(idx)] = val
 
     def __iter__(self):
         for i in range(self.t.shape[0]):
@@ -239,7 +262,7 @@ class Array:
         if isinstance(other, Array):
             b = other.resolve()
         elif isinstance(other, np.ndarray):
-            b = torch.as_tensor(other, device=a.device)
+            b = torch.as_tensor(np.ascontiguousarray(other), device=a.device)
         elif isinstance(other, (numbers.Number, np.generic)):
             b = other.item() if isinstance(other, np.generic) else other
         elif isinstance(other, torch.Tensor):
@@ -282,6 +305,25 @@ class Array:
     def __le__(self, o): return self._order(o, torch.le)
     def __gt__(self, o): return self._order(o, torch.gt)
     def __ge__(self, o): return self._order(o, torch.ge)
+    def _logic(self, o, fn):
+        def f(a, b):
+            dev = a.device if isinstance(a, torch.Tensor) else b.device
+            return fn(torch.as_tensor(a, device=dev), torch.as_tensor(b, device=dev))
+        return self._bin(o, f)
+
+    def __or__(self, o): return self._logic(o, torch.logical_or)
+    __ror__ = __or__
+    def __and__(self, o): return self._logic(o, torch.logical_and)
+    __rand__ = __and__
+    def __xor__(self, o): return self._logic(o, torch.logical_xor)
+    __rxor__ = __xor__
+    def __invert__(self): return Array(torch.logical_not(self.resolve()))
+
+    def __format__(self, spec):
+        if self.t.dim() == 0 and spec:
+            return format(self.item(), spec)
+        return repr(self) if spec else str(self)
+
     def __eq__(self, o): return self._bin(o, torch.eq)
     def __ne__(self, o): return self._bin(o, torch.ne)
     __hash__ = None
@@ -318,17 +360,17 @@ class Array:
         return matmul(asarray(other), self)
 
     # reductions used by quimb on arrays directly
-    def sum(self, axis=None, **kw):
+    def sum(self, axis=None, keepdims=False, **kw):
         from .ops import sum as _sum
-        return _sum(self, axis=axis, **kw)
+        return _sum(self, axis=axis, keepdims=keepdims)
 
-    def max(self, axis=None):
+    def max(self, axis=None, keepdims=False):
         from .ops import max as _max
-        return _max(self, axis=axis)
+        return _max(self, axis=axis, keepdims=keepdims)
 
-    def min(self, axis=None):
+    def min(self, axis=None, keepdims=False):
         from .ops import min as _min
-        return _min(self, axis=axis)
+        return _min(self, axis=axis, keepdims=keepdims)
 
     def all(self):
         return bool(self.t.all().item())

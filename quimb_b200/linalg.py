@@ -474,3 +474,11 @@ def expm(x):
     construction (``isometrize(method="exp")``, Trotter terms), not on the
     contraction hot path."""
     return Array(torch.linalg.matrix_exp(ops.asarray(x).resolve()))
+
+
+def eig(x):
+    """General (non-Hermitian) eigendecomposition ``(w, v)``.  Library forward
+    (torch / cuSOLVER geev; belief-propagation gauging of quimb calls it on
+    small message matrices): not on the contraction hot path."""
+    w, v = torch.linalg.eig(ops.asarray(x).resolve())
+    return Array(w), Array(v)

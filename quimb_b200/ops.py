@@ -396,24 +396,34 @@ def abs(x):  # noqa: A001
 absolute = abs
 
 
-def sum(x, axis=None, **kw):  # noqa: A001
-    t = _t(x)
-    return Array(t.sum() if axis is None else t.sum(dim=axis))
+def _reduce(x, axis, keepdims, full, along):
+    t = _t(asarray(x))
+    if axis is None:
+        out = full(t)
+        if keepdims:
+            out = out.reshape((1,) * t.ndim)
+        return Array(out)
+    return Array(along(t, axis, bool(keepdims)))
 
 
-def max(x, axis=None):  # noqa: A001
-    t = _t(x)
-    return Array(t.max() if axis is None else t.max(dim=axis).values)
+def sum(x, axis=None, keepdims=False, **kw):  # noqa: A001
+    return _reduce(x, axis, keepdims, lambda t: t.sum(),
+                   lambda t, ax, kd: t.sum(dim=ax, keepdim=kd))
 
 
-def min(x, axis=None):  # noqa: A001
-    t = _t(x)
-    return Array(t.min() if axis is None else t.min(dim=axis).values)
+def max(x, axis=None, keepdims=False):  # noqa: A001
+    return _reduce(x, axis, keepdims, lambda t: t.max(),
+                   lambda t, ax, kd: t.amax(dim=ax, keepdim=kd))
 
 
-def mean(x, axis=None):
-    t = _t(x)
-    return Array(t.mean() if axis is None else t.mean(dim=axis))
+def min(x, axis=None, keepdims=False):  # noqa: A001
+    return _reduce(x, axis, keepdims, lambda t: t.min(),
+                   lambda t, ax, kd: t.amin(dim=ax, keepdim=kd))
+
+
+def mean(x, axis=None, keepdims=False):
+    return _reduce(x, axis, keepdims, lambda t: t.mean(),
+                   lambda t, ax, kd: t.mean(dim=ax, keepdim=kd))
 
 
 def all(x):  # noqa: A001
@@ -541,7 +551,6 @@ def sort(x, axis=-1):
     return Array(torch.sort(_t(asarray(x)), dim=axis).values)
 
 
-prod = _wrap(torch.prod)
 outer = _wrap(torch.outer)
 
 
@@ -645,3 +654,8 @@ def tril(x, k=0):
 
 def triu(x, k=0):
     return Array(torch.triu(_t(asarray(x)), diagonal=k))
+
+
+def prod(x, axis=None, keepdims=False):
+    return _reduce(x, axis, keepdims, lambda t: t.prod(),
+                   lambda t, ax, kd: t.prod(dim=ax, keepdim=kd))

@@ -214,3 +214,29 @@ def test_numpy_signature_helpers():
     a = rng.standard_normal((4, 4)) + 1j * rng.standard_normal((4, 4))
     np.testing.assert_allclose(_np(qb.linalg.expm(qb.asarray(a))), sla.expm(a), atol=1e-12)
     np.testing.assert_allclose(_np(qb.scipy.linalg.expm(qb.asarray(a.real))), sla.expm(a.real), atol=1e-12)
+
+
+def test_reductions_keepdims_and_eig():
+    """numpy's ``keepdims`` on sum / max / min / mean / prod (quimb's belief
+    propagation normalises messages with it) and the general ``linalg.eig``."""
+    rng = np.random.default_rng(8)
+    x = rng.standard_normal((3, 4, 5))
+    X = qb.asarray(x)
+    for name in ("sum", "max", "min", "mean", "prod"):
+        f, g = getattr(qb, name), getattr(np, name)
+        for ax in (None, 0, -1, (0, 2)):
+            for kd in (False, True):
+                if name in ("prod",) and isinstance(ax, tuple):
+                    continue
+                got = f(X, axis=ax, keepdims=kd)
+                ref = g(x, axis=ax, keepdims=kd)
+                assert tuple(got.shape) == np.shape(ref), (name, ax, kd)
+                np.testing.assert_allclose(_np(got), ref, rtol=1e-12)
+    np.testing.assert_allclose(_np(X.sum(axis=-1, keepdims=True)), x.sum(axis=-1, keepdims=True))
+    y = X / qb.sum(qb.abs(X), axis=-1, keepdims=True)
+    np.testing.assert_allclose(_np(y), x / np.abs(x).sum(axis=-1, keepdims=True), rtol=1e-13)
+    a = rng.standard_normal((6, 6))
+    w, v = qb.linalg.eig(qb.asarray(a))
+    w, v = _np(w), _np(v)
+    np.testing.assert_allclose(a @ v, v * w, atol=1e-10)
+    np.testing.assert_allclose(np.sort_complex(w), np.sort_complex(np.linalg.eigvals(a)), atol=1e-10)
