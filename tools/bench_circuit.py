@@ -75,7 +75,10 @@ def main():
             return x
         return x[tuple(fix[ix] if ix in fix else slice(None) for ix in t)]
 
+    from quimb_b200 import treeopt
+    elems_slice = 2.0 ** treeopt.tree_traffic(tr.inputs, tr.output, sd, [(i, j) for i, j, _, _ in tr.steps])
     res = {"config": f"{args.Lx}x{args.Ly} depth {args.depth} complex128", "n_gpus": world,
+           "algorithmic_gbytes_per_slice": round(16.0 * elems_slice / 1e9, 3),
            "tensors": len(inputs), "log2_width": tr.contraction_width(),
            "n_sliced": len(sliced), "log2_macs_per_slice": round(math.log2(macs_slice), 2),
            "find_seconds": round(t_find, 1), "runs": []}
@@ -103,6 +106,8 @@ def main():
         flops = 8.0 * macs_slice * done                  # complex multiply-add = 8 real flop
         res["runs"].append({"seconds": dt, "slices_done": done, "launches": qb.launch_count() - n0,
                             "tflops": flops / dt / 1e12,
+                            # operands read + results written by every tree node, complex128
+                            "algorithmic_GBps": 16.0 * elems_slice * done / dt / 1e9,
                             "seconds_all_slices_extrapolated": dt * n_slices / done})
     res["partial"] = len(units) < n_slices
     res["value"] = [val.real, val.imag]
