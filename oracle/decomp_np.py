@@ -345,6 +345,71 @@ def eigh_truncated(x, cutoff=-1.0, cutoff_mode=4, max_bond=-1, absorb=0, renorm=
     return left, sv, right
 
 
+_ABSORB_TRANSPOSE = {get_U_sVH: get_Us_VH, get_U: get_VH, get_sVH: get_Us,
+                     get_Us_VH: get_U_sVH, get_VH: get_U, get_Us: get_sVH}
+
+
+def cholesky_regularized(x, absorb=get_Usq_sqVH, shift=True):
+    """decomp.py:2245-2322 (numba :2325-2335): (L, None, L^H) of a positive
+    definite matrix; ``shift`` True -> eps * trace on the diagonal, 'auto' ->
+    retry with it after a failure, float -> relative shift."""
+    absorb = ABSORB_MAP[absorb]
+
+    def run(sh):
+        L = np.linalg.cholesky(with_diag_shift(x, sh))
+        if absorb == get_Usq:
+            return L, None, None
+        if absorb == get_sqVH:
+            return None, None, _dag(L)
+        if absorb == get_Usq_sqVH:
+            return L, None, _dag(L)
+        raise ValueError(f"Invalid absorb={absorb} in cholesky_regularized.")
+    if isinstance(shift, str) and shift == "auto":
+        try:
+            return run(0.0)
+        except np.linalg.LinAlgError:
+            return run(-1.0)
+    return run({False: 0.0, True: -1.0}.get(shift, shift))
+
+
+def qr_via_cholesky(x, absorb=get_Us_VH, shift=True):
+    """decomp.py:2359-2424: LQ-like split x = L Q from the Cholesky factor of
+    x x^H (QR-like through the transpose)."""
+    import scipy.linalg as sla
+    absorb = ABSORB_MAP[absorb]
+    if absorb in (get_U_sVH, get_U, get_sVH):
+        transposed = True
+    elif absorb in (get_Us_VH, get_Us, get_VH):
+        transposed = False
+    else:
+        raise ValueError(f"Invalid absorb mode for qr_via_cholesky: {absorb}")
+    if transposed:
+        absorb = _ABSORB_TRANSPOSE[absorb]
+        xT = x.T
+        xx = xT @ x.conj()
+        x = xT
+    else:
+        xx = x @ x.conj().T
+    L, _, _ = cholesky_regularized(xx, absorb=get_Usq, shift=shift)
+    right = sla.solve_triangular(L, x, lower=True) if absorb != get_Us else None
+    left = L if absorb != get_VH else None
+    if transposed:
+        left, right = (None if right is None else right.T), (None if left is None else left.T)
+    return left, None, right
+
+
+def polar_right(x):
+    """decomp.py:2673-2700: x = U P, U isometric, P positive semi-definite."""
+    W, s, VH = np.linalg.svd(x, full_matrices=False)
+    return W @ VH, None, _dag(VH) @ (s[:, None] * VH)
+
+
+def polar_left(x):
+    """decomp.py:2703-2730: x = P U."""
+    W, s, VH = np.linalg.svd(x, full_matrices=False)
+    return (W * s[None, :]) @ _dag(W), None, W @ VH
+
+
 def svd_rand_truncated(x, max_bond, absorb=0, oversample=10, num_iterations=2,
                        right=None, seed=None):
     """decomp.py:1689-1861 with method_lorthog='qr', method_reduced='svd'."""

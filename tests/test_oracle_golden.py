@@ -334,3 +334,31 @@ def test_dmrg1_oracle_matches_reference_energies(golden_mps):
         assert abs(d.energy - r["energies"][-1]) < 50 * r["tol"]
         assert abs(d.energy - r["exact"]) < 1e-6
         assert abs(r["energies"][-1] - r["exact"]) < 1e-6     # the reference itself
+
+
+def test_cholesky_qr_cholesky_polar_oracle_match_reference(golden_decomp3):
+    """oracle restatements of 'cholesky', 'qr:cholesky' and the polar splits
+    pinned on the reference's outputs (tests/golden/decomp3.*); these factors
+    are unique, so they are compared directly."""
+    import warnings
+    data, meta = golden_decomp3
+
+    def check(res, c, atol):
+        left, sv, right = res
+        assert sv is None and [left is not None, False, right is not None] == c["has"], c
+        if left is not None:
+            np.testing.assert_allclose(left, data[f"{c['key']}__left"], atol=atol)
+        if right is not None:
+            np.testing.assert_allclose(right, data[f"{c['key']}__right"], atol=atol)
+    for c in meta["cholesky_cases"]:
+        check(dn.cholesky_regularized(data[f"mat__{c['mat']}"], absorb=c["absorb"], shift=c["shift"]),
+              c, 1e-12)
+    for c in meta["qr_cholesky_cases"]:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            check(dn.qr_via_cholesky(data[f"mat__{c['mat']}"], absorb=c["absorb"]), c, 1e-9)
+    for c in meta["polar_cases"]:
+        fn = dn.polar_right if c["side"] == "right" else dn.polar_left
+        check(fn(data[f"mat__{c['mat']}"]), c, 1e-12)
+    with pytest.raises(np.linalg.LinAlgError):
+        dn.cholesky_regularized(data["mat__indef"], shift="auto")
