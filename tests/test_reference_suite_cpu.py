@@ -87,6 +87,9 @@ CASES = [
     # 1D compression algorithms (dm / direct / fit / zipup / src) on MPS and
     # double-MPO networks, double precision
     ("test_tn1d/test_compress.py", "float64 and not torch", [], 230),
+    # all effectively exact circuit simulators agree at 1e-10 (Circuit, CircuitDense,
+    # CircuitMPS, CircuitMPSLazy, CircuitPermMPS): SURVEY 8(c) pins this file
+    ("test_circuit/test_cross_backend.py", "", [], 20),
     # boundary-MPS contraction in all of the reference's modes ('mps', 'full-bond',
     # 'projector'), HOTRG / CTMRG and the Ising accuracy regression
     ("test_tn2d/test_core.py",
