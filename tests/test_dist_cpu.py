@@ -36,6 +36,24 @@ def _worker(rank, world, port, ret):
     # automatic choice of the sliced indices: at least one slice per rank
     out2, mine2 = qd.contract_sliced([a, b, c], inputs, ("i", "t"), contract_fn=_np_contract)
     ok = ok and np.allclose(out2.numpy(), ref, atol=1e-12) and len(mine2) >= 1
+    # tree and slices searched together (auto-hq + width target): every rank
+    # searches, rank 0's choice is broadcast; the stand-in executor receives
+    # the Tree of the sliced network
+    from tests.circuit_util import random_grid_circuit_amplitude
+    arrs, ins, outp, amp = random_grid_circuit_amplitude(3, 3, 8, seed=5)
+
+    def _tree_contract(arrays, inputs_, output_, tree_):
+        from oracle import contract_np as cn
+        nodes = dict(enumerate(arrays))
+        inds = dict(enumerate(tree_.inputs))
+        for i, j, k, res in tree_.steps:
+            nodes[k] = cn.contract_pair(nodes.pop(i), inds[i], nodes.pop(j), inds[j], res)
+            inds[k] = res
+        (o,) = nodes.values()
+        return np.asarray(o)
+    out3, mine3 = qd.contract_sliced(arrs, ins, outp, optimize="auto-hq", target_width=6,
+                                     contract_fn=_tree_contract)
+    ok = ok and abs(complex(out3.numpy()) - amp) < 1e-12 and len(mine3) >= 1
     # units are disjoint and cover everything
     allu = [None] * world
     dist.all_gather_object(allu, mine)
