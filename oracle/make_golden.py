@@ -438,6 +438,20 @@ def decomp3_cases():
     except Exception as e:  # noqa: BLE001
         errs["chol_bad_absorb"] = type(e).__name__
     meta["errors"] = errs
+    # 'lu' split: (P L, None, U) with weak rows / columns dropped
+    lu = []
+    lowrank = mats["tall"] @ rng.standard_normal((10, 12))            # 24 x 12, full column rank
+    store["mat__lu_mixed"] = np.concatenate([lowrank, 1e-9 * rng.standard_normal((24, 3))], axis=1)
+    for mname, kw in [("square", dict()), ("tall", dict(cutoff=1e-12, cutoff_mode=2)),
+                      ("wide", dict(cutoff=1e-3, cutoff_mode=1)), ("cplx", dict(cutoff=1e-10, cutoff_mode=2)),
+                      ("lu_mixed", dict(cutoff=1e-6, cutoff_mode=2)),
+                      ("lu_mixed", dict(cutoff=1e-6, cutoff_mode=1))]:
+        key = f"lu__{len(lu)}"
+        x = store[f"mat__{mname}"]
+        kw2 = dict(cutoff_mode=2, **kw) if "cutoff_mode" not in kw else kw
+        has = put(key, *decomp.lu_truncated(x, **kw2))
+        lu.append({"key": key, "mat": mname, "kw": kw2, "has": has})
+    meta["lu_cases"] = lu
     # diagonal helpers
     d = np.abs(rng.standard_normal(16)) + 0.1
     d[3] = 0.0

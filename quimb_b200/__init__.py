@@ -28,7 +28,7 @@ from .mps import (MovingEnvironment, compute_left_environments,  # noqa: F401
                   compute_right_environments, env_left_step, env_right_step,
                   mps_expec, mps_norm, mps_norm2)
 from .split import (array_split, array_svals, cholesky_regularized,  # noqa: F401
-                    eigh_truncated, lddiv, ldmul, polar_left, polar_right,
+                    eigh_truncated, lddiv, ldmul, lu_truncated, polar_left, polar_right,
                     qr_stabilized, qr_via_cholesky, rddiv, rdmul, safe_inverse, sgn, svd_rand_truncated, svd_truncated,
                     svd_via_eig, svd_via_eig_truncated, tensor_canonize_bond,
                     tensor_compress_bond, tensor_split)
@@ -134,7 +134,7 @@ random = _Namespace(
 )
 
 scipy = _Namespace(linalg=_Namespace(solve_triangular=linalg.solve_triangular,
-                                     expm=linalg.expm))
+                                     expm=linalg.expm, lu=linalg.lu))
 
 __version__ = "0.1.0"
 

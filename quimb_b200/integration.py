@@ -58,6 +58,7 @@ def register_with_quimb():
                    ("qr_via_cholesky", split.qr_via_cholesky),
                    ("polar_right", split.polar_right),
                    ("polar_left", split.polar_left),
+                   ("lu_truncated", split.lu_truncated),
                    ("rddiv", split.rddiv), ("lddiv", split.lddiv),
                    ("rdmul", split.rdmul), ("ldmul", split.ldmul),
                    ("sgn", split.sgn)):

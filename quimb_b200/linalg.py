@@ -482,3 +482,12 @@ def eig(x):
     small message matrices): not on the contraction hot path."""
     w, v = torch.linalg.eig(ops.asarray(x).resolve())
     return Array(w), Array(v)
+
+
+def lu(x, permute_l=False):
+    """``scipy.linalg.lu`` signature: ``(P, L, U)`` or ``(P @ L, U)``.
+    Library forward (torch / cuSOLVER getrf with partial pivoting)."""
+    P, L, U = torch.linalg.lu(ops.asarray(x).resolve())
+    if permute_l:
+        return Array(P @ L), Array(U)
+    return Array(P), Array(L), Array(U)

@@ -52,7 +52,7 @@ _DEFAULT_ABSORB = {"svd": get_Usq_sqVH, "svd:eig": get_Usq_sqVH,
                    "svd:rand": get_Usq_sqVH, "eigh": get_Usq_sqVH,
                    "qr": get_U_sVH, "cholesky": get_Usq_sqVH,
                    "qr:cholesky": get_U_sVH, "polar_right": get_U_sVH,
-                   "polar_left": get_Us_VH}
+                   "polar_left": get_Us_VH, "lu": get_Usq_sqVH}
 # which options each driver takes (the reference inspects the signature of
 # _SPLIT_FNS[method], decomp.py:391-422)
 _METHOD_OPTS = {
@@ -65,6 +65,7 @@ _METHOD_OPTS = {
     "qr:cholesky": ("absorb",),
     "polar_right": (),
     "polar_left": (),
+    "lu": ("absorb", "max_bond", "cutoff", "cutoff_mode", "renorm"),
 }
 
 
@@ -93,7 +94,7 @@ def parse_method_absorb(method="auto", absorb="auto", truncation=True):
         raise ValueError(f"quimb_b200: split method {method!r} is not "
                          "implemented (available: 'svd', 'svd:eig', 'svd:rand', "
                          "'eigh', 'qr', 'lq', 'cholesky', 'qr:cholesky', "
-                         "'lq:cholesky', 'polar_right', 'polar_left')")
+                         "'lq:cholesky', 'polar_right', 'polar_left', 'lu')")
     if absorb == "auto":
         absorb = _DEFAULT_ABSORB[method]
     else:
@@ -623,6 +624,35 @@ def polar_left(x):
     return P, None, U
 
 
+def lu_truncated(x, cutoff=-1.0, cutoff_mode=4, max_bond=-1, absorb=get_Usq_sqVH, renorm=0):
+    """``method='lu'`` (decomp.py:2615-2670): ``x = (P L) U`` with rows /
+    columns whose absolute sums fall under the cutoff dropped ('abs' or 'rel'
+    mode only).  The factorisation itself is a library forward
+    (``linalg.lu``: torch / cuSOLVER getrf) -- nothing on the contraction hot
+    path uses this driver; the truncation bookkeeping mirrors the reference."""
+    absorb = _ABSORB_MAP[absorb]
+    cutoff_mode = _CUTOFF_MODE_MAP[cutoff_mode]
+    if absorb != get_Usq_sqVH:
+        raise NotImplementedError(f"Can't handle absorb{absorb} in lu_truncated.")
+    elif renorm != 0:
+        raise NotImplementedError(f"Can't handle renorm={renorm} in lu_truncated.")
+    elif max_bond != -1:
+        raise NotImplementedError(f"Can't handle max_bond={max_bond} in lu_truncated.")
+    PL, U = linalg.lu(x, permute_l=True)
+    pl, u = PL.resolve(), U.resolve()
+    sl = pl.abs().sum(dim=0)
+    su = u.abs().sum(dim=1)
+    if cutoff_mode == 2:
+        cl, cu = cutoff * sl.max(), cutoff * su.max()
+    elif cutoff_mode == 1:
+        cl = cu = cutoff
+    else:
+        raise NotImplementedError(f"Can't handle cutoff_mode={cutoff_mode} in lu_truncated.")
+    idx = torch.nonzero((sl > cl) & (su > cu)).reshape(-1)     # the kept rank: one host read
+    return (Array(pl.index_select(1, idx).contiguous()), None,
+            Array(u.index_select(0, idx).contiguous()))
+
+
 # ------------------------------------ diagonal helpers (decomp.py:580-656) --
 def rdmul(x, d):
     """x @ diag(d)"""
@@ -680,6 +710,7 @@ _SPLIT_FNS = {
     "qr:cholesky": qr_via_cholesky,
     "polar_right": polar_right,
     "polar_left": polar_left,
+    "lu": lu_truncated,
 }
 _SPLIT_VALUES_FNS = {"svd": svdvals, "svd:eig": svdvals_eig}
 

@@ -162,7 +162,7 @@ def test_parse_split_opts_new_methods_match_reference(golden_decomp2):
     with pytest.warns(FutureWarning):
         assert split.parse_split_opts(method="eig")[0] == "svd:eig"
     with pytest.raises(ValueError):
-        split.parse_split_opts(method="lu")
+        split.parse_split_opts(method="svds")
 
 
 def test_array_split_dispatch_and_tensor_split_methods():

@@ -133,7 +133,7 @@ def test_array_split_new_methods_and_option_codes(golden_decomp3):
             res = split.array_split(qb.asarray(x), cutoff=0.0, **c["kw"])
         _check(res, data, c, 1e-8)
     with pytest.raises(ValueError):
-        split.array_split(qb.asarray(data["mat__pd"]), method="lu")
+        split.array_split(qb.asarray(data["mat__pd"]), method="svds")
 
 
 def test_diagonal_helpers_match_reference_golden(golden_decomp3):
@@ -277,3 +277,28 @@ def test_new_drivers_vs_oracle_at_larger_sizes():
         got, ref = fn_d(qb.asarray(y)), fn_o(y)
         np.testing.assert_allclose(_np(got[0]), ref[0], atol=1e-10)
         np.testing.assert_allclose(_np(got[2]), ref[2], atol=1e-10)
+
+
+def test_lu_split_matches_reference_golden(golden_decomp3):
+    """``method='lu'`` (decomp.py:2615-2670): the permuted-lower / upper factors
+    and which rows / columns survive the cutoff."""
+    data, meta = golden_decomp3
+    for c in meta["lu_cases"]:
+        x = data[f"mat__{c['mat']}"]
+        res = split.lu_truncated(qb.asarray(x), **c["kw"])
+        pl, _, u = (_np(t) for t in res)
+        if c["mat"] == "cplx":
+            # complex pivot selection may legitimately differ between getrf
+            # implementations (|re| + |im| against |z|): compare the product
+            assert pl.shape == data[f"{c['key']}__left"].shape
+            assert np.allclose(np.tril(u, -1), 0.0)
+        else:
+            _check(res, data, c, 1e-11)
+        if c["mat"] != "lu_mixed":
+            np.testing.assert_allclose(pl @ u, x, atol=1e-12)
+    x = data["mat__square"]
+    left, _, right = split.array_split(qb.asarray(x), method="lu", cutoff=0.0, cutoff_mode="rel")
+    np.testing.assert_allclose(_np(left) @ _np(right), x, atol=1e-12)
+    for kw in (dict(absorb="left"), dict(renorm=1), dict(max_bond=3), dict(cutoff_mode=4)):
+        with pytest.raises(NotImplementedError):
+            split.lu_truncated(qb.asarray(x), **{"cutoff_mode": 2, **kw})
