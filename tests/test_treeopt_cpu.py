@@ -218,3 +218,35 @@ def test_tree_search_does_not_depend_on_the_hash_seed():
         assert res.returncode == 0, res.stderr[-2000:]
         outs.add(res.stdout)
     assert len(outs) == 1
+
+
+def test_auto_hq_and_sliced_search_on_random_hyper_networks():
+    """the full pipelines (simplify -> greedy / spectral -> anneal -> reconfigure,
+    and slicing interleaved with re-optimisation) on random networks with
+    hyper-indices, open outputs and mixed index sizes."""
+    rng = np.random.default_rng(99)
+    for trial in range(16):
+        n = int(rng.integers(10, 15))
+        arrays, inputs, output, sizes = _rand_network(rng, n, int(rng.integers(n, 2 * n)),
+                                                      bool(trial % 2), n_out=int(rng.integers(0, 4)))
+        ref = cn.array_contract(arrays, inputs, output, "greedy")
+        for opt in ("auto-hq", "spectral"):
+            tr = tree.find_tree(inputs, output, sizes, opt)
+            out, _ = _run_ssa(inputs, output, sizes, [(i, j) for i, j, _, _ in tr.steps], arrays)
+            np.testing.assert_allclose(out, ref, rtol=1e-9, atol=1e-9)
+        w = tree.find_tree(inputs, output, sizes, "auto-hq").contraction_width()
+        tr, sl = tree.find_sliced_tree(inputs, output, sizes, max(1.0, w - 2))
+        assert not set(sl) & set(output)
+        total = 0
+        for vals in it.product(*[range(sizes[ix]) for ix in sl]):
+            fix = dict(zip(sl, vals))
+            sub = [a[tuple(fix[ix] if ix in fix else slice(None) for ix in t)]
+                   for a, t in zip(arrays, inputs)]
+            nodes = dict(enumerate(sub))
+            inds = dict(enumerate(tr.inputs))
+            for i, j, k, res in tr.steps:
+                nodes[k] = cn.contract_pair(nodes.pop(i), inds[i], nodes.pop(j), inds[j], res)
+                inds[k] = res
+            (part,) = nodes.values()
+            total = total + part
+        np.testing.assert_allclose(total, ref, rtol=1e-9, atol=1e-9)
