@@ -182,12 +182,7 @@ bool stream_eligible(const PairPlan &plan) {
 
 template <bool CPLX, int KMAX, int NMAX>
 static int launch_stream_t(const ContractParams &p, cudaStream_t st) {
-  int sms = 148;
-  {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  }
+  const int sms = sm_count();
   const int64_t want = (p.M + kStreamThreads - 1) / kStreamThreads;
   const int64_t cap = (int64_t)sms * 8;  // 8 resident CTAs of 256 threads per SM
   dim3 grid((unsigned)std::max<int64_t>(1, std::min<int64_t>(want, cap)),
