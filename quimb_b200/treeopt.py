@@ -22,7 +22,7 @@ Trees are exchanged as SSA step lists like everywhere in ``tree.py``.
 import math
 import random
 
-__all__ = ["reconfigure", "anneal", "slice_and_reconfigure", "tree_stats", "tree_traffic",
+__all__ = ["reconfigure", "anneal", "slice_and_reconfigure", "tree_stats", "tree_traffic", "tree_peak",
            "spectral_ssa", "growth_ssa", "simplify_inputs", "compose_ssa"]
 
 
@@ -316,6 +316,23 @@ def tree_traffic(inputs, output, size_dict, ssa):
     for k, (i, j) in bt.children.items():
         tot += 2.0 ** lsize(bt.legs[i]) + 2.0 ** lsize(bt.legs[j]) + 2.0 ** lsize(bt.legs[k])
     return math.log2(tot) if tot > 0 else 0.0
+
+
+def tree_peak(inputs, output, size_dict, ssa):
+    """log2 of the largest number of elements alive at once when the tree is
+    executed step by step (operands are released after the step that consumes
+    them): the memory the executor needs, in elements."""
+    bt = _BinTree(inputs, output, size_dict, ssa)
+    lsize = bt.bits.lsize
+    size = {k: 2.0 ** lsize(m) for k, m in bt.legs.items()}
+    live = sum(size[k] for k in range(bt.n))
+    peak = live
+    # replay in SSA order (ids grow with the steps)
+    for k in sorted(bt.children):
+        i, j = bt.children[k]
+        peak = max(peak, live + size[k])
+        live += size[k] - size[i] - size[j]
+    return math.log2(peak) if peak > 0 else 0.0
 
 
 def _greedy_slices(bt, target_width, fixed=(), max_new=None):

@@ -250,3 +250,16 @@ def test_auto_hq_and_sliced_search_on_random_hyper_networks():
             (part,) = nodes.values()
             total = total + part
         np.testing.assert_allclose(total, ref, rtol=1e-9, atol=1e-9)
+
+
+def test_tree_traffic_and_peak_bookkeeping():
+    # chain A(ab) B(bc) C(cd) contracted left to right, sizes 2, 3, 4, 5
+    inputs, output = [("a", "b"), ("b", "c"), ("c", "d")], ("a", "d")
+    sizes = dict(a=2, b=3, c=4, d=5)
+    ssa = [(0, 1), (3, 2)]
+    # node 3 = (a, c): reads 6 + 12, writes 8; node 4 = (a, d): reads 8 + 20, writes 10
+    assert treeopt.tree_traffic(inputs, output, sizes, ssa) == pytest.approx(math.log2(6 + 12 + 8 + 8 + 20 + 10))
+    # alive: inputs 6 + 12 + 20 = 38; + node 3 (8) = 46 is the peak; then 38 - 18 + 8 = 28, + 10 = 38
+    assert treeopt.tree_peak(inputs, output, sizes, ssa) == pytest.approx(math.log2(46))
+    c, w = treeopt.tree_stats(inputs, output, sizes, ssa)
+    assert c == pytest.approx(math.log2(2 * 3 * 4 + 2 * 4 * 5)) and w == pytest.approx(math.log2(20))

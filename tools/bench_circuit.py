@@ -36,6 +36,8 @@ def main():
     ap.add_argument("--target-width", type=int, default=28)
     ap.add_argument("--max-slices", type=int, default=64)
     ap.add_argument("--reps", type=int, default=1)
+    ap.add_argument("--max-gb", type=float, default=140.0,
+                    help="refuse trees whose live intermediates exceed this many GB")
     ap.add_argument("--out", default=None)
     args = ap.parse_args()
     import numpy as np
@@ -77,7 +79,16 @@ def main():
 
     from quimb_b200 import treeopt
     elems_slice = 2.0 ** treeopt.tree_traffic(tr.inputs, tr.output, sd, [(i, j) for i, j, _, _ in tr.steps])
+    peak_gb = 16.0 * 2.0 ** treeopt.tree_peak(tr.inputs, tr.output, sd,
+                                             [(i, j) for i, j, _, _ in tr.steps]) / 1e9
+    if peak_gb > args.max_gb:
+        # never drive the box out of memory: refuse instead
+        if rank == 0:
+            print(json.dumps({"refused": f"the tree needs about {peak_gb:.0f} GB alive at once "
+                              f"(> --max-gb {args.max_gb}); lower --target-width"}))
+        return
     res = {"config": f"{args.Lx}x{args.Ly} depth {args.depth} complex128", "n_gpus": world,
+           "peak_gbytes_estimate": round(peak_gb, 1),
            "algorithmic_gbytes_per_slice": round(16.0 * elems_slice / 1e9, 3),
            "tensors": len(inputs), "log2_width": tr.contraction_width(),
            "n_sliced": len(sliced), "log2_macs_per_slice": round(math.log2(macs_slice), 2),
