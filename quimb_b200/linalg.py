@@ -491,3 +491,17 @@ def lu(x, permute_l=False):
     if permute_l:
         return Array(P @ L), Array(U)
     return Array(P), Array(L), Array(U)
+
+
+def lstsq(a, b, rcond=None):
+    """``numpy.linalg.lstsq`` return convention ``(x, residuals, rank, s)``.
+    Library forward (torch / cuSOLVER gels); tensor-network fitting calls it on
+    small normal-equation blocks, nothing on the contraction hot path does."""
+    A = ops.asarray(a).resolve()
+    B = ops.asarray(b).resolve()
+    vec = B.ndim == 1
+    if vec:
+        B = B[:, None]
+    sol = torch.linalg.lstsq(A, B.to(A.dtype), rcond=rcond)
+    x = sol.solution[:, 0] if vec else sol.solution
+    return Array(x), Array(sol.residuals), sol.rank, Array(sol.singular_values)

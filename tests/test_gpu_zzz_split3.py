@@ -178,6 +178,10 @@ def test_pinv_inv_solve_and_small_surface():
         A = L if kw.get("lower") else L.T
         np.testing.assert_allclose(_np(qb.scipy.linalg.solve_triangular(qb.asarray(A), qb.asarray(b), **kw)),
                                    sla.solve_triangular(A, b, **kw), atol=1e-11)
+    tall = rng.standard_normal((20, 6))
+    rhs = rng.standard_normal((20, 2))
+    xs = qb.linalg.lstsq(qb.asarray(tall), qb.asarray(rhs))[0]
+    np.testing.assert_allclose(_np(xs), np.linalg.lstsq(tall, rhs, rcond=None)[0], atol=1e-11)
     np.testing.assert_array_equal(_np(qb.indices((2, 3))), np.indices((2, 3)))
     assert qb.finfo("float64").eps == np.finfo(np.float64).eps
     assert qb.finfo(qb.asarray(np.zeros(2, np.complex64))).eps == np.finfo(np.float32).eps
