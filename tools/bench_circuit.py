@@ -14,7 +14,7 @@ launch of the pairwise contraction kernel per node), slices are dealt
 round-robin to the ranks and summed with ONE all-reduce.  When the slice count
 exceeds ``--max-slices`` only that many slices are executed and the time is
 reported per slice together with the extrapolated total (``partial: true``;
-the amplitude is then not the full sum).  For <= 25 qubits the exact amplitude
+the amplitude is then not the full sum).  For <= 20 qubits the exact amplitude
 from a dense state-vector simulation is compared.
 """
 import argparse
@@ -53,7 +53,7 @@ def main():
         dist.init_process_group("nccl")
     nq = args.Lx * args.Ly
     arrays, inputs, output, amp = random_grid_circuit_amplitude(
-        args.Lx, args.Ly, args.depth, seed=3, dense=nq <= 25)
+        args.Lx, args.Ly, args.depth, seed=3, dense=nq <= 20)
     sd = {ix: 2 for t in inputs for ix in t}
     t0 = time.perf_counter()
     tr, sliced = T.find_sliced_tree(inputs, output, sd, args.target_width,

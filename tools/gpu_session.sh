@@ -20,14 +20,14 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --c
 # 4. callers either side of the path
 timeout 900 python tools/bench_dmrg.py --L 30 --chi 1024 --no-cpu --left-sweep > $out/${tag}_dmrg_L30.log 2>&1
 timeout 600 python tools/bench_boundary.py --Lx 10 --Ly 10 --D 8 --chi 256 > $out/${tag}_boundary.json 2> $out/${tag}_boundary.err
-timeout 600 python tools/bench_circuit.py --Lx 5 --Ly 5 --depth 16 --target-width 28 \
+timeout 600 python tools/bench_circuit.py --Lx 5 --Ly 5 --depth 16 --target-width 22 \
     --out $out/${tag}_circuit_5x5_d16.json > $out/${tag}_circuit.log 2>&1
 timeout 900 python tools/bench_circuit.py --Lx 6 --Ly 6 --depth 24 --target-width 31 --max-slices 2 \
     --out $out/${tag}_circuit_6x6_d24_partial.json >> $out/${tag}_circuit.log 2>&1
 ls -la $out | tail -20
 # 5. streaming engine (opt-in) against the DMMA path on the same circuit tree
 timeout 300 python -m pytest tests/test_gpu_zzz_stream.py -q > $out/${tag}_pytest_stream.log 2>&1; tail -2 $out/${tag}_pytest_stream.log
-QB_ENGINE=stream timeout 600 python tools/bench_circuit.py --Lx 5 --Ly 5 --depth 16 --target-width 28 \
+QB_ENGINE=stream timeout 600 python tools/bench_circuit.py --Lx 5 --Ly 5 --depth 16 --target-width 22 \
     --out $out/${tag}_circuit_5x5_d16_stream.json >> $out/${tag}_circuit.log 2>&1
 QB_ENGINE=stream timeout 900 python tools/bench_circuit.py --Lx 6 --Ly 6 --depth 24 --target-width 31 --max-slices 2 \
     --out $out/${tag}_circuit_6x6_d24_partial_stream.json >> $out/${tag}_circuit.log 2>&1
