@@ -129,28 +129,56 @@ def contract_pair(a, la, b, lb, lc, conj_a=False, conj_b=False, out=None,
 _CHUNK = 5
 
 
-def permute_contiguous(t, order):
+def permute_modes(t):
+    """Number of modes the permute kernel sees when ``t`` (any strided view) is
+    copied into a contiguous tensor of the same axis order: axes of extent > 1,
+    ordered by destination stride, neighbours merged when they are jointly
+    contiguous in source and destination (mirrors qb_permute's host logic,
+    csrc/elementwise.cu; the kernel takes 17, or 18 when the fastest source
+    mode differs from the fastest destination mode)."""
+    dims = [(t.shape[i], t.stride(i)) for i in range(t.dim()) if t.shape[i] > 1]
+    ds, acc = [], 1
+    for e, _ in reversed(dims):
+        ds.append(acc)
+        acc *= e
+    ds.reverse()
+    ms = sorted(((e, ss, d) for (e, ss), d in zip(dims, ds)), key=lambda m: m[2])
+    n, last = 0, None
+    for e, ss, d in ms:
+        if last is not None and ss == last[1] * last[0] and d == last[2] * last[0]:
+            last = (last[0] * e, last[1], last[2])
+            continue
+        n += 1
+        last = (e, ss, d)
+    return n
+
+
+PERMUTE_MAX_MODES = 17   # 16 generic modes + the fastest destination mode (+1 more when a distinct fastest source mode exists)
+
+
+def permute_contiguous(t, order, conj=False):
     """Contiguous tensor whose axis k is axis ``order[k]`` of ``t``, for any
     rank: the permute kernel takes up to 15 jointly non-mergeable modes, so a
     general permutation of a high-rank tensor is done in passes that each move
     ``_CHUNK`` axes behind the rest (<= 2 * _CHUNK + 2 modes per pass)."""
     lib = _lib.load()
 
-    def one_pass(src, perm):
+    def one_pass(src, perm, cj=False):
         view = src.permute(tuple(perm))
         dst = torch.empty(view.shape, dtype=src.dtype, device=src.device)
         if dst.numel():
-            rc = lib.qb_permute(_lib.desc(view), _lib.desc(dst), 0, _lib.stream_ptr())
+            rc = lib.qb_permute(_lib.desc(view), _lib.desc(dst), int(cj), _lib.stream_ptr())
             _lib.check(rc, "qb_permute")
         return dst
 
     order = list(order)
     r = t.dim()
     if r <= 2 * _CHUNK:
-        return one_pass(t, order)
-    # start from a copy laid out in the source's own stride order (few modes)
+        return one_pass(t, order, conj)
+    # start from a copy laid out in the source's own stride order (few modes);
+    # a lazy conjugation is applied in this first pass
     by_stride = sorted(range(r), key=lambda ax: (-abs(t.stride(ax)), ax))
-    cur = one_pass(t, by_stride)
+    cur = one_pass(t, by_stride, conj)
     names = list(by_stride)                   # names[k] = original axis held by cur's axis k
     placed = 0
     while placed < r:

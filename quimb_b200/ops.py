@@ -81,6 +81,13 @@ def materialize(x, force=False):
     if not force and not x.cj and t.is_contiguous():
         return x
     _lib.require_cuda(t)
+    if t.dim() > 10:
+        # a general permutation of a high-rank tensor (to_dense of a 20-qubit
+        # state, fuse over interleaved axes) can exceed the permute kernel's
+        # mode limit: take the multi-pass route then
+        from .contract import PERMUTE_MAX_MODES, permute_contiguous, permute_modes
+        if permute_modes(t) > PERMUTE_MAX_MODES:
+            return Array(permute_contiguous(t, list(range(t.dim())), conj=x.cj))
     out = torch.empty(t.shape, dtype=t.dtype, device=t.device)
     if t.numel():
         lib = _lib.load()

@@ -350,3 +350,27 @@ def test_contraction_with_more_than_12_interleaved_modes_regroups():
     got = permute_contiguous(qb.asarray(z).t, order)
     assert got.is_contiguous()
     np.testing.assert_array_equal(got.cpu().numpy(), np.transpose(z, order))
+
+
+def test_materialize_of_a_high_rank_general_permutation():
+    """fuse / to_dense of a 22-index tensor under a general axis permutation
+    has more modes than one launch of the permute kernel takes (17-18): the copy
+    is done in passes; lazy conjugation is applied on the way."""
+    from quimb_b200 import ops
+    from quimb_b200.contract import PERMUTE_MAX_MODES, permute_modes
+    rng = np.random.default_rng(6)
+    z = rng.standard_normal((2,) * 22) + 1j * rng.standard_normal((2,) * 22)
+    perm = [int(p) for p in rng.permutation(22)]
+    view = qb.asarray(z).transpose(*perm)
+    assert permute_modes(view.t) > PERMUTE_MAX_MODES
+    got = ops.materialize(view)
+    assert got.t.is_contiguous() and not got.cj
+    np.testing.assert_array_equal(got.to_numpy(), np.transpose(z, perm))
+    got_c = ops.materialize(view.conj())
+    np.testing.assert_array_equal(got_c.to_numpy(), np.transpose(z, perm).conj())
+    # reshape (fuse) of the permuted view goes through the same route
+    fused = ops.reshape(view, (2 ** 11, 2 ** 11))
+    np.testing.assert_array_equal(fused.to_numpy(), np.transpose(z, perm).reshape(2 ** 11, 2 ** 11))
+    # a contiguous tensor and a plain transpose stay single-launch
+    assert permute_modes(qb.asarray(z).t) == 1
+    assert permute_modes(qb.asarray(z.reshape(2 ** 11, 2 ** 11)).t.t()) == 2
