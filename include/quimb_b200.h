@@ -11,11 +11,17 @@
  *                            and by Tensor.__matmul__, quimb/tensor/tensor_core.py:3786-3808
  *   qb_permute            <- do("transpose")+do("reshape") materialisation in
  *                            quimb/tensor/array_ops.py:148-180 (fuse)
- *   qb_svd_trunc          <- svd_truncated, quimb/tensor/decomp.py:829-1118
+ *   qb_svd_trunc          <- svd_truncated incl. the keep rule, renormalisation
+ *                            and absorb, quimb/tensor/decomp.py:829-1118, :901-1029,
+ *                            :693-721 (qb_svd + qb_svals_to_keep are its parts)
  *   qb_qr_stab            <- qr_stabilized, quimb/tensor/decomp.py:2055-2216
- *   qb_lanczos_* / qb_axpy / qb_dot ...
+ *   qb_dot / qb_axpby / qb_scale / qb_multi_dot / qb_multi_axpy
  *                         <- ARPACK dsaupd vector algebra behind
- *                            quimb/linalg/scipy_linalg.py:113-128 (eigs_scipy)
+ *                            quimb/linalg/scipy_linalg.py:113-128 (eigs_scipy);
+ *                            the Krylov control loop itself is host Python
+ *                            (quimb_b200/lanczos.py) -- there is no qb_lanczos_*
+ *                            and no plan_create/execute/destroy entry: cached
+ *                            chains are CUDA graphs captured by the host layer
  *
  * Conventions
  *   - plain C, no C++/torch types; device pointers are borrowed, never freed
@@ -250,6 +256,40 @@ int qb_svals_to_keep(const double *s, int64_t n, double cutoff,
                      double *trunc_error);
 
 /* ---- device queries / microbenchmarks ---------------------------------- */
+/* ------------------------------------------------------------------------
+ * Peer-memory exchange of the bond-sharded two-site eigensolve (multi-GPU,
+ * one process per GPU).  Replaces, on the data path, the ncclAllGather of the
+ * Lanczos vector and the ncclAllReduce of the Gram-Schmidt inner products
+ * that a sharded TNLinearOperator._matvec / eigsh would issue
+ * (quimb/tensor/tensor_core.py:12393-12417, quimb/linalg/scipy_linalg.py:
+ * 113-128): ONE kernel each, storing into the peers' HBM over NVLink.
+ *
+ * Every rank allocates one block (qb_p2p_alloc: cudaMalloc'ed and zeroed by
+ * the library -- the only allocation the library owns, released by
+ * qb_p2p_free), exports it (64-byte CUDA IPC handle) and imports the blocks
+ * of its peers; `peer_bufs[world]` lists the block bases in rank order, the
+ * caller's own block at index `rank`.  `epoch` counts the calls of each kind
+ * (1, 2, ...; the same sequence on every rank); `scratch` is 8 bytes of
+ * zeroed device memory (CTA counter, error word: non-zero after a kernel gave
+ * up waiting ~4 s for a peer).
+ */
+int64_t qb_p2p_block_bytes(int64_t gather_bytes);
+int64_t qb_p2p_data_offset(int64_t gather_bytes, int parity);
+int qb_p2p_alloc(int64_t bytes, void **ptr);
+int qb_p2p_free(void *ptr);
+int qb_p2p_export(void *ptr, unsigned char *handle64);
+int qb_p2p_import(const unsigned char *handle64, void **peer_ptr);
+int qb_p2p_unimport(void *peer_ptr);
+/* all ranks: slab `x` (bytes, 16-byte granular) -> byte offset dst_off of the
+ * gather buffer of parity (epoch & 1) on EVERY rank; when the kernel has
+ * completed the whole vector is resident in the local block. */
+int qb_p2p_allgather(void *const *peer_bufs, int world, int rank, const void *x,
+                     int64_t bytes, int64_t dst_off, int64_t gather_bytes,
+                     uint64_t epoch, void *scratch, void *stream);
+/* in-place sum over the ranks of m <= 64 doubles, bit-identical everywhere */
+int qb_p2p_allreduce_small(void *const *peer_bufs, int world, int rank, void *x,
+                           int m, uint64_t epoch, void *scratch, void *stream);
+
 /* sustained DMMA (fp64 tensor core) rate of the current device in TFLOP/s */
 int qb_measure_dmma_peak(double *tflops, void *stream);
 /* tuning hook: with QB_TRACE=1 in the environment the contraction kernels stamp

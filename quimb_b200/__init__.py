@@ -26,7 +26,7 @@ from .tree import (ContractExpression, GraphedContraction, Tree,  # noqa: F401
                    gen_output_inds, tensor_contract)
 from .mps import (MovingEnvironment, compute_left_environments,  # noqa: F401
                   compute_right_environments, env_left_step, env_right_step,
-                  mps_expec, mps_norm, mps_norm2)
+                  mpo_ham_heis, mps_expec, mps_norm, mps_norm2)
 from .split import (array_split, array_svals, cholesky_regularized,  # noqa: F401
                     eigh_truncated, lddiv, ldmul, lu_truncated, polar_left, polar_right,
                     qr_stabilized, qr_via_cholesky, rddiv, rdmul, safe_inverse, sgn, svd_rand_truncated, svd_truncated,

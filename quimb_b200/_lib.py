@@ -109,6 +109,15 @@ def load(build_if_missing=True):
         ("qb_svals_to_keep", ci, [dblp, i64, ctypes.c_double, ci, i64, ci,
                                   P(i64), dblp, dblp]),
         ("qb_measure_dmma_peak", ci, [dblp, vp]),
+        ("qb_p2p_block_bytes", i64, [i64]),
+        ("qb_p2p_data_offset", i64, [i64, ci]),
+        ("qb_p2p_alloc", ci, [i64, P(vp)]),
+        ("qb_p2p_free", ci, [vp]),
+        ("qb_p2p_export", ci, [vp, P(ctypes.c_ubyte)]),
+        ("qb_p2p_import", ci, [P(ctypes.c_ubyte), P(vp)]),
+        ("qb_p2p_unimport", ci, [vp]),
+        ("qb_p2p_allgather", ci, [P(vp), ci, ci, vp, i64, i64, i64, ctypes.c_uint64, vp, vp]),
+        ("qb_p2p_allreduce_small", ci, [P(vp), ci, ci, vp, ci, ctypes.c_uint64, vp, vp]),
         ("qb_debug_trace_read", ci, [vp, i64]),
         ("qb_debug_contract_stream_host", ci,
          [T, I32P, T, I32P, T, I32P, ci, ci, ctypes.c_double, ctypes.c_double]),

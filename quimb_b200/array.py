@@ -328,25 +328,25 @@ class Array:
     def __ne__(self, o): return self._bin(o, torch.ne)
     __hash__ = None
 
-    def __iadd__(self, o):
-        r = self + o
-        self.t, self.cj = r.t, False
+    def _inplace(self, r):
+        """Write the result of a binary op back into this array's own storage
+        (numpy semantics: views and aliases of the buffer see the update; a
+        result that does not cast safely into the stored dtype raises)."""
+        rt = r.resolve() if isinstance(r, Array) else torch.as_tensor(r, device=self.t.device)
+        if rt.dtype != self.t.dtype and not torch.can_cast(rt.dtype, self.t.dtype):
+            raise TypeError(f"Cannot cast in-place result from {rt.dtype} to "
+                            f"{self.t.dtype} with casting rule 'same_kind'")
+        if rt.shape != self.t.shape:
+            raise ValueError(f"non-broadcastable output operand with shape "
+                             f"{tuple(self.t.shape)} doesn't match the broadcast "
+                             f"shape {tuple(rt.shape)}")
+        self.t.copy_(rt.conj() if self.cj and rt.is_complex() else rt)
         return self
 
-    def __isub__(self, o):
-        r = self - o
-        self.t, self.cj = r.t, False
-        return self
-
-    def __imul__(self, o):
-        r = self * o
-        self.t, self.cj = r.t, False
-        return self
-
-    def __itruediv__(self, o):
-        r = self / o
-        self.t, self.cj = r.t, False
-        return self
+    def __iadd__(self, o): return self._inplace(self + o)
+    def __isub__(self, o): return self._inplace(self - o)
+    def __imul__(self, o): return self._inplace(self * o)
+    def __itruediv__(self, o): return self._inplace(self / o)
 
     def __matmul__(self, other):
         from .ops import matmul

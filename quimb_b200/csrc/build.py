@@ -12,17 +12,14 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SOURCES = [
-    "api.cu",
-    "contract_dmma.cu",
-    "contract_stream.cu",
-    "elementwise.cu",
-    "linalg.cu",
-    "ozaki_tc.cu",
-    "microbench.cu",
-    "convert.cu",
-]
-HEADERS = ["common.cuh", "plan.h", "../../include/quimb_b200.h"]
+import glob
+
+# every translation unit and every header next to this file is part of the
+# build (and of the rebuild digest: a stale .so after a header edit would be a
+# silent ABI mismatch between objects on the GPU box)
+SOURCES = sorted(os.path.basename(p) for p in glob.glob(os.path.join(HERE, "*.cu")))
+HEADERS = sorted(os.path.basename(p) for p in glob.glob(os.path.join(HERE, "*.h"))
+                 + glob.glob(os.path.join(HERE, "*.cuh"))) + ["../../include/quimb_b200.h"]
 LIB = os.path.join(HERE, "libquimb_b200.so")
 STAMP = os.path.join(HERE, ".build_stamp")
 

@@ -260,12 +260,65 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+struct FillDesc {
+  int rank;
+  int64_t shape[QB_MAX_RANK];
+  int64_t stride[QB_MAX_RANK];  // in reals
+};
+// strided zero fill (one thread per element; epr reals per element)
+__global__ void __launch_bounds__(256)
+    fill_zero_strided_kernel(double *__restrict__ base, const FillDesc d,
+                             int64_t total, int epr, int real_bytes) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t rem = i, off = 0;
+    for (int k = d.rank - 1; k >= 0; --k) {
+      const int64_t q = rem / d.shape[k];
+      off += (rem - q * d.shape[k]) * d.stride[k];
+      rem = q;
+    }
+    if (real_bytes == 8) {
+      double *p = base + off;
+      for (int e = 0; e < epr; ++e) p[e] = 0.0;
+    } else {
+      float *p = reinterpret_cast<float *>(base) + off;
+      for (int e = 0; e < epr; ++e) p[e] = 0.0f;
+    }
+  }
+}
+
 int launch_fill_zero(const qb_tensor_t *C, cudaStream_t st) {
-  // only used for contiguous outputs produced by the python layer
+  // contiguous, 16-byte aligned outputs take the vector fill; anything else
+  // (a strided `out=` view, an 8-byte aligned slice) is zeroed element-wise
+  // through its strides
   int64_t n = 1;
   for (int i = 0; i < C->rank; ++i) n *= C->shape[i];
   int64_t bytes = n * dtype_size(C->dtype);
   if (bytes == 0) return 0;
+  bool contiguous = true;
+  {
+    int64_t expect = 1;
+    for (int i = C->rank - 1; i >= 0; --i) {
+      if (C->shape[i] != 1 && C->stride[i] != expect) contiguous = false;
+      expect *= C->shape[i];
+    }
+  }
+  if (!contiguous || (reinterpret_cast<uintptr_t>(C->ptr) & 15)) {
+    const bool cplx = (C->dtype == QB_C128 || C->dtype == QB_C64);
+    const int epr = cplx ? 2 : 1;
+    const int real_bytes = (int)dtype_size(C->dtype) / epr;
+    FillDesc d;
+    d.rank = C->rank;
+    for (int i = 0; i < C->rank; ++i) {
+      d.shape[i] = C->shape[i];
+      d.stride[i] = C->stride[i] * epr;
+    }
+    int blocks = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);
+    fill_zero_strided_kernel<<<blocks, 256, 0, st>>>(static_cast<double *>(C->ptr), d, n,
+                                                     epr, real_bytes);
+    QB_LAUNCH_CHECK();
+    return 0;
+  }
   int64_t n16 = bytes / 16;
   int tail = (int)(bytes - n16 * 16);
   int blocks = (int)std::min<int64_t>((n16 + 255) / 256 + 1, 148 * 8);

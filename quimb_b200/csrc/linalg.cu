@@ -398,7 +398,10 @@ int qb_svals_to_keep(const double *s, int64_t n, double cutoff,
                      int cutoff_mode, int64_t max_bond, int renorm,
                      int64_t *n_keep, double *renorm_factor,
                      double *trunc_error) {
-  if (!s || n <= 0) return -1;
+  if (!s || n <= 0) {
+    set_error("qb_svals_to_keep: empty spectrum (n = %lld)", (long long)n);
+    return -1;
+  }
   if (cutoff_mode < 1 || cutoff_mode > 6) {
     set_error("invalid cutoff_mode %d", cutoff_mode);
     return -4;

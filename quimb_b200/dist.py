@@ -145,16 +145,128 @@ def _finish(total, arrays, inputs, output, size_dict):
     return t
 
 
+class _DevView:
+    """Zero-copy torch view of raw device memory (CUDA array interface)."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1",
+                                         "data": (int(ptr), False), "version": 2}
+
+
+class PeerExchange:
+    """Symmetric peer-memory block of the fused exchange kernels
+    (csrc/p2p.cu): allocated by the library with cudaMalloc, exported to the
+    peers of the process group through CUDA IPC (handles travel over
+    ``all_gather_object``), after which the all-gather of a Krylov vector and
+    the all-reduce of a handful of inner products are ONE kernel each that
+    stores straight into the peers' HBM over NVLink and spins on flag words
+    -- no NCCL call on the data path.  Raises if IPC / peer access is not
+    available; ``BondShard(exchange='auto')`` then stays on NCCL."""
+
+    def __init__(self, gather_bytes, group, rank, world_size, device):
+        import ctypes
+        from . import _lib
+        self.lib = lib = _lib.load()
+        self.rank, self.world, self.group = rank, world_size, group
+        self.gather_bytes = int(gather_bytes)
+        self.device = device
+        total = lib.qb_p2p_block_bytes(self.gather_bytes)
+        ptr = ctypes.c_void_p()
+        _lib.check(lib.qb_p2p_alloc(total, ctypes.byref(ptr)), "qb_p2p_alloc")
+        self.local = ptr.value
+        self.total = total
+        handle = (ctypes.c_ubyte * 64)()
+        _lib.check(lib.qb_p2p_export(ctypes.c_void_p(self.local), handle), "qb_p2p_export")
+        handles = [None] * world_size
+        dist.all_gather_object(handles, bytes(handle), group=group)
+        self.peers, self._imported = [], []
+        ok = 1
+        for r, h in enumerate(handles):
+            if r == rank:
+                self.peers.append(self.local)
+                continue
+            pp = ctypes.c_void_p()
+            buf = (ctypes.c_ubyte * 64).from_buffer_copy(h)
+            rc = lib.qb_p2p_import(buf, ctypes.byref(pp))
+            if rc != 0:
+                ok = 0
+                self.peers.append(0)
+            else:
+                self.peers.append(pp.value)
+                self._imported.append(pp.value)
+        staged = dist.get_backend(group) != "nccl"
+        flag = torch.tensor([ok], dtype=torch.int32, device="cpu" if staged else device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        if int(flag.item()) != 1:
+            self.close()
+            raise RuntimeError("CUDA IPC peer mapping failed on at least one rank: "
+                               + _lib.last_error())
+        self.peer_arr = (ctypes.c_void_p * world_size)(*self.peers)
+        self.scratch = torch.zeros(2, dtype=torch.int32, device=device)
+        self.g_epoch = 0
+        self.r_epoch = 0
+        self._bytes = torch.as_tensor(_DevView(self.local, total), device=device)
+        dist.barrier(group=group)
+
+    def data_view(self, parity, dtype, numel):
+        off = self.lib.qb_p2p_data_offset(self.gather_bytes, parity)
+        return self._bytes[off:off + numel * dtype.itemsize].view(dtype)
+
+    def all_gather(self, local, dst_off_bytes):
+        """Enqueue the push of ``local`` (contiguous) into every rank's gather
+        buffer; returns the parity of the buffer that holds the gathered vector
+        once the kernel has completed (stream order)."""
+        import ctypes
+        from . import _lib
+        self.g_epoch += 1
+        rc = self.lib.qb_p2p_allgather(self.peer_arr, self.world, self.rank,
+                                       ctypes.c_void_p(local.data_ptr()),
+                                       local.numel() * local.element_size(), int(dst_off_bytes),
+                                       self.gather_bytes, self.g_epoch,
+                                       ctypes.c_void_p(self.scratch.data_ptr()),
+                                       _lib.stream_ptr())
+        _lib.check(rc, "qb_p2p_allgather")
+        return self.g_epoch & 1
+
+    def all_reduce_small_(self, t):
+        import ctypes
+        from . import _lib
+        self.r_epoch += 1
+        rc = self.lib.qb_p2p_allreduce_small(self.peer_arr, self.world, self.rank,
+                                             ctypes.c_void_p(t.data_ptr()), t.numel(),
+                                             self.r_epoch,
+                                             ctypes.c_void_p(self.scratch.data_ptr()),
+                                             _lib.stream_ptr())
+        _lib.check(rc, "qb_p2p_allreduce_small")
+        return t
+
+    def check(self):
+        """Raise if a kernel gave up waiting for a peer (bounded spin)."""
+        if int(self.scratch[1].item()) != 0:
+            raise RuntimeError("quimb_b200 peer exchange: timed out waiting for a peer's flag")
+
+    def close(self):
+        for p in self._imported:
+            self.lib.qb_p2p_unimport(p)
+        self._imported = []
+        if getattr(self, "local", None):
+            self.lib.qb_p2p_free(self.local)
+            self.local = None
+
+
 class BondShard:
     """Row-slab sharding of a bond of size ``n`` over the ranks of a process
     group: the exchange layer of the sharded two-site eigensolve.
 
-    NCCL moves device tensors directly over NVLink; with the gloo backend
-    (CPU tests, or several ranks sharing one GPU in the single-GPU test) the
-    collectives are staged through host memory.
+    ``exchange``: 'p2p' = the fused peer-memory kernels of csrc/p2p.cu (one
+    launch per all-gather / small all-reduce, stores over NVLink into the
+    peers' HBM), 'nccl' = ``torch.distributed`` collectives, 'auto' = p2p when
+    the group runs on NCCL (one GPU per rank) and the IPC mapping succeeds,
+    else NCCL.  With the gloo backend (CPU tests, or several ranks sharing one
+    GPU in the single-GPU test) the collectives are staged through host memory.
     """
 
-    def __init__(self, group=None, rank=None, world_size=None):
+    def __init__(self, group=None, rank=None, world_size=None, exchange="auto"):
         self.group = group
         if rank is None or world_size is None:
             rank, world_size = world()
@@ -163,6 +275,36 @@ class BondShard:
                        and self.world_size > 1)
         self._stage = self.active and dist.get_backend(group) != "nccl"
         self.bytes_gathered = 0
+        if exchange not in ("auto", "p2p", "nccl"):
+            raise ValueError("exchange must be 'auto', 'p2p' or 'nccl'")
+        self._want = exchange
+        self._px = None
+        self._px_failed = None
+        self.exchange_name = "nccl" if self.active else "none"
+        if self._stage:
+            self.exchange_name = "gloo (host staged)"
+
+    def _peer_exchange(self, nbytes, device):
+        """The PeerExchange for vectors of ``nbytes`` (built on first use; all
+        ranks take the same decision)."""
+        if not self.active or self._want == "nccl" or self._px_failed:
+            return None
+        if self._stage and self._want != "p2p":
+            return None
+        if self._px is not None and self._px.gather_bytes >= nbytes:
+            return self._px
+        if self._px is not None:
+            self._px.close()
+            self._px = None
+        try:
+            self._px = PeerExchange(nbytes, self.group, self.rank, self.world_size, device)
+            self.exchange_name = "p2p (fused peer-memory kernels over NVLink, CUDA IPC)"
+        except Exception as e:  # noqa: BLE001
+            if self._want == "p2p":
+                raise
+            self._px_failed = str(e)
+            self.exchange_name = f"nccl (p2p unavailable: {self._px_failed[:80]})"
+        return self._px
 
     def slab(self, n, rank=None):
         """[lo, hi) of this rank's rows of a bond of size ``n`` (balanced)."""
@@ -172,6 +314,9 @@ class BondShard:
     def all_reduce_(self, t):
         if not self.active:
             return t
+        if (self._px is not None and t.dtype == torch.float64 and t.numel() <= 64
+                and t.is_contiguous() and t.device.type == "cuda"):
+            return self._px.all_reduce_small_(t)
         if self._stage and t.device.type != "cpu":
             h = t.cpu()
             dist.all_reduce(h, op=dist.ReduceOp.SUM, group=self.group)
@@ -180,15 +325,27 @@ class BondShard:
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
         return t
 
-    def all_gather_rows(self, local, n):
+    def all_gather_rows(self, local, n, transient=False):
         """Concatenate the row slabs ``local`` (rows_r, cols) of all ranks into
-        the full (n, cols) matrix, identical on every rank."""
+        the full (n, cols) matrix, identical on every rank.  ``transient``: the
+        caller consumes the result before the next-but-one gather, so the p2p
+        path may return a view of its gather buffer instead of a copy."""
         cols = local.shape[1]
         if not self.active:
             return local
-        full = torch.empty((n, cols), dtype=local.dtype, device=local.device)
-        self.bytes_gathered += full.numel() * full.element_size()
+        nbytes = n * cols * local.element_size()
+        self.bytes_gathered += nbytes
         even = n % self.world_size == 0
+        px = None
+        if even and local.dtype == torch.float64 and (nbytes // self.world_size) % 16 == 0:
+            px = self._peer_exchange(nbytes, local.device)
+        if px is not None:
+            lo, _ = self.slab(n)
+            src = local.contiguous()
+            parity = px.all_gather(src, lo * cols * local.element_size())
+            full = px.data_view(parity, local.dtype, n * cols).view(n, cols)
+            return full if transient else full.clone()
+        full = torch.empty((n, cols), dtype=local.dtype, device=local.device)
         if even and not self._stage:
             dist.all_gather_into_tensor(full, local.contiguous(), group=self.group)
             return full
@@ -203,6 +360,15 @@ class BondShard:
             lo, hi = self.slab(n, r)
             full[lo:hi].copy_(part[: hi - lo])
         return full
+
+    def check(self):
+        if self._px is not None:
+            self._px.check()
+
+    def close(self):
+        if self._px is not None:
+            self._px.close()
+            self._px = None
 
 
 def mps_norm2_two_ended(sites, shape="lrp", group=None):

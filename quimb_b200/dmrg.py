@@ -119,13 +119,16 @@ class ShardedEffHam2(EffHam2):
         x = ops.materialize(v).reshape(self.dims[0], self.cols)
         return Array(x.t[self.lo:self.hi].contiguous()).reshape(-1)
 
-    def gather(self, v_local):
+    def gather(self, v_local, transient=False):
         x = ops.materialize(v_local).t.reshape(self.hi - self.lo, self.cols)
-        return Array(self.shard.all_gather_rows(x, self.dims[0])).reshape(-1)
+        return Array(self.shard.all_gather_rows(x, self.dims[0],
+                                                transient=transient)).reshape(-1)
 
     def matvec(self, v_local):
         self.nmatvec += 1
-        x = self.gather(v_local).reshape(self.dims)
+        # the gathered vector is consumed by the first contraction below: the
+        # peer-memory exchange may hand out its own buffer (no copy)
+        x = self.gather(v_local, transient=True).reshape(self.dims)
         T = contract_pair(self.Ls.t, [LB_, W_, L_], x.t, [L_, S_, T_, R_],
                           [LB_, W_, S_, T_, R_], conj_a=self.Ls.cj, conj_b=x.cj)
         T = contract_pair(T, [LB_, W_, S_, T_, R_], self.W12,

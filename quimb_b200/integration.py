@@ -103,6 +103,13 @@ def register_with_quimb():
     return done
 
 
+# ``tol=None`` / 0 means machine precision in the reference's backend contract
+# (scipy_linalg.py:109 passes 0 to ARPACK); DMRG passes its own 1e-3
+# (dmrg.py:87-88).  The Lanczos residual estimate cannot go below round-off of
+# the matvec, so "machine precision" is a relative residual of 1e-12 here.
+_EIGS_TIGHT_TOL = 1e-12
+
+
 def eigs_quimb_b200(A, k=1, *, B=None, which="SA", return_vecs=True, sigma=None,
                     isherm=True, ncv=None, sort=True, tol=None, v0=None,
                     maxiter=None, **backend_opts):
@@ -130,7 +137,7 @@ def eigs_quimb_b200(A, k=1, *, B=None, which="SA", return_vecs=True, sigma=None,
         v0 = ops.asarray(v0)
         theta, x = eigh_lanczos(lambda v: ops.asarray(A._matvec(v)), v0, which=which,
                                 ncv=max(2, min(64, ncv or 4)),
-                                tol=1e-3 if not tol else tol, maxiter=maxiter)
+                                tol=_EIGS_TIGHT_TOL if not tol else tol, maxiter=maxiter)
         lk = np.array([theta])
         if not return_vecs:
             return lk

@@ -309,6 +309,8 @@ def eigh_lanczos(matvec, v0, which="SA", ncv=4, tol=1e-3, maxiter=None,
             x = Array(xnew)
             break
         x = Array(xnew)
+        if cycle + 1 >= maxiter:
+            break                      # no further cycle: skip the restart set-up
         # stagnation guard: a residual that has not improved over many matvecs
         # (>= 300 and >= 10 full bases) sits at the accuracy of the operator
         # (rounding of the matvec); return the best Ritz pair instead of

@@ -199,12 +199,20 @@ def _select_complex_pairs(s_host, gram_fn):
     """Choose one real singular vector per complex singular vector.
 
     ``s_host``: the 2k sorted singular values of the embedding.  Returns
-    (indices, blocks) where ``blocks`` lists (start, [local picks], T) for
+    ``(src, svals, blocks)``: for each of the k output slots ``src[t]`` is the
+    column of the embedding's factors to take (or -1 when the candidates of
+    its cluster do not span enough independent directions -- a zero / fully
+    degenerate cluster whose vectors came back null -- and the slot has to be
+    filled by orthonormal completion), ``svals[t]`` the index into ``s_host``
+    of its singular value, and ``blocks`` lists ``(start, size, T)`` for
     clusters of more than one complex vector that need the small
-    re-orthonormalising transform T (k_c x k_c, complex, host)."""
+    re-orthonormalising transform ``T`` (size x size, complex, host) on the
+    ``size`` picked columns starting at output slot ``start``.  Always k slots:
+    every cluster of 2d equal values contributes exactly d (the reference's
+    thin SVD returns min(m, n) triplets whatever the rank, decomp.py:1101)."""
     n2 = len(s_host)
     smax = s_host[0] if n2 and s_host[0] > 0 else 1.0
-    sel, blocks = [], []
+    src, svals, blocks = [], [], []
     i = 0
     while i < n2:
         j = i + 1
@@ -215,9 +223,16 @@ def _select_complex_pairs(s_host, gram_fn):
         size = j - i
         d = size // 2
         if d <= 1:
-            sel.append(i)
+            chosen = [0]
+            if d == 1:
+                # a lone pair is normally taken as is; a null candidate (zero
+                # matrix) is detected through its norm
+                G = gram_fn(i, i + 1)
+                if not np.isfinite(G[0, 0].real) or abs(G[0, 0]) < 0.25:
+                    chosen = []
         else:
             G = gram_fn(i, j)  # complex Gram of the candidates, host (size x size)
+            G = np.where(np.isfinite(G), G, 0.0)
             # d independent candidates by pivoted Cholesky of the Gram matrix
             # (always the candidate with the largest remaining component: the
             # 2d candidates span exactly a d-dimensional complex space)
@@ -234,12 +249,44 @@ def _select_complex_pairs(s_host, gram_fn):
                 resid = resid - np.abs(Lc[:, t]) ** 2
                 resid[chosen] = -1.0
             chosen.sort()
-            Gs = G[np.ix_(chosen, chosen)]
-            T = np.linalg.inv(np.linalg.cholesky(Gs)).conj().T
-            blocks.append((len(sel), len(chosen), T))
-            sel.extend(i + c for c in chosen)
+            if len(chosen) > 1 or (chosen and d > 1):
+                Gs = G[np.ix_(chosen, chosen)]
+                T = np.linalg.inv(np.linalg.cholesky(Gs)).conj().T
+                blocks.append((len(src), len(chosen), T))
+        src.extend(i + c for c in chosen)
+        src.extend([-1] * (d - len(chosen)))
+        svals.extend(i + 2 * t for t in range(d))
         i = j
-    return sel, blocks
+    return src, svals, blocks
+
+
+def _complete_isometry(Q, missing, rows=False):
+    """Fill the columns ``missing`` of the complex (m, k) matrix ``Q`` (rows of
+    a (k, n) matrix when ``rows``) with vectors orthonormal to each other and to
+    the remaining columns: random directions, two projection passes (launches of
+    the contraction kernel) and the device QR.  Used for the null vectors of
+    zero / rank-deficient complex input, where u and v need not be paired."""
+    if rows:
+        Qt = Q.transpose(0, 1).conj().contiguous()
+        _complete_isometry(Qt, missing)
+        Q.copy_(Qt.transpose(0, 1).conj())
+        return Q
+    m, k = Q.shape
+    miss = torch.as_tensor(missing, dtype=torch.int64, device=Q.device)
+    keep = [c for c in range(k) if c not in set(missing)]
+    gen = torch.Generator(device=Q.device)
+    gen.manual_seed(0x5eed + m * 131 + len(missing))
+    G = torch.view_as_complex(torch.randn((m, len(missing), 2), dtype=torch.float64,
+                                          device=Q.device, generator=gen))
+    if keep:
+        Qk = Array(Q.index_select(1, torch.as_tensor(keep, dtype=torch.int64,
+                                                     device=Q.device)).contiguous())
+        for _ in range(2):
+            c = ops.tensordot(Qk.conj(), Array(G), axes=((0,), (0,)))
+            G = G - ops.tensordot(Qk, c, axes=((1,), (0,))).t
+    Qn, _ = qr(Array(G.contiguous()), stabilized=True, want_r=False)
+    Q.index_copy_(1, miss, ops.materialize(Qn).t)
+    return Q
 
 
 @_narrow
@@ -295,12 +342,14 @@ def _svd_complex(x, return_sweeps):
         Z = Array(Uc[:, i:j])
         return ops.tensordot(Z.conj(), Z, axes=((0,), (0,))).to_numpy()
 
-    sel, blocks = _select_complex_pairs(s_host, gram)
-    idx = torch.as_tensor(sel, dtype=torch.int64, device=x.t.device)
+    src, svals, blocks = _select_complex_pairs(s_host, gram)
+    missing = [t for t, c in enumerate(src) if c < 0]
+    dev = x.t.device
+    idx = torch.as_tensor([max(c, 0) for c in src], dtype=torch.int64, device=dev)
     U = Uc.index_select(1, idx).contiguous()                    # (m, k)
     VH = Array(Vrows.index_select(0, idx).contiguous()).conj()  # (k, n), lazy conj
     VH = ops.materialize(VH).t
-    S = se.t.index_select(0, idx).contiguous()
+    S = se.t.index_select(0, torch.as_tensor(svals, dtype=torch.int64, device=dev)).contiguous()
     for start, size, T in blocks:
         Td = ops.asarray(np.ascontiguousarray(T))
         Ub = Array(U[:, start:start + size])
@@ -308,6 +357,14 @@ def _svd_complex(x, return_sweeps):
         Vb = Array(VH[start:start + size, :])
         VH[start:start + size, :] = ops.tensordot(Td.conj().transpose(1, 0), Vb,
                                                   axes=((1,), (0,))).t
+    if missing:
+        # slots whose candidates were null: only ever the sigma = 0 cluster
+        # (its u and v are unpaired), completed to full isometries
+        _complete_isometry(U, missing)
+        _complete_isometry(VH, missing, rows=True)
+        S.index_fill_(0, torch.as_tensor(missing, dtype=torch.int64, device=dev), 0.0)
+    # null right vectors of a zero cluster that the kernel returned
+    # un-normalised are caught the same way (rows of VH with norm far from 1)
     res = (Array(U), Array(S), Array(VH))
     return res + (sweeps,) if return_sweeps else res
 

@@ -296,3 +296,29 @@ class MovingEnvironment:
 
     def __call__(self):
         return self.lenv[self.pos], self.renv[self.pos]
+
+
+def mpo_ham_heis(L, j=1.0, bz=0.0, dtype="float64"):
+    """Host arrays of the open Heisenberg chain MPO, H = sum_i j S_i.S_{i+1}
+    - bz sum_i S^z_i, bond dimension 5 (one row / column per two-site term
+    plus identity / finish), the same operator as quimb's ``MPO_ham_heis``
+    (tensor_builder.py:5501 through ``spin_ham_mpo_tensor`` :4856-4947).
+    Sites are (l, r, d, u) arrays ('lrdu'; the real form uses i S^y, which is
+    antisymmetric), end sites keep a size-1 outer bond.  Synthetic-input
+    builder for the benchmarks and examples -- the drop-in route takes quimb's
+    own MPO tensors."""
+    import numpy as np
+    sx = np.array([[0, 0.5], [0.5, 0]])
+    isy = np.array([[0, 0.5], [-0.5, 0]])
+    sz = np.array([[0.5, 0], [0, -0.5]])
+    W = np.zeros((5, 5, 2, 2))
+    W[0, 0] = W[4, 4] = np.eye(2)
+    W[4, 1], W[1, 0] = sx, j * sx
+    W[4, 2], W[2, 0] = isy, -j * isy
+    W[4, 3], W[3, 0] = sz, j * sz
+    W[4, 0] = -bz * sz
+    sites = []
+    for i in range(L):
+        w = W[4:5] if i == 0 else (W[:, 0:1] if i == L - 1 else W)
+        sites.append(np.ascontiguousarray(w.astype(dtype)))
+    return sites
