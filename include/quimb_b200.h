@@ -246,6 +246,28 @@ int qb_svd(int dtype, int64_t m, int64_t n, const void *X, void *U, void *S,
 int64_t qb_svd_workspace(int dtype, int64_t m, int64_t n);
 
 /*
+ * Truncated SVD with the reference's epilogue fused in: svd_truncated,
+ * quimb/tensor/decomp.py:829-898 with the keep rule
+ * _compute_number_svals_to_keep (:901-937; cutoff_mode 1..6 = QB_CUTOFF_*,
+ * cutoff <= 0 and renorm == 0: only max_bond applies, max_bond = -1: none),
+ * _compute_svals_renorm_factor (:940-965), the trim (:968-1029) and
+ * _do_absorb (:693-721; `absorb` = QB_ABSORB_*).  X is row-major m x n with
+ * m >= n (the host layer passes the transpose of a wide matrix and swaps the
+ * roles of the factors).  Only the kept rank k = *n_keep is written, compactly:
+ * U as m x k (leading dimension k), S as k values (renormalised), VH as
+ * k x n; factors the absorb mode does not request are not touched and may be
+ * NULL.  The caller provides room for k = n.  *trunc_error = sqrt(sum of the
+ * discarded s^2) (info["error"]); *n_null = number of kept singular values
+ * that are exactly zero (their rows of VH are zero: complete them if an
+ * isometry is needed).  Workspace: qb_svd_workspace(dtype, m, n) bytes.
+ */
+int qb_svd_trunc(int dtype, int64_t m, int64_t n, const void *X, double cutoff,
+                 int cutoff_mode, int64_t max_bond, int absorb, int renorm,
+                 void *U, void *S, void *VH, int64_t *n_keep,
+                 double *trunc_error, int64_t *n_null, void *workspace,
+                 size_t workspace_bytes, int *sweeps_out, void *stream);
+
+/*
  * Host-side truncation rule of svd_truncated's numba core,
  * decomp.py:901-937 (_compute_number_svals_to_keep_numba) followed by the
  * max_bond clamp of decomp.py:1000-1004.  s: host array, descending.

@@ -292,7 +292,7 @@ static bool qr_geometry(int64_t m, int64_t n, QrGeom &g) {
 
 // Householder QR of row-major X (m x n) -> factored F (in workspace), V, T.
 // Q (m x k) and/or R (k x n) formed on request.  k = min(m, n).
-static int qr_f64(int64_t m, int64_t n, const double *X, double *Q, double *R,
+int qr_f64(int64_t m, int64_t n, const double *X, double *Q, double *R,
                   int stabilized, double *ws, cudaStream_t st) {
   QrGeom g;
   if (!qr_geometry(m, n, g)) {
@@ -358,6 +358,12 @@ static int qr_f64(int64_t m, int64_t n, const double *X, double *Q, double *R,
     QB_LAUNCH_CHECK();
   }
   return 0;
+}
+
+int64_t qr_workspace_doubles(int64_t m, int64_t n) {
+  QrGeom g;
+  if (!qr_geometry(m, n, g)) return -1;
+  return g.total;
 }
 
 }  // namespace qb
@@ -915,7 +921,7 @@ static bool svd_geometry(int64_t m, int64_t n, SvdGeom &g) {
 }
 
 // SVD of row-major X (m x n), m >= n.  U (m x n), S (n), VH (n x n).
-static int svd_tall_f64(int64_t m, int64_t n, const double *X, double *U,
+int svd_tall_f64_v1(int64_t m, int64_t n, const double *X, double *U,
                         double *S, double *VH, double *ws, int *sweeps_out,
                         cudaStream_t st) {
   SvdGeom g;
@@ -1026,46 +1032,10 @@ static int svd_tall_f64(int64_t m, int64_t n, const double *X, double *U,
   return 0;
 }
 
+int64_t svd_v1_workspace_doubles(int64_t m, int64_t n) {
+  SvdGeom g;
+  if (!svd_geometry(m, n, g)) return -1;
+  return g.total;
+}
+
 }  // namespace qb
-
-extern "C" {
-
-int64_t qb_svd_workspace(int dtype, int64_t m, int64_t n) {
-  if (dtype != QB_F64) return -1;
-  qb::SvdGeom g;
-  const int64_t mm = std::max(m, n), nn = std::min(m, n);
-  if (!qb::svd_geometry(mm, nn, g)) return -2;
-  return g.total * 8;
-}
-
-int qb_svd(int dtype, int64_t m, int64_t n, const void *X, void *U, void *S,
-           void *VH, void *workspace, size_t workspace_bytes, int *sweeps_out,
-           void *stream) {
-  using namespace qb;
-  if (dtype != QB_F64) {
-    set_error("qb_svd: only f64 is implemented (got dtype %d)", dtype);
-    return -1;
-  }
-  if (m <= 0 || n <= 0) return 0;
-  const int64_t need = qb_svd_workspace(dtype, m, n);
-  if (need < 0) {
-    set_error("qb_svd: unsupported shape %lld x %lld", (long long)m, (long long)n);
-    return -2;
-  }
-  if (!workspace || (int64_t)workspace_bytes < need) {
-    set_error("qb_svd: workspace too small (need %lld bytes)", (long long)need);
-    return -8;
-  }
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  double *ws = static_cast<double *>(workspace);
-  if (m >= n)
-    return svd_tall_f64(m, n, (const double *)X, (double *)U, (double *)S,
-                        (double *)VH, ws, sweeps_out, st);
-  // wide matrices: the host layer factors the transpose (a strided view
-  // materialised by qb_permute) and swaps the roles of U and VH.
-  (void)st; (void)ws;
-  set_error("qb_svd: m < n -- pass the transpose (m >= n required)");
-  return -2;
-}
-
-}  // extern "C"

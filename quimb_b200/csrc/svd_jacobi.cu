@@ -1,0 +1,909 @@
+// qb_svd / qb_svd_trunc <- svd_truncated (quimb/tensor/decomp.py:829-1118):
+// thin SVD by one-sided block Jacobi on the R factor of a QR preconditioner,
+// with the reference's truncation rule (:901-937), renormalisation (:940-965),
+// trimming (:968-1029) and absorption of the singular values (:693-721) fused
+// into the epilogue, so that a truncated split is ONE library call that
+// writes exactly the kept factors.
+//
+// Round structure (what changed against the round-1 kernel, which is kept in
+// linalg.cu as the `QB_JAC_MODE=v1` A/B reference):
+//
+//   * a sweep is cut into INDEPENDENT sub-tournaments (2 or 4 groups of column
+//     blocks: round robin inside every group, then bipartite rounds between
+//     groups, themselves split into independent halves), each running on its
+//     own CUDA stream.  Launches of different streams are co-resident on an SM
+//     (2-4 CTAs per SM), so the latency-bound 32 x 32 eigen-solve of one pair
+//     overlaps the DMMA-bound Gram / apply phases of others -- the phases of
+//     one launch all coincide, which is what left the tensor pipe 33 % busy;
+//   * a column-block pair is owned by a CLUSTER of 4 or 8 CTAs (rows dealt in
+//     chunks), 256 or 512 CTAs per round over all streams: all 148 SMs busy;
+//   * the partial Gram is computed with each warp owning one 16 x 8 output
+//     tile over all rows of the chunk: no cross-warp reduction, only the
+//     fixed-order cluster reduction through distributed shared memory;
+//   * rotations from two rsqrt (cos 2t = |a| r, u = (1 + cos 2t) / 2,
+//     c = u rsqrt(u), s = sin 2t rsqrt(u) / 2) instead of sqrt + divide +
+//     rsqrt: half the dependent latency of a Jacobi step, same rounding-level
+//     orthogonality;
+//   * the sweep that would only confirm convergence is skipped when the
+//     largest scaled off-diagonal met in a sweep is below 1e-9 (one more
+//     rotation of a quadratically convergent iteration is at round-off).
+#include <cooperative_groups.h>
+#include <math.h>
+#include <stdlib.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "internal.h"
+
+namespace qb {
+
+int svd_tall_f64_v1(int64_t m, int64_t n, const double *X, double *U, double *S,
+                    double *VH, double *ws, int *sweeps_out, cudaStream_t st);
+int64_t svd_v1_workspace_doubles(int64_t m, int64_t n);
+int qr_f64(int64_t m, int64_t n, const double *X, double *Q, double *R,
+           int stabilized, double *ws, cudaStream_t st);
+int64_t qr_workspace_doubles(int64_t m, int64_t n);
+
+namespace jac2 {
+
+constexpr int JB = 16;          // columns per block
+constexpr int JP = 2 * JB;      // columns per pair
+constexpr int JPITCH = JP + 4;  // smem pitch (== 4 mod 16 doubles)
+
+struct Params {
+  double *W;       // rows_w x ld  working matrix (columns get orthogonalised)
+  double *V;       // rows_v x ld  accumulated right rotations
+  int64_t ld;
+  int rows_w, rows_v;
+  const int2 *pairs;  // column-block pairs of this launch (one per cluster)
+  double tol;
+  int *flag;                     // set to 1 when any pair still needed rotating
+  unsigned long long *offmax;    // max scaled off-diagonal met (double bits)
+  int inner_max;
+  unsigned long long *trace;
+  int trace_slot;
+};
+
+__device__ __forceinline__ unsigned long long now_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define J2_TRACE(ph)                                                       \
+  do {                                                                     \
+    if (P.trace && blockIdx.x == 0 && threadIdx.x == 0)                    \
+      P.trace[(size_t)P.trace_slot * 8 + (ph)] = now_ns();              \
+  } while (0)
+
+__device__ __forceinline__ void rr_pair(int k, int round, int nblk, int &p, int &q) {
+  const int m = nblk - 1;
+  int a, b;
+  if (k == 0) { a = m; b = round; }
+  else { a = (round + k) % m; b = (round - k + m) % m; }
+  p = min(a, b); q = max(a, b);
+}
+
+template <int CH>
+__device__ __forceinline__ void load_chunk(double (*Xs)[JPITCH], const double *M,
+                                           int64_t ld, int rows, int row0,
+                                           int cp, int cq, int tid) {
+#pragma unroll
+  for (int i = 0; i < CH / 16; ++i) {
+    const int idx = tid + 256 * i;       // CH * 16 double2 per chunk
+    const int r = idx >> 4, c2 = (idx & 15) * 2;
+    const int gc = (c2 < JB) ? (cp + c2) : (cq + c2 - JB);
+    const int gr = row0 + r;
+    const bool ok = gr < rows;
+    const double *src = ok ? (M + (int64_t)gr * ld + gc) : M;
+    cp_async16(smem_u32(&Xs[r][c2]), src, ok ? 16 : 0);
+  }
+}
+
+template <int CH, int STG>
+struct Smem {
+  double Xs[STG][CH][JPITCH];
+  double Gb[2][JP][JP + 1];
+  double Gpart[JP][JP];
+  double Jm[JP][JPITCH];
+  double redmax[8];
+  int rank_s[JP];
+};
+
+// One round of one sub-tournament: cluster c of the launch owns pair
+// P.pairs[c]; see the file header.  CH rows per streamed chunk, STG cp.async
+// stages; the cluster size comes from the launch attribute.
+template <int CH, int STG, int MINB>
+__global__ void __launch_bounds__(256, MINB) jacobi_round_kernel(const Params P) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int CS = (int)cluster.num_blocks();
+  extern __shared__ __align__(16) unsigned char jac2_smem[];
+  Smem<CH, STG> &S = *reinterpret_cast<Smem<CH, STG> *>(jac2_smem);
+  double(*G)[JP + 1] = S.Gb[0];
+  double(*Gn)[JP + 1] = S.Gb[1];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int2 pr = P.pairs[blockIdx.x / CS];
+  const int cp = pr.x * JB, cq = pr.y * JB;
+
+  J2_TRACE(0);
+  // ---------------- phase 1: partial Gram over this CTA's row chunks --------
+  // warp (ta, tj) owns the 16 x 8 tile rows ta*16.., cols tj*8.. of the Gram
+  {
+    const int ta = warp >> 2, tj = warp & 3;
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    const int nch_all = (P.rows_w + CH - 1) / CH;
+    const int nmine = (nch_all - rank + CS - 1) / CS;  // chunks rank, rank+CS, ...
+    auto issue = [&](int i) {
+      if (i < nmine)
+        load_chunk<CH>(S.Xs[i % STG], P.W, P.ld, P.rows_w, (rank + i * CS) * CH, cp, cq, tid);
+      cp_async_commit();
+    };
+    for (int s = 0; s < STG - 1; ++s) issue(s);
+    for (int i = 0; i < nmine; ++i) {
+      cp_async_wait<STG - 2>();
+      __syncthreads();
+      issue(i + STG - 1);
+      const double(*X)[JPITCH] = S.Xs[i % STG];
+#pragma unroll
+      for (int kb = 0; kb < CH; kb += 8) {
+        double af[4], bf[2];
+        af[0] = X[kb + t][ta * 16 + g];
+        af[1] = X[kb + t][ta * 16 + g + 8];
+        af[2] = X[kb + t + 4][ta * 16 + g];
+        af[3] = X[kb + t + 4][ta * 16 + g + 8];
+        bf[0] = X[kb + t][tj * 8 + g];
+        bf[1] = X[kb + t + 4][tj * 8 + g];
+        dmma_16x8x8(acc, af, bf);
+      }
+    }
+    cp_async_wait<0>();
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+      *reinterpret_cast<double2 *>(&S.Gpart[ta * 16 + g + h * 8][tj * 8 + 2 * t]) =
+          make_double2(acc[2 * h], acc[2 * h + 1]);
+  }
+  J2_TRACE(1);
+  cluster.sync();
+  // full Gram = sum over the cluster (same order everywhere), symmetrised
+  for (int idx = tid; idx < JP * JP; idx += 256) {
+    const int r = idx / JP, c = idx % JP;
+    double s = 0.0;
+    for (int q = 0; q < CS; ++q) {
+      const double *gp = cluster.map_shared_rank(&S.Gpart[0][0], q);
+      s += 0.5 * (gp[r * JP + c] + gp[c * JP + r]);
+    }
+    G[r][c] = s;
+    S.Jm[r][c] = (r == c) ? 1.0 : 0.0;
+  }
+  __syncthreads();
+  auto offmax = [&]() -> double {
+    double mx = 0.0;
+    for (int idx = tid; idx < JP * JP; idx += 256) {
+      const int r = idx / JP, c = idx % JP;
+      if (r < c) {
+        const double d = G[r][r] * G[c][c];
+        const double v = fabs(G[r][c]);
+        if (d > 0.0) mx = fmax(mx, v * rsqrt(d));
+        else if (v > 0.0) mx = fmax(mx, 1.0);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) S.redmax[warp] = mx;
+    __syncthreads();
+    double m2 = 0.0;
+    for (int w = 0; w < 8; ++w) m2 = fmax(m2, S.redmax[w]);
+    __syncthreads();
+    return m2;
+  };
+  const double off0 = offmax();
+  J2_TRACE(2);
+  if (tid == 0 && rank == 0)
+    atomicMax(P.offmax, (unsigned long long)__double_as_longlong(off0));
+  // all CTAs of the cluster take the same decision (same G)
+  if (off0 <= P.tol) {
+    cluster.sync();  // peers may still be reading our Gpart
+    return;
+  }
+  if (tid == 0 && rank == 0) atomicOr(P.flag, 1);
+
+  // ---------------- phase 2: J^T G J = diag by cyclic Jacobi ----------------
+  for (int sweep = 0; sweep < P.inner_max; ++sweep) {
+    if (sweep > 0) {
+      const double off = offmax();
+      if (off <= 1e-15 || off <= 1e-4 * off0) break;
+    }
+    for (int step = 0; step < JP - 1; ++step) {
+      // thread (k1, k2) owns the 2x2 block (rows of pair k1) x (columns of
+      // pair k2); the 16 rotations of the step are computed once per warp
+      // (lanes 0-15, same instruction sequence everywhere -> bit-identical
+      // c, s in all warps and all CTAs of the cluster), handed out by shuffles
+      const int k1 = tid >> 4, k2 = tid & 15;
+      int p1, q1, p2, q2;
+      rr_pair(k1, step, JP, p1, q1);
+      rr_pair(k2, step, JP, p2, q2);
+      double c = 1.0, s = 0.0;
+      if (lane < 16) {  // lane == k2 here
+        const double app = G[p2][p2], aqq = G[q2][q2], apq = G[p2][q2];
+        if (fabs(apq) > 1e-300) {
+          // tan 2t = b / a with a = aqq - app, b = 2 apq, |t| <= pi / 4
+          const double a = __dsub_rn(aqq, app), b = __dmul_rn(2.0, apq);
+          const double n2 = __fma_rn(a, a, __dmul_rn(b, b));
+          if (n2 > 1e-280 && n2 < 1e280) {
+            const double r = rsqrt(n2);
+            const double c2t = __dmul_rn(fabs(a), r);                       // cos 2t >= 0
+            const bool neg = (a < 0.0) != (b < 0.0);                        // sign of a b
+            const double s2t = __dmul_rn(neg ? -fabs(b) : fabs(b), r);      // sin 2t
+            const double u = __fma_rn(0.5, c2t, 0.5);                       // cos^2 t
+            const double ru = rsqrt(u);
+            c = __dmul_rn(u, ru);
+            s = __dmul_rn(__dmul_rn(0.5, s2t), ru);
+          } else {
+            // badly scaled pair: the textbook formula on the ratio
+            const double tt = copysign(fabs(b), __dmul_rn(a, b)) / (fabs(a) + hypot(a, b));
+            c = rsqrt(__fma_rn(tt, tt, 1.0));
+            s = __dmul_rn(c, tt);
+          }
+        }
+      }
+      const double c2 = __shfl_sync(0xffffffffu, c, k2), s2 = __shfl_sync(0xffffffffu, s, k2);
+      const double c1 = __shfl_sync(0xffffffffu, c, k1), s1 = __shfl_sync(0xffffffffu, s, k1);
+      {
+        const double gpp = G[p1][p2], gpq = G[p1][q2], gqp = G[q1][p2], gqq = G[q1][q2];
+        const double a0 = c2 * gpp - s2 * gpq, a1 = s2 * gpp + c2 * gpq;
+        const double b0 = c2 * gqp - s2 * gqq, b1 = s2 * gqp + c2 * gqq;
+        double n00 = c1 * a0 - s1 * b0, n01 = c1 * a1 - s1 * b1;
+        double n10 = s1 * a0 + c1 * b0, n11 = s1 * a1 + c1 * b1;
+        if (k1 == k2) { n01 = 0.0; n10 = 0.0; }  // the annihilated pair
+        Gn[p1][p2] = n00; Gn[p1][q2] = n01; Gn[q1][p2] = n10; Gn[q1][q2] = n11;
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+          const int r = k1 + 16 * it;
+          const double jp = S.Jm[r][p2], jq = S.Jm[r][q2];
+          S.Jm[r][p2] = c2 * jp - s2 * jq;
+          S.Jm[r][q2] = s2 * jp + c2 * jq;
+        }
+      }
+      __syncthreads();
+      { double(*tmp)[JP + 1] = G; G = Gn; Gn = tmp; }
+    }
+  }
+  J2_TRACE(3);
+  // sort: larger column norms first (ties by index) -> new column order
+  if (tid < JP) {
+    const double d = G[tid][tid];
+    int rk = 0;
+    for (int j = 0; j < JP; ++j) {
+      const double dj = G[j][j];
+      rk += (dj > d) || (dj == d && j < tid);
+    }
+    S.rank_s[tid] = rk;
+  }
+  __syncthreads();
+  for (int idx = tid; idx < JP * JP; idx += 256) {
+    const int r = idx / JP, c = idx % JP;
+    G[r][S.rank_s[c]] = S.Jm[r][c];
+  }
+  __syncthreads();
+  for (int idx = tid; idx < JP * JP; idx += 256) {
+    const int r = idx / JP, c = idx % JP;
+    S.Jm[r][c] = G[r][c];
+  }
+  __syncthreads();
+
+  J2_TRACE(4);
+  // ---------------- phase 3: apply J to this CTA's rows of W and V ----------
+  {
+    constexpr int RT = CH / 16;       // 16-row tiles per chunk
+    constexpr int CG = 8 / RT;        // column groups (warps per row tile)
+    constexpr int NT = 4 / CG;        // 8-column tiles per warp
+    const int nchw = (P.rows_w + CH - 1) / CH, nchv = (P.rows_v + CH - 1) / CH;
+    const int ntot = nchw + nchv;
+    const int nmine = (ntot - rank + CS - 1) / CS;
+    auto chunk_src = [&](int i, double *&M, int &rows, int &row0) {
+      const int ch = rank + i * CS;
+      if (ch < nchw) { M = P.W; rows = P.rows_w; row0 = ch * CH; }
+      else { M = P.V; rows = P.rows_v; row0 = (ch - nchw) * CH; }
+    };
+    auto issue = [&](int i) {
+      if (i < nmine) {
+        double *M; int rows, row0;
+        chunk_src(i, M, rows, row0);
+        load_chunk<CH>(S.Xs[i % STG], M, P.ld, rows, row0, cp, cq, tid);
+      }
+      cp_async_commit();
+    };
+    for (int s = 0; s < STG - 1; ++s) issue(s);
+    const int mt = warp % RT, nh = warp / RT;
+    // this warp's slice of J stays in registers for the whole phase
+    double bj[JP / 8][NT][2];
+#pragma unroll
+    for (int kk = 0; kk < JP / 8; ++kk)
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        bj[kk][j][0] = S.Jm[kk * 8 + t][nh * (8 * NT) + j * 8 + g];
+        bj[kk][j][1] = S.Jm[kk * 8 + t + 4][nh * (8 * NT) + j * 8 + g];
+      }
+    for (int i = 0; i < nmine; ++i) {
+      cp_async_wait<STG - 2>();
+      __syncthreads();
+      issue(i + STG - 1);
+      double *M; int rows, row0;
+      chunk_src(i, M, rows, row0);
+      const double(*X)[JPITCH] = S.Xs[i % STG];
+      double c2[NT][4];
+#pragma unroll
+      for (int j = 0; j < NT; ++j)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) c2[j][v] = 0.0;
+#pragma unroll
+      for (int kk = 0; kk < JP / 8; ++kk) {
+        double af[4];
+        af[0] = X[mt * 16 + g][kk * 8 + t];
+        af[1] = X[mt * 16 + g + 8][kk * 8 + t];
+        af[2] = X[mt * 16 + g][kk * 8 + t + 4];
+        af[3] = X[mt * 16 + g + 8][kk * 8 + t + 4];
+#pragma unroll
+        for (int j = 0; j < NT; ++j) dmma_16x8x8(c2[j], af, bj[kk][j]);
+      }
+#pragma unroll
+      for (int j = 0; j < NT; ++j)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int r = row0 + mt * 16 + g + h * 8;
+          const int c = nh * (8 * NT) + j * 8 + 2 * t;  // column within the pair
+          if (r < rows) {
+            const int gc = (c < JB) ? (cp + c) : (cq + c - JB);
+            *reinterpret_cast<double2 *>(M + (int64_t)r * P.ld + gc) =
+                make_double2(c2[j][2 * h], c2[j][2 * h + 1]);
+          }
+        }
+    }
+    cp_async_wait<0>();
+  }
+  J2_TRACE(5);
+  cluster.sync();  // nobody exits while peers may read its shared memory
+  J2_TRACE(6);
+}
+
+// ---------------------------------------------------------------- schedule ---
+// A sweep as a list of phases; inside a phase `ngroups` independent launch
+// sequences (one per stream), each a list of rounds, each round a list of
+// column-block pairs (disjoint blocks).
+struct Phase {
+  // rounds[g][r] = (offset into the pair array, number of pairs)
+  std::vector<std::vector<std::pair<int, int>>> rounds;
+};
+
+static void rr_rounds(const std::vector<int> &blk, std::vector<std::vector<int2>> &out) {
+  // circle-method round robin over the blocks in `blk` (odd count: one bye)
+  std::vector<int> b = blk;
+  if (b.size() % 2) b.push_back(-1);
+  const int nb = (int)b.size(), m = nb - 1;
+  for (int round = 0; round < m; ++round) {
+    std::vector<int2> prs;
+    for (int k = 0; k < nb / 2; ++k) {
+      int x, y;
+      if (k == 0) { x = m; y = round; }
+      else { x = (round + k) % m; y = (round - k + m) % m; }
+      int p = b[x], q = b[y];
+      if (p < 0 || q < 0) continue;
+      prs.push_back(make_int2(std::min(p, q), std::max(p, q)));
+    }
+    if (!prs.empty()) out.push_back(prs);
+  }
+}
+
+static void bip_rounds(const std::vector<int> &A, const std::vector<int> &B,
+                       std::vector<std::vector<int2>> &out) {
+  // all pairs A x B, |A| <= |B|: round r pairs A[i] with B[(i + r) % |B|]
+  const std::vector<int> &a = A.size() <= B.size() ? A : B;
+  const std::vector<int> &b = A.size() <= B.size() ? B : A;
+  const int nb = (int)b.size();
+  for (int r = 0; r < nb; ++r) {
+    std::vector<int2> prs;
+    for (int i = 0; i < (int)a.size(); ++i) {
+      const int p = a[i], q = b[(i + r) % nb];
+      prs.push_back(make_int2(std::min(p, q), std::max(p, q)));
+    }
+    if (!prs.empty()) out.push_back(prs);
+  }
+}
+
+struct Schedule {
+  std::vector<int2> pairs;                 // flat
+  std::vector<Phase> phases;
+  int ngroups = 1;
+};
+
+static std::vector<int> slice(const std::vector<int> &v, int lo, int hi) {
+  return std::vector<int>(v.begin() + lo, v.begin() + hi);
+}
+
+static void build_schedule(int nblk, int ngroups, Schedule &S) {
+  S.pairs.clear(); S.phases.clear(); S.ngroups = ngroups;
+  std::vector<int> all(nblk);
+  for (int i = 0; i < nblk; ++i) all[i] = i;
+  auto add_phase = [&](const std::vector<std::vector<std::vector<int2>>> &groups) {
+    Phase ph;
+    for (const auto &gr : groups) {
+      std::vector<std::pair<int, int>> rr;
+      for (const auto &round : gr) {
+        rr.emplace_back((int)S.pairs.size(), (int)round.size());
+        S.pairs.insert(S.pairs.end(), round.begin(), round.end());
+      }
+      ph.rounds.push_back(rr);
+    }
+    S.phases.push_back(ph);
+  };
+  if (ngroups <= 1 || nblk < 4 * ngroups) {
+    S.ngroups = 1;
+    std::vector<std::vector<int2>> r;
+    rr_rounds(all, r);
+    add_phase({r});
+    return;
+  }
+  // the blocks in `ngroups` contiguous sets, each set in two halves
+  const int G = ngroups;
+  std::vector<std::vector<int>> set(G);
+  for (int s = 0; s < G; ++s) set[s] = slice(all, nblk * s / G, nblk * (s + 1) / G);
+  auto halves = [](const std::vector<int> &v, std::vector<int> &a, std::vector<int> &b) {
+    const int h = (int)v.size() / 2;
+    a = slice(v, 0, h); b = slice(v, h, (int)v.size());
+  };
+  // phase A: round robin inside every set
+  {
+    std::vector<std::vector<std::vector<int2>>> groups(G);
+    for (int s = 0; s < G; ++s) rr_rounds(set[s], groups[s]);
+    add_phase(groups);
+  }
+  // phases B..: the sets meet pairwise (round robin over the sets); a meeting
+  // of two sets is all pairs A x B, run as two independent halves at a time:
+  // (Aa x Ba, Ab x Bb) then (Aa x Bb, Ab x Ba) -> G groups per phase again
+  std::vector<int> sid(G);
+  for (int s = 0; s < G; ++s) sid[s] = s;
+  std::vector<std::vector<int2>> meet;
+  rr_rounds(sid, meet);
+  for (const auto &mr : meet) {
+    for (int cross = 0; cross < 2; ++cross) {
+      std::vector<std::vector<std::vector<int2>>> groups;
+      for (const int2 &ab : mr) {
+        std::vector<int> Aa, Ab, Ba, Bb;
+        halves(set[ab.x], Aa, Ab);
+        halves(set[ab.y], Ba, Bb);
+        std::vector<std::vector<int2>> g0, g1;
+        if (cross == 0) { bip_rounds(Aa, Ba, g0); bip_rounds(Ab, Bb, g1); }
+        else { bip_rounds(Aa, Bb, g0); bip_rounds(Ab, Ba, g1); }
+        groups.push_back(g0);
+        groups.push_back(g1);
+      }
+      add_phase(groups);
+    }
+  }
+}
+
+// ------------------------------------------------------------ small kernels ---
+__global__ void __launch_bounds__(256)
+    colnorm_kernel(const double *__restrict__ W, int64_t ld, int rows, int ncols,
+                   double *__restrict__ out) {
+  __shared__ double sh[8][33];
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int ry = threadIdx.x >> 5;
+  double s = 0.0;
+  if (c < ncols)
+    for (int r = ry; r < rows; r += 8) {
+      const double v = W[(int64_t)r * ld + c];
+      s += v * v;
+    }
+  sh[ry][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (ry == 0 && c < ncols) {
+    double tot = 0.0;
+    for (int k = 0; k < 8; ++k) tot += sh[k][threadIdx.x & 31];
+    out[c] = sqrt(tot);
+  }
+}
+
+// UR[:, k] = Z[:, perm[k]] * ls[k]   (rows_w x nk, row-major, ld nk), and
+// VH[k, :] = (W[:, perm[k]] / s[perm[k]]) * rs[k]   (nk x rows_w): the kept
+// columns only, with the absorbed powers of the singular values folded in.
+__global__ void __launch_bounds__(256)
+    gather_scaled_kernel(const double *__restrict__ W, const double *__restrict__ Z,
+                         int64_t ld, int n, int nk, const int *__restrict__ perm,
+                         const double *__restrict__ s, const double *__restrict__ lscale,
+                         const double *__restrict__ rscale, double *__restrict__ UR,
+                         double *__restrict__ VH) {
+  const int64_t tot_u = UR ? (int64_t)n * nk : 0, tot_v = VH ? (int64_t)nk * n : 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < tot_u + tot_v;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    if (i < tot_u) {
+      const int64_t r = i / nk;
+      const int k = (int)(i - r * nk);
+      UR[i] = Z[r * ld + perm[k]] * lscale[k];
+    } else {
+      const int64_t j = i - tot_u;
+      const int k = (int)(j / n);
+      const int64_t r = j - (int64_t)k * n;
+      const int c = perm[k];
+      const double sv = s[c];
+      VH[j] = (sv > 0.0) ? (W[r * ld + c] / sv) * rscale[k] : 0.0;
+    }
+  }
+}
+
+__global__ void pad_copy_kernel(const double *__restrict__ src, int64_t rows,
+                                int64_t cols, int64_t ld_src, double *__restrict__ dst,
+                                int64_t ld_dst, int64_t rows_dst, int mode) {
+  // mode 1: identity; mode 2: dst = [src^T | 0]
+  const int64_t tot = rows_dst * ld_dst;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < tot;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / ld_dst, c = i - r * ld_dst;
+    double v = 0.0;
+    if (mode == 1) v = (r == c) ? 1.0 : 0.0;
+    else if (r < rows && c < cols) v = src[c * ld_src + r];
+    dst[i] = v;
+  }
+}
+
+// ------------------------------------------------------------------ driver ---
+struct Geom {
+  int64_t npad, qr_off, q1_off, r_off, w_off, v_off, s_off, ur_off, perm_off,
+      flag_off, pairs_off, scale_off, total;
+};
+
+static bool geometry(int64_t m, int64_t n, Geom &g) {
+  const int64_t q = qr_workspace_doubles(m, n);
+  if (q < 0) return false;
+  g.npad = ((n + JP - 1) / JP) * JP;
+  auto al = [](int64_t x) { return (x + 31) / 32 * 32; };
+  int64_t off = 0;
+  g.qr_off = off; off += al(q);
+  g.q1_off = off; off += al(m * n);
+  g.r_off = off; off += al(n * n);
+  g.w_off = off; off += al(n * g.npad);
+  g.v_off = off; off += al(g.npad * g.npad);
+  g.s_off = off; off += al(g.npad);
+  g.ur_off = off; off += al(n * n);
+  g.perm_off = off; off += al((g.npad + 1) / 2 + 1);
+  g.flag_off = off; off += 32;
+  const int64_t nblk = g.npad / JB;
+  g.pairs_off = off; off += al(nblk * (nblk - 1) / 2 + 8);   // int2 == one double each
+  g.scale_off = off; off += al(2 * n);
+  g.total = off;
+  return true;
+}
+
+struct Config { int cs, ch, stg, groups; };
+
+static Config pick_config(int nblk) {
+  static const Config env = [] {
+    Config c{0, 0, 0, 0};
+    if (const char *e = getenv("QB_JAC_CS")) c.cs = atoi(e);
+    if (const char *e = getenv("QB_JAC_CH")) c.ch = atoi(e);
+    if (const char *e = getenv("QB_JAC_STG")) c.stg = atoi(e);
+    if (const char *e = getenv("QB_JAC_GROUPS")) c.groups = atoi(e);
+    return c;
+  }();
+  Config c{8, 32, 2, 4};
+  if (nblk < 64) { c.cs = 4; c.groups = 2; }
+  if (nblk < 16) { c.cs = 2; c.groups = 1; }
+  if (env.cs == 1 || env.cs == 2 || env.cs == 4 || env.cs == 8) c.cs = env.cs;
+  if (env.ch == 32 || env.ch == 64) c.ch = env.ch;
+  if (env.stg >= 2 && env.stg <= 4) c.stg = env.stg;
+  if (env.groups == 1 || env.groups == 2 || env.groups == 4) c.groups = env.groups;
+  while (c.groups > 1 && (nblk < 4 * c.groups || nblk % (2 * c.groups))) c.groups /= 2;
+  return c;
+}
+
+template <int CH, int STG, int MINB>
+static int launch_round(const Params &P, int npairs, int cs, cudaStream_t st) {
+  auto kern = jacobi_round_kernel<CH, STG, MINB>;
+  const size_t smem = sizeof(Smem<CH, STG>);
+  static bool attr_set = false;
+  if (!attr_set) {
+    QB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem));
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(npairs * cs), 1, 1);
+  cfg.blockDim = dim3(256, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)cs;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  QB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, P));
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+
+static int launch_round_cfg(const Config &c, const Params &P, int npairs, cudaStream_t st) {
+  if (c.ch == 64) {
+    if (c.stg >= 4) return launch_round<64, 4, 1>(P, npairs, c.cs, st);
+    if (c.stg == 3) return launch_round<64, 3, 2>(P, npairs, c.cs, st);
+    return launch_round<64, 2, 2>(P, npairs, c.cs, st);
+  }
+  if (c.stg >= 4) return launch_round<32, 4, 3>(P, npairs, c.cs, st);
+  if (c.stg == 3) return launch_round<32, 3, 3>(P, npairs, c.cs, st);
+  return launch_round<32, 2, 4>(P, npairs, c.cs, st);
+}
+
+struct SideStreams {
+  cudaStream_t s[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t fork = nullptr, join[4] = {nullptr, nullptr, nullptr, nullptr};
+  bool ok = false;
+};
+static SideStreams &side_streams() {
+  static thread_local SideStreams S;
+  if (!S.ok) {
+    for (int i = 0; i < 4; ++i) {
+      cudaStreamCreateWithFlags(&S.s[i], cudaStreamNonBlocking);
+      cudaEventCreateWithFlags(&S.join[i], cudaEventDisableTiming);
+    }
+    cudaEventCreateWithFlags(&S.fork, cudaEventDisableTiming);
+    S.ok = true;
+  }
+  return S;
+}
+
+// Jacobi iteration on W (n x npad, ld npad) accumulating rotations in Z
+// (npad x npad).  Returns the number of sweeps (negative: error code).
+static int jacobi_iterate(double *W, double *Z, int64_t n, int64_t npad, int2 *d_pairs,
+                          int *flag, int *sweeps_out, cudaStream_t st) {
+  const int nblk = (int)(npad / JB);
+  const Config cfg = pick_config(nblk);
+  Schedule sched;
+  build_schedule(nblk, cfg.groups, sched);
+  QB_CUDA_CHECK(cudaMemcpyAsync(d_pairs, sched.pairs.data(), sizeof(int2) * sched.pairs.size(),
+                                cudaMemcpyHostToDevice, st));
+  Params P;
+  P.W = W; P.V = Z; P.ld = npad; P.rows_w = (int)n; P.rows_v = (int)npad;
+  P.tol = 1e-15 * sqrt((double)n) * 8.0;
+  P.flag = flag;
+  P.offmax = reinterpret_cast<unsigned long long *>(flag + 2);
+  P.trace = trace_buffer() ? trace_buffer() + 16 * 8192 : nullptr;
+  static const int inner0 = [] { const char *e = getenv("QB_JAC_INNER"); return e ? atoi(e) : 1; }();
+  SideStreams &SS = side_streams();
+  const bool multi = sched.ngroups > 1;
+  int sweeps = 0;
+  const int max_sweeps = 60;
+  int slot = 0;
+  bool done = false;
+  for (; sweeps < max_sweeps && !done; ++sweeps) {
+    P.inner_max = (sweeps < 25) ? inner0 : std::max(inner0, 4);
+    QB_CUDA_CHECK(cudaMemsetAsync(flag, 0, 16, st));
+    for (const Phase &ph : sched.phases) {
+      if (multi) QB_CUDA_CHECK(cudaEventRecord(SS.fork, st));
+      for (size_t g = 0; g < ph.rounds.size(); ++g) {
+        cudaStream_t gs = multi ? SS.s[g % 4] : st;
+        if (multi) QB_CUDA_CHECK(cudaStreamWaitEvent(gs, SS.fork, 0));
+        for (const auto &rd : ph.rounds[g]) {
+          P.pairs = d_pairs + rd.first;
+          P.trace_slot = (slot++) & 1023;
+          int rc = launch_round_cfg(cfg, P, rd.second, gs);
+          if (rc) return -rc;
+        }
+        if (multi) {
+          QB_CUDA_CHECK(cudaEventRecord(SS.join[g % 4], gs));
+          QB_CUDA_CHECK(cudaStreamWaitEvent(st, SS.join[g % 4], 0));
+        }
+      }
+    }
+    struct { int flag; int pad; unsigned long long off; } h = {0, 0, 0};
+    QB_CUDA_CHECK(cudaMemcpyAsync(&h, flag, 16, cudaMemcpyDeviceToHost, st));
+    QB_CUDA_CHECK(cudaStreamSynchronize(st));
+    double off;
+    memcpy(&off, &h.off, 8);
+    // converged: nothing rotated, or everything that rotated was already so
+    // small that the rotation itself finished the job (quadratic convergence)
+    if (!h.flag || off < 1e-9) done = true;
+  }
+  if (sweeps_out) *sweeps_out = sweeps;
+  if (!done) {
+    set_error("qb_svd: Jacobi did not converge in %d sweeps", max_sweeps);
+    return -2;
+  }
+  return sweeps;
+}
+
+}  // namespace jac2
+
+// quimb's absorb codes -> powers of s on the two factors and which to form
+struct AbsorbPlan { double lpow, rpow; bool want_l, want_r, want_s; };
+static bool absorb_plan(int absorb, AbsorbPlan &a) {
+  switch (absorb) {
+    case QB_ABSORB_FULL:    a = {0.0, 0.0, true, true, true}; return true;
+    case QB_ABSORB_S:       a = {0.0, 0.0, false, false, true}; return true;
+    case QB_ABSORB_LEFT:    a = {1.0, 0.0, true, true, false}; return true;
+    case QB_ABSORB_LFACTOR: a = {1.0, 0.0, true, false, false}; return true;
+    case QB_ABSORB_RORTHOG: a = {0.0, 0.0, false, true, false}; return true;
+    case QB_ABSORB_BOTH:    a = {0.5, 0.5, true, true, false}; return true;
+    case QB_ABSORB_LSQRT:   a = {0.5, 0.0, true, false, false}; return true;
+    case QB_ABSORB_RSQRT:   a = {0.0, 0.5, false, true, false}; return true;
+    case QB_ABSORB_RIGHT:   a = {0.0, 1.0, true, true, false}; return true;
+    case QB_ABSORB_LORTHOG: a = {0.0, 0.0, true, false, false}; return true;
+    case QB_ABSORB_RFACTOR: a = {0.0, 1.0, false, true, false}; return true;
+  }
+  return false;
+}
+
+// SVD of row-major X (m x n), m >= n, with the truncation / absorb epilogue.
+// U: m x nk (ld nk), S: nk, VH: nk x n, written compactly for the kept rank.
+static int svd_trunc_tall(int64_t m, int64_t n, const double *X, double cutoff,
+                          int cutoff_mode, int64_t max_bond, int absorb, int renorm,
+                          double *U, double *S, double *VH, int64_t *n_keep_out,
+                          double *err_out, int64_t *n_null_out, double *ws,
+                          int *sweeps_out, cudaStream_t st) {
+  using namespace jac2;
+  Geom g;
+  if (!geometry(m, n, g)) {
+    set_error("qb_svd: unsupported shape %lld x %lld", (long long)m, (long long)n);
+    return -2;
+  }
+  AbsorbPlan ap;
+  if (!absorb_plan(absorb, ap)) {
+    set_error("qb_svd_trunc: invalid absorb code %d", absorb);
+    return -8;
+  }
+  double *Q1 = ws + g.q1_off, *R = ws + g.r_off, *W = ws + g.w_off;
+  double *Z = ws + g.v_off, *sv = ws + g.s_off, *UR = ws + g.ur_off;
+  int *perm = reinterpret_cast<int *>(ws + g.perm_off);
+  int *flag = reinterpret_cast<int *>(ws + g.flag_off);
+  int2 *d_pairs = reinterpret_cast<int2 *>(ws + g.pairs_off);
+  double *d_scale = ws + g.scale_off;
+  const int blocks = sm_count() * 4;
+  const bool need_u = ap.want_l && U;
+  int rc = qr_f64(m, n, X, need_u ? Q1 : nullptr, R, /*stabilized=*/0, ws + g.qr_off, st);
+  if (rc) return rc;
+  const int64_t npad = g.npad;
+  pad_copy_kernel<<<blocks, 256, 0, st>>>(R, n, n, n, W, npad, n, 2);  // W = R^T
+  QB_LAUNCH_CHECK();
+  pad_copy_kernel<<<blocks, 256, 0, st>>>(nullptr, 0, 0, 0, Z, npad, npad, 1);
+  QB_LAUNCH_CHECK();
+  int sw = jacobi_iterate(W, Z, n, npad, d_pairs, flag, sweeps_out, st);
+  if (sw < 0) return -sw;
+  colnorm_kernel<<<(unsigned)(npad / 32), 256, 0, st>>>(W, npad, (int)n, (int)npad, sv);
+  QB_LAUNCH_CHECK();
+  std::vector<double> hs(npad);
+  QB_CUDA_CHECK(cudaMemcpyAsync(hs.data(), sv, sizeof(double) * npad,
+                                cudaMemcpyDeviceToHost, st));
+  QB_CUDA_CHECK(cudaStreamSynchronize(st));
+  std::vector<int> hp(npad);
+  for (int i = 0; i < npad; ++i) hp[i] = i;
+  std::stable_sort(hp.begin(), hp.end(), [&](int a, int b) {
+    const bool pa = a >= n, pb = b >= n;  // padding columns last
+    if (pa != pb) return pb;
+    return hs[a] > hs[b];
+  });
+  std::vector<double> ss(n);
+  for (int i = 0; i < n; ++i) ss[i] = hs[hp[i]];
+  // ---- the reference's keep rule / renormalisation on the sorted values ----
+  int64_t nk = n;
+  double f = 1.0, err = 0.0;
+  if (cutoff_mode != 0) {
+    rc = qb_svals_to_keep(ss.data(), n, cutoff, cutoff_mode, max_bond, renorm, &nk, &f, &err);
+    if (rc) return rc;
+  }
+  int64_t n_null = 0;
+  for (int64_t i = 0; i < nk; ++i) n_null += !(ss[i] > 0.0);
+  if (n_keep_out) *n_keep_out = nk;
+  if (err_out) *err_out = err;
+  if (n_null_out) *n_null_out = n_null;
+  // scales of the kept columns / rows: (f s)^lpow, (f s)^rpow
+  std::vector<double> sc(2 * nk), sk(nk);
+  for (int64_t i = 0; i < nk; ++i) {
+    const double v = ss[i] * f;
+    sk[i] = v;
+    sc[i] = ap.lpow == 0.0 ? 1.0 : (ap.lpow == 1.0 ? v : sqrt(v));
+    sc[nk + i] = ap.rpow == 0.0 ? 1.0 : (ap.rpow == 1.0 ? v : sqrt(v));
+  }
+  QB_CUDA_CHECK(cudaMemcpyAsync(perm, hp.data(), sizeof(int) * nk, cudaMemcpyHostToDevice, st));
+  QB_CUDA_CHECK(cudaMemcpyAsync(d_scale, sc.data(), sizeof(double) * 2 * nk,
+                                cudaMemcpyHostToDevice, st));
+  if (S && ap.want_s)
+    QB_CUDA_CHECK(cudaMemcpyAsync(S, sk.data(), sizeof(double) * nk, cudaMemcpyHostToDevice, st));
+  const bool need_v = ap.want_r && VH;
+  if (need_u || need_v) {
+    gather_scaled_kernel<<<blocks, 256, 0, st>>>(W, Z, npad, (int)n, (int)nk, perm, sv,
+                                                 d_scale, d_scale + nk,
+                                                 need_u ? UR : nullptr, need_v ? VH : nullptr);
+    QB_LAUNCH_CHECK();
+  }
+  QB_CUDA_CHECK(cudaStreamSynchronize(st));  // host vectors go out of scope
+  if (need_u) {
+    // U (m x nk) = Q1 (m x n) . UR (n x nk)
+    rc = gemm_f64(Q1, n, 1, UR, nk, 1, U, nk, 1, m, nk, n, 1.0, 0.0, st);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+}  // namespace qb
+
+using namespace qb;
+
+extern "C" {
+
+int64_t qb_svd_workspace(int dtype, int64_t m, int64_t n) {
+  if (dtype != QB_F64) return -1;
+  jac2::Geom g;
+  const int64_t mm = std::max(m, n), nn = std::min(m, n);
+  if (!jac2::geometry(mm, nn, g)) return -2;
+  const int64_t v1 = svd_v1_workspace_doubles(mm, nn);
+  return std::max(g.total, v1) * 8;
+}
+
+static int svd_check(const char *who, int dtype, int64_t m, int64_t n, void *workspace,
+                     size_t workspace_bytes) {
+  if (dtype != QB_F64) {
+    set_error("%s: only f64 is implemented (got dtype %d)", who, dtype);
+    return -1;
+  }
+  if (m < n) {
+    set_error("%s: m < n -- pass the transpose (m >= n required)", who);
+    return -2;
+  }
+  const int64_t need = qb_svd_workspace(dtype, m, n);
+  if (need < 0) {
+    set_error("%s: unsupported shape %lld x %lld", who, (long long)m, (long long)n);
+    return -2;
+  }
+  if (!workspace || (int64_t)workspace_bytes < need) {
+    set_error("%s: workspace too small (need %lld bytes)", who, (long long)need);
+    return -8;
+  }
+  return 0;
+}
+
+int qb_svd(int dtype, int64_t m, int64_t n, const void *X, void *U, void *S,
+           void *VH, void *workspace, size_t workspace_bytes, int *sweeps_out,
+           void *stream) {
+  if (m <= 0 || n <= 0) return 0;
+  int rc = svd_check("qb_svd", dtype, m, n, workspace, workspace_bytes);
+  if (rc) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  double *ws = static_cast<double *>(workspace);
+  static const bool v1 = [] {
+    const char *e = getenv("QB_JAC_MODE");
+    return e && !strcmp(e, "v1");
+  }();
+  if (v1)
+    return svd_tall_f64_v1(m, n, (const double *)X, (double *)U, (double *)S,
+                           (double *)VH, ws, sweeps_out, st);
+  return svd_trunc_tall(m, n, (const double *)X, -1.0, 0, -1, QB_ABSORB_FULL, 0,
+                        (double *)U, (double *)S, (double *)VH, nullptr, nullptr, nullptr,
+                        ws, sweeps_out, st);
+}
+
+int qb_svd_trunc(int dtype, int64_t m, int64_t n, const void *X, double cutoff,
+                 int cutoff_mode, int64_t max_bond, int absorb, int renorm, void *U,
+                 void *S, void *VH, int64_t *n_keep, double *trunc_error,
+                 int64_t *n_null, void *workspace, size_t workspace_bytes,
+                 int *sweeps_out, void *stream) {
+  if (m <= 0 || n <= 0) {
+    if (n_keep) *n_keep = 0;
+    return 0;
+  }
+  int rc = svd_check("qb_svd_trunc", dtype, m, n, workspace, workspace_bytes);
+  if (rc) return rc;
+  if (cutoff_mode < 1 || cutoff_mode > 6) {
+    set_error("qb_svd_trunc: invalid cutoff_mode %d", cutoff_mode);
+    return -6;
+  }
+  return svd_trunc_tall(m, n, (const double *)X, cutoff, cutoff_mode, max_bond, absorb,
+                        renorm, (double *)U, (double *)S, (double *)VH, n_keep,
+                        trunc_error, n_null, static_cast<double *>(workspace), sweeps_out,
+                        static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

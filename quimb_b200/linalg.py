@@ -261,7 +261,7 @@ def _select_complex_pairs(s_host, gram_fn):
 
 
 def _complete_isometry(Q, missing, rows=False):
-    """Fill the columns ``missing`` of the complex (m, k) matrix ``Q`` (rows of
+    """Fill the columns ``missing`` of the (m, k) matrix ``Q`` (rows of
     a (k, n) matrix when ``rows``) with vectors orthonormal to each other and to
     the remaining columns: random directions, two projection passes (launches of
     the contraction kernel) and the device QR.  Used for the null vectors of
@@ -276,8 +276,11 @@ def _complete_isometry(Q, missing, rows=False):
     keep = [c for c in range(k) if c not in set(missing)]
     gen = torch.Generator(device=Q.device)
     gen.manual_seed(0x5eed + m * 131 + len(missing))
-    G = torch.view_as_complex(torch.randn((m, len(missing), 2), dtype=torch.float64,
-                                          device=Q.device, generator=gen))
+    if Q.dtype.is_complex:
+        G = torch.view_as_complex(torch.randn((m, len(missing), 2), dtype=torch.float64,
+                                              device=Q.device, generator=gen))
+    else:
+        G = torch.randn((m, len(missing)), dtype=Q.dtype, device=Q.device, generator=gen)
     if keep:
         Qk = Array(Q.index_select(1, torch.as_tensor(keep, dtype=torch.int64,
                                                      device=Q.device)).contiguous())
@@ -326,6 +329,81 @@ def svd(x, full_matrices=False, return_sweeps=False):
     _lib.check(rc, "qb_svd")
     out = (Array(U), Array(S), Array(VH))
     return out + (sweeps.value,) if return_sweeps else out
+
+
+_MIRROR_ABSORB = {100: 100, 2: 2, -1: 1, 1: -1, -10: 11, 11: -10, -11: 10, 10: -11,
+                  -12: 12, 12: -12, 0: 0}
+# absorb codes whose right (resp. left) factor is returned as an isometry
+_ISO_RIGHT = (100, -1, -11)
+_ISO_LEFT = (100, 1, 10)
+
+
+def svd_trunc(x, cutoff=-1.0, cutoff_mode=4, max_bond=-1, absorb=0, renorm=0, info=None):
+    """``svd_truncated`` (decomp.py:829-898) as ONE library call on a float64
+    device matrix: Jacobi SVD, the reference's keep rule / renormalisation and
+    the absorption of the kept singular values run inside ``qb_svd_trunc``
+    (csrc/svd_jacobi.cu), which writes only the kept rank.  ``absorb`` is
+    quimb's integer code (100 = the three parts).  Returns (left, s, right)
+    device Arrays (``None`` for parts the mode does not request); the factors
+    are views of exactly-sized buffers -- no slicing copies."""
+    x = _as_matrix(x)
+    if x.t.dtype != torch.float64:
+        raise TypeError("svd_trunc: float64 only (other dtypes go through svd())")
+    m, n = x.shape
+    code = 100 if absorb is None else int(absorb)
+    if m < n:
+        # X^T = V s U^T: factor the transpose, swap the roles of the factors
+        xt = ops.materialize(Array(x.t.t()))
+        l, s, r = svd_trunc(xt, cutoff, cutoff_mode, max_bond, _MIRROR_ABSORB[code],
+                            renorm, info)
+        left = None if r is None else Array(r.t.t())
+        right = None if l is None else Array(l.t.t())
+        return left, s, right
+    if m > _QR_MAX_ROWS:
+        # blocked QR first (m beyond the register-panel limit), then the core
+        q, rr = qr(x)
+        l, s, r = svd_trunc(rr, cutoff, cutoff_mode, max_bond, code, renorm, info)
+        if l is not None:
+            l = ops.tensordot(q, l, axes=((1,), (0,)))
+        return l, s, r
+    lib = _lib.load()
+    dev = x.t.device
+    need = lib.qb_svd_workspace(_lib.QB_F64, m, n)
+    if need < 0:
+        raise ValueError(f"quimb_b200.linalg.svd_trunc: unsupported shape {x.shape}")
+    ws = _workspace(need, dev)
+    want_l = code in (100, -1, -10, 0, -12, 1, 10)
+    want_r = code in (100, -1, -11, 0, 12, 1, 11)
+    want_s = code in (100, 2)
+    U = torch.empty((m * n,), dtype=torch.float64, device=dev) if want_l else None
+    VH = torch.empty((n * n,), dtype=torch.float64, device=dev) if want_r else None
+    S = torch.empty((n,), dtype=torch.float64, device=dev) if want_s else None
+    nk, err, nnull = ctypes.c_int64(0), ctypes.c_double(0.0), ctypes.c_int64(0)
+    sweeps = ctypes.c_int(0)
+    rc = lib.qb_svd_trunc(_lib.QB_F64, m, n, x.t.data_ptr(), float(cutoff), int(cutoff_mode),
+                          int(max_bond), code, int(renorm),
+                          U.data_ptr() if want_l else None,
+                          S.data_ptr() if want_s else None,
+                          VH.data_ptr() if want_r else None,
+                          ctypes.byref(nk), ctypes.byref(err), ctypes.byref(nnull),
+                          ws.data_ptr(), ws.numel(), ctypes.byref(sweeps), _lib.stream_ptr())
+    _lib.check(rc, "qb_svd_trunc")
+    k = int(nk.value)
+    if info is not None:
+        if "error" in info:
+            info["error"] = float(err.value)
+        info["n_keep"] = k
+        info["sweeps"] = int(sweeps.value)
+    left = U[:m * k].view(m, k) if want_l else None
+    right = VH[:k * n].view(k, n) if want_r else None
+    if nnull.value and right is not None and code in _ISO_RIGHT:
+        # exactly-zero singular values among the kept ones: their rows of VH
+        # came back null; complete the right factor to an isometry (the
+        # reference's LAPACK V always is one)
+        miss = list(range(k - int(nnull.value), k))
+        _complete_isometry(right, miss, rows=True)
+    return (None if left is None else Array(left), None if S is None else Array(S[:k]),
+            None if right is None else Array(right))
 
 
 def _svd_complex(x, return_sweeps):

@@ -229,6 +229,12 @@ def svd_truncated(x, cutoff=-1.0, cutoff_mode=4, max_bond=-1,
     (decomp.py:829-898)."""
     absorb = _ABSORB_MAP[absorb]
     cutoff_mode = _CUTOFF_MODE_MAP[cutoff_mode]
+    xa = ops.asarray(x)
+    if xa.t.dtype == torch.float64 and xa.ndim == 2 and min(xa.shape) > 0:
+        # one library call: Jacobi SVD + keep rule + renorm + absorb, writing
+        # only the kept rank (csrc/svd_jacobi.cu:qb_svd_trunc)
+        return linalg.svd_trunc(xa, cutoff, cutoff_mode, -1 if max_bond is None else max_bond,
+                                absorb, renorm, info=info)
     U, s, VH = linalg.svd(x)
     return _trim_renorm_absorb(U.t, s.t, VH.t, cutoff, cutoff_mode, max_bond,
                                absorb, renorm, info=info)

@@ -354,6 +354,61 @@ class EmulatedLib:
                 tgt.value = 1
         return 0
 
+    def qb_svd_trunc(self, dtype, m, n, X, cutoff, cutoff_mode, max_bond, absorb, renorm,
+                     U, S, VH, n_keep, trunc_error, n_null, ws, ws_bytes, sweeps_out, stream):
+        """Same contract as csrc/svd_jacobi.cu:qb_svd_trunc, incl. what the
+        Jacobi kernel does for exactly-zero singular values (null rows of VH)."""
+        if dtype != _lib.QB_F64:
+            return self._fail(-1, "qb_svd_trunc: only f64 is implemented")
+        if m < n:
+            return self._fail(-2, "qb_svd_trunc: m < n -- pass the transpose")
+        need = self._real.qb_svd_workspace(dtype, m, n)
+        if need < 0:
+            return self._fail(-2, f"qb_svd_trunc: unsupported shape {m} x {n}")
+        if not _addr(ws) or ws_bytes < need:
+            return self._fail(-8, "qb_svd_trunc: workspace too small")
+        plan = {100: (0, 0, 1, 1, 1), 2: (0, 0, 0, 0, 1), -1: (1, 0, 1, 1, 0),
+                -10: (1, 0, 1, 0, 0), -11: (0, 0, 0, 1, 0), 0: (.5, .5, 1, 1, 0),
+                -12: (.5, 0, 1, 0, 0), 12: (0, .5, 0, 1, 0), 1: (0, 1, 1, 1, 0),
+                10: (0, 0, 1, 0, 0), 11: (0, 1, 0, 1, 0)}.get(absorb)
+        if plan is None:
+            return self._fail(-8, f"qb_svd_trunc: invalid absorb code {absorb}")
+        lpow, rpow, want_l, want_r, want_s = plan
+        self._tick("qb_svd_trunc")
+        x = _flat(X, m * n, np.float64).reshape(m, n)
+        u, s, vh = np.linalg.svd(x, full_matrices=False)
+        s = np.where(s > 1e-300 * max(s[0], 1e-300), s, 0.0) if s.size else s
+        nk = ctypes.c_int64(0)
+        f = ctypes.c_double(1.0)
+        err = ctypes.c_double(0.0)
+        sc = np.ascontiguousarray(s, dtype=np.float64)
+        rc = self._real.qb_svals_to_keep(
+            sc.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), sc.size, float(cutoff),
+            int(cutoff_mode), int(max_bond), int(renorm), ctypes.byref(nk), ctypes.byref(f),
+            ctypes.byref(err))
+        if rc:
+            return rc
+        k = int(nk.value)
+        sk = s[:k] * f.value
+        for ref, val in ((n_keep, k), (trunc_error, err.value),
+                         (n_null, int(np.sum(~(s[:k] > 0.0))))):
+            tgt = getattr(ref, "_obj", None)
+            if tgt is not None:
+                tgt.value = val
+        vk = vh[:k].copy()
+        vk[~(s[:k] > 0.0)] = 0.0             # the kernel: W[:, c] / s with s == 0 -> 0
+        if want_l and _addr(U):
+            _flat(U, m * k, np.float64).reshape(m, k)[...] = u[:, :k] * (sk ** lpow if lpow else 1.0)
+        if want_r and _addr(VH):
+            scale = (sk ** rpow)[:, None] if rpow else 1.0
+            _flat(VH, k * n, np.float64).reshape(k, n)[...] = vk * scale
+        if want_s and _addr(S):
+            _flat(S, k, np.float64)[...] = sk
+        tgt = getattr(sweeps_out, "_obj", None)
+        if tgt is not None:
+            tgt.value = 1
+        return 0
+
 
 class _FakeStream:
     cuda_stream = 0

@@ -14,6 +14,8 @@ timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > $out/${tag}_
 timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29611 \
     tools/p2p_check.py --one-gpu > $out/${tag}_p2p_onegpu.log 2>&1
 tail -3 $out/${tag}_p2p_onegpu.log
+bash tools/svd_tune.sh gpurun_out/${tag}_svd_tune.log > /dev/null 2>&1
+grep -h '"ms"' gpurun_out/${tag}_svd_tune.log | cut -c1-300
 timeout 400 python tools/lanczos_compare.py 100 1024 12,15 > $out/${tag}_lanczos_compare.log 2>&1
 tail -3 $out/${tag}_lanczos_compare.log
 timeout 400 python tools/bench_boundary.py --Lx 10 --Ly 10 --D 8 --chi 256 > $out/${tag}_boundary.json 2> $out/${tag}_boundary.err
