@@ -70,8 +70,9 @@ def contract_pair(a, la, b, lb, lc, conj_a=False, conj_b=False, out=None,
         raise TypeError(f"dtype mismatch: {a.dtype} vs {b.dtype}")
     if len(la) != a.dim() or len(lb) != b.dim():
         raise ValueError("label count does not match operand rank")
-    if a.dtype in _WIDE:
-        # single precision: widen exactly, contract in fp64, round once
+    if a.dtype in _WIDE and not _native_single(a, la, b, lb, lc, out, engine):
+        # single precision below the tcgen05 engine's tile minimum (or with
+        # batch modes): widen exactly, contract in fp64, round once
         wide = _WIDE[a.dtype]
         wout = None if out is None else convert(out, wide)
         res = contract_pair(convert(a, wide), la, convert(b, wide), lb, lc, conj_a,
@@ -124,6 +125,36 @@ def contract_pair(a, la, b, lb, lc, conj_a=False, conj_b=False, out=None,
                                      _lib.stream_ptr())
     _lib.check(rc, "qb_contract_pair")
     return out
+
+
+_NO_NATIVE_SINGLE = -101
+
+
+def _native_single(a, la, b, lb, lc, out, engine):
+    """True when the library takes this float32 / complex64 contraction on its
+    native engine (tcgen05, 4 int8 slices, float epilogue -- csrc/ozaki_tc.cu);
+    decided by the library's own planner, so the rule lives in one place."""
+    ext = {}
+    for t, ls in ((a, la), (b, lb)):
+        if len(ls) != t.dim():
+            return False
+        for l, s in zip(ls, t.shape):
+            if ext.setdefault(l, s) != s:
+                return False
+    if any(l not in ext for l in lc):
+        return False
+    if out is None:
+        shape = [ext[l] for l in lc]
+        st, acc = [], 1
+        for e in reversed(shape):
+            st.append(acc)
+            acc *= max(e, 1)
+        dc = _lib.np_desc(shape, list(reversed(st)), _lib.qb_dtype(a.dtype))
+    else:
+        dc = _lib.desc(out)
+    need = _lib.load().qb_contract_pair_workspace(_lib.desc(a), _lib.labels(la), _lib.desc(b),
+                                                  _lib.labels(lb), dc, _lib.labels(lc), engine)
+    return need != _NO_NATIVE_SINGLE and need >= 0
 
 
 _CHUNK = 5

@@ -69,11 +69,19 @@ int gemm_f64(const double *A, int64_t a_rs, int64_t a_cs, const double *B,
   return launch_contract_f64(plan, st);
 }
 
-static int check_device_dtype(int dt) {
-  if (dt != QB_F64 && dt != QB_C128) {
-    set_error("dtype %d is not supported by the contraction engine yet "
-              "(supported: f64, c128)", dt);
-    return -1;
+static bool is_single(int dt) { return dt == QB_F32 || dt == QB_C64; }
+
+// f64 / c128: every engine.  f32 / c64: the tcgen05 engine only (4 int8
+// slices, float epilogue); shapes below its tile minimum are refused with
+// QB_NO_NATIVE_SINGLE and the host layer widens them instead.
+constexpr int QB_NO_NATIVE_SINGLE = -101;
+static int check_device_dtype(const PairPlan &plan) {
+  if (is_single(plan.dtype) && !(plan.empty_out || plan.zero_fill) && !ozaki_eligible(plan)) {
+    set_error("single-precision contraction M=%lld N=%lld K=%lld batch=%lld is below the "
+              "tcgen05 engine's minimum (M >= 128, N >= 64, K >= 128 real units, no "
+              "batch modes): widen it", (long long)plan.p.M, (long long)plan.p.N,
+              (long long)plan.p.K, (long long)plan.p.nbatch);
+    return QB_NO_NATIVE_SINGLE;
   }
   return 0;
 }
@@ -95,6 +103,7 @@ static int env_engine() {
   return v;
 }
 static bool want_ozaki(int engine, const PairPlan &plan) {
+  if (is_single(plan.dtype)) return ozaki_eligible(plan);   // the only native engine
   if (engine == QB_ENGINE_AUTO) engine = env_engine();
   return engine == QB_ENGINE_OZAKI && ozaki_eligible(plan);
 }
@@ -134,6 +143,7 @@ int64_t qb_contract_pair_workspace(const qb_tensor_t *A, const int32_t *la,
   PairPlan plan;
   int rc = plan_pair(A, la, B, lb, C, lc, 0, 0, plan);
   if (rc) return rc;
+  if ((rc = check_device_dtype(plan))) return rc;
   int64_t need = plan_workspace_bytes(plan);
   if (want_ozaki(engine & 0xff, plan))
     need = std::max(need, ozaki_workspace_bytes(plan) + kWsHeaderBytes);
@@ -192,7 +202,7 @@ static int contract_pair_impl(const qb_tensor_t *A, const int32_t *la,
   engine &= 0xff;
   int rc = plan_pair(A, la, B, lb, C, lc, conjA, conjB, plan, force_cfg);
   if (rc) return rc;
-  if ((rc = check_device_dtype(plan.dtype))) return rc;
+  if ((rc = check_device_dtype(plan))) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (plan.empty_out) return 0;
   if (plan.zero_fill) {
@@ -258,7 +268,10 @@ int qb_contract_batched(const qb_tensor_t *A0, const int32_t *la,
   PairPlan plan;
   int rc = plan_pair(A0, la, B0, lb, C0, lc, conjA, conjB, plan);
   if (rc) return rc;
-  if ((rc = check_device_dtype(plan.dtype))) return rc;
+  if (is_single(plan.dtype)) {
+    set_error("qb_contract_batched: single precision has no batched engine: widen");
+    return QB_NO_NATIVE_SINGLE;
+  }
   if (plan.p.b.n) {
     set_error("qb_contract_batched: batch labels are not allowed inside the "
               "per-item signature");

@@ -32,6 +32,19 @@
 //                in fp64 with exact power-of-two weights, apply the row /
 //                column scales and alpha/beta, scatter to the strided C
 //                (output permutation folded into the store).
+//
+// Round 2: the same engine serves all four dtypes natively.
+//   * float32 / complex64 (BASELINE configs[4]: PEPS boundary contraction):
+//     S = 4 slices (6 + 7*3 = 27 bits below the row maximum, finer than the
+//     24-bit significand), 10 slice products, 128 x 128 output tiles (4
+//     accumulators x 128 TMEM columns); the split kernel reads the strided
+//     single-precision operand directly and the epilogue rounds once to
+//     float -- no widening passes through HBM.
+//   * complex64 / complex128: the real GEMM of the embedding
+//       A_e[m, 2k+c] = (re, im)(A[m,k]),   B_e[2k+c, 2n+d] = [[re, im], [-im, re]]
+//     (C_e[m, 2n+d] is the interleaved storage of complex C); the embedding is
+//     produced inside the split kernel's gather (conjugation = a sign there),
+//     so complex operands cost no extra pass either.
 #include <cuda.h>
 #include <math.h>
 
@@ -42,12 +55,11 @@
 namespace qb {
 
 constexpr int OZ_BM = 128;     // tile rows (TMEM lanes)
-constexpr int OZ_BN = 64;      // tile columns per accumulator
 constexpr int OZ_BK = 128;     // bytes (= int8 elements) of K per slice tile
-constexpr int OZ_MAXS = 8;     // max slices: S * OZ_BN <= 512 TMEM columns
+constexpr int OZ_MAXS = 8;     // max slices: S * BN <= 512 TMEM columns
 constexpr int OZ_ASLOTS = 4;   // A ring depth
 constexpr int OZ_A_TILE = OZ_BM * OZ_BK;  // 16 KB
-constexpr int OZ_B_TILE = OZ_BN * OZ_BK;  // 8 KB
+// tile columns per accumulator: 64 with 8 slices (double), 128 with 4 (single)
 
 // ------------------------------------------------------------------ PTX ----
 __device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
@@ -123,10 +135,14 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 
 // --------------------------------------------------- operand preparation ----
 struct SplitParams {
-  const double *src;
-  ModeGroup rows;      // s0 = stride of the row (free) modes in src
+  const void *src;
+  int32_t single;      // 1: float / complex64 source, 0: double / complex128
+  int32_t role;        // 0 real; 1 complex, A-role (K doubled); 2 complex, B-role
+                       // (rows and K doubled: [[re, im], [-im, re]])
+  int32_t conj;        // complex operand enters conjugated
+  ModeGroup rows;      // s0 = stride of the row (free) modes in src (elements)
   ModeGroup ks;        // s0 = stride of the contracted modes in src
-  int64_t R, K;        // logical extents
+  int64_t R, K;        // extents of the (embedded) real operand
   int64_t Rpad, Kpad;  // padded extents of the slice planes
   int32_t S;
   int32_t k_contig;    // 1: consecutive k contiguous in memory, 0: rows
@@ -135,6 +151,27 @@ struct SplitParams {
   int8_t *slices;              // [S][Rpad][Kpad]
 };
 
+// element (r_e, k_e) of the real operand the GEMM sees: `off` = element offset
+// of the underlying (possibly complex) entry, d = r_e & 1, c = k_e & 1
+__device__ __forceinline__ double oz_load(const SplitParams &P, int64_t off, int d, int c) {
+  if (P.role == 0)
+    return P.single ? (double)static_cast<const float *>(P.src)[off]
+                    : static_cast<const double *>(P.src)[off];
+  double re, im;
+  if (P.single) {
+    const float2 z = static_cast<const float2 *>(P.src)[off];
+    re = z.x; im = z.y;
+  } else {
+    const double2 z = static_cast<const double2 *>(P.src)[off];
+    re = z.x; im = z.y;
+  }
+  if (P.conj) im = -im;
+  if (P.role == 1) return c ? im : re;
+  // B-role: B_e[2k+c, 2n+d]
+  if (c == d) return re;
+  return c ? -im : im;
+}
+
 __global__ void __launch_bounds__(256)
     ozaki_rowmax_kernel(const __grid_constant__ SplitParams P) {
   __shared__ int64_t roff[64];
@@ -142,14 +179,15 @@ __global__ void __launch_bounds__(256)
   __shared__ double red[8][65];
   const int tid = threadIdx.x;
   const int64_t r0 = (int64_t)blockIdx.x * 64, k0 = (int64_t)blockIdx.y * 256;
+  const int rsh = P.role == 2 ? 1 : 0, ksh = P.role != 0 ? 1 : 0;
   if (tid < 64) {
     int64_t r = r0 + tid, o = -1, d;
-    if (r < P.R) decode2(r, P.rows, o, d);
+    if (r < P.R) decode2(r >> rsh, P.rows, o, d);
     roff[tid] = o;
   }
   {
     int64_t k = k0 + tid, o = -1, d;
-    if (k < P.K) decode2(k, P.ks, o, d);
+    if (k < P.K) decode2(k >> ksh, P.ks, o, d);
     koff[tid] = o;
   }
   __syncthreads();
@@ -163,7 +201,7 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const int64_t ko = koff[tx + 32 * j];
-          if (ko >= 0) m = fmax(m, fabs(P.src[ro + ko]));
+          if (ko >= 0) m = fmax(m, fabs(oz_load(P, ro + ko, (int)((r0 + r) & 1), (tx + 32 * j) & 1)));
         }
       }
 #pragma unroll
@@ -178,8 +216,9 @@ __global__ void __launch_bounds__(256)
     for (int j = 0; j < 32; ++j) {
       const int64_t ko = koff[ty + 8 * j];
       if (ko >= 0) {
-        if (ro0 >= 0) m0 = fmax(m0, fabs(P.src[ro0 + ko]));
-        if (ro1 >= 0) m1 = fmax(m1, fabs(P.src[ro1 + ko]));
+        const int c = (ty + 8 * j) & 1;   // k0 is even
+        if (ro0 >= 0) m0 = fmax(m0, fabs(oz_load(P, ro0 + ko, tx & 1, c)));
+        if (ro1 >= 0) m1 = fmax(m1, fabs(oz_load(P, ro1 + ko, tx & 1, c)));
       }
     }
     red[ty][tx] = m0; red[ty][tx + 32] = m1;
@@ -202,12 +241,13 @@ __global__ void __launch_bounds__(256)
   __shared__ double inv_s[32];
   const int tid = threadIdx.x;
   const int64_t r0 = (int64_t)blockIdx.x * 32, k0 = (int64_t)blockIdx.y * 128;
+  const int rsh = P.role == 2 ? 1 : 0, ksh = P.role != 0 ? 1 : 0;
   if (tid < 32) {
     const int64_t r = r0 + tid;
     int64_t o = -1, d;
     double inv = 0.0;
     if (r < P.R) {
-      decode2(r, P.rows, o, d);
+      decode2(r >> rsh, P.rows, o, d);
       const double mx = __longlong_as_double((long long)P.rowmax[r]);
       int e = 0;
       if (mx > 0.0) e = ilogb(mx) + 1;  // mx * 2^-e in [0.5, 1)
@@ -221,7 +261,7 @@ __global__ void __launch_bounds__(256)
   if (tid < 128) {
     const int64_t k = k0 + tid;
     int64_t o = -1, d;
-    if (k < P.K) decode2(k, P.ks, o, d);
+    if (k < P.K) decode2(k >> ksh, P.ks, o, d);
     koff[tid] = o;
   }
   __syncthreads();
@@ -231,7 +271,7 @@ __global__ void __launch_bounds__(256)
     if (P.k_contig) { k = idx & 127; r = idx >> 7; } else { r = idx & 31; k = idx >> 5; }
     const int64_t ro = roff[r], ko = koff[k];
     double x = 0.0;
-    if (ro >= 0 && ko >= 0) x = P.src[ro + ko] * inv_s[r];
+    if (ro >= 0 && ko >= 0) x = oz_load(P, ro + ko, r & 1, k & 1) * inv_s[r];  // r0, k0 even
     tile[r][(k >> 4) * 17 + (k & 15)] = x;
   }
   __syncthreads();
@@ -260,23 +300,33 @@ struct OzGemmParams {
   ContractParams c;   // for the C scatter (mode groups m, n with s1 = stride in C)
   int32_t S;
   int32_t nkb;        // k-blocks of 128
+  int32_t cplx;       // C is complex (interleaved): column 2n+d of the real GEMM
+  int64_t Me, Ne;     // extents of the real GEMM
   const double *scaleA;   // [Mpad]
   const double *scaleB;   // [Npad]
 };
 
-constexpr size_t OZ_SMEM_TILES = (size_t)OZ_ASLOTS * OZ_A_TILE + 2 * OZ_MAXS * OZ_B_TILE;
-constexpr size_t OZ_SMEM = OZ_SMEM_TILES + 1024 /*align*/ + 4096 /*tables, barriers*/;
+template <int BN>
+struct OzSmem {
+  static constexpr int B_TILE = BN * OZ_BK;               // 8 / 16 KB
+  static constexpr int NS = 512 / BN;                     // slices that fit TMEM
+  static constexpr size_t TILES = (size_t)OZ_ASLOTS * OZ_A_TILE + 2 * (size_t)NS * B_TILE;
+  static constexpr size_t BYTES = TILES + 1024 /*align*/ + 8192 /*tables, barriers*/;
+};
 
+template <int BN, typename OutT>
 __global__ void __launch_bounds__(192, 1)
     ozaki_gemm_kernel(const __grid_constant__ CUtensorMap mapA,
                       const __grid_constant__ CUtensorMap mapB,
                       const __grid_constant__ OzGemmParams P) {
+  constexpr int B_TILE = OzSmem<BN>::B_TILE;
+  constexpr int NS = OzSmem<BN>::NS;
   extern __shared__ unsigned char oz_smem_raw[];
   unsigned char *base = reinterpret_cast<unsigned char *>(
       ((uintptr_t)oz_smem_raw + 1023) & ~(uintptr_t)1023);
   unsigned char *sA = base;                                   // 4 x 16 KB
-  unsigned char *sB = base + (size_t)OZ_ASLOTS * OZ_A_TILE;   // 2 x S x 8 KB
-  unsigned char *aux = base + OZ_SMEM_TILES;
+  unsigned char *sB = base + (size_t)OZ_ASLOTS * OZ_A_TILE;   // 2 x NS x B_TILE
+  unsigned char *aux = base + OzSmem<BN>::TILES;
   uint64_t *fullA = reinterpret_cast<uint64_t *>(aux);        // [4]
   uint64_t *emptyA = fullA + OZ_ASLOTS;                       // [4]
   uint64_t *fullB = emptyA + OZ_ASLOTS;                       // [2]
@@ -284,9 +334,9 @@ __global__ void __launch_bounds__(192, 1)
   uint64_t *tmem_full = emptyB + 2;                           // [1]
   uint32_t *tmem_base_s = reinterpret_cast<uint32_t *>(tmem_full + 1);
   int64_t *offCm = reinterpret_cast<int64_t *>(aux + 256);    // [128]
-  int64_t *offCn = offCm + OZ_BM;                             // [64]
-  double *sclM = reinterpret_cast<double *>(offCn + OZ_BN);   // [128]
-  double *sclN = sclM + OZ_BM;                                // [64]
+  int64_t *offCn = offCm + OZ_BM;                             // [BN]
+  double *sclM = reinterpret_cast<double *>(offCn + BN);      // [128]
+  double *sclN = sclM + OZ_BM;                                // [BN]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int S = P.S, nkb = P.nkb;
@@ -304,22 +354,23 @@ __global__ void __launch_bounds__(192, 1)
                  "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
-  // epilogue tables (warps 2..5 = 128 threads)
+  // epilogue tables (warps 2..5 = 128 threads); offsets in units of OutT
   if (warp >= 2) {
     const int e = tid - 64;
+    const int csh = P.cplx ? 1 : 0;
     {
       const int64_t m = (int64_t)tm * OZ_BM + e;
       int64_t oa, oc = -1;
-      if (m < P.c.M) decode2(m, P.c.m, oa, oc);
+      if (m < P.Me) { decode2(m, P.c.m, oa, oc); oc <<= csh; }
       offCm[e] = oc;
       sclM[e] = P.scaleA[(int64_t)tm * OZ_BM + e];
     }
-    if (e < OZ_BN) {
-      const int64_t n = (int64_t)tn * OZ_BN + e;
+    if (e < BN) {
+      const int64_t ne = (int64_t)tn * BN + e;
       int64_t ob, oc = -1;
-      if (n < P.c.N) decode2(n, P.c.n, ob, oc);
+      if (ne < P.Ne) { decode2(ne >> csh, P.c.n, ob, oc); oc = (oc << csh) + (csh ? (ne & 1) : 0); }
       offCn[e] = oc;
-      sclN[e] = P.scaleB[(int64_t)tn * OZ_BN + e];
+      sclN[e] = P.scaleB[(int64_t)tn * BN + e];
     }
   }
   tc_fence_before();
@@ -334,10 +385,10 @@ __global__ void __launch_bounds__(192, 1)
       for (int kb = 0; kb < nkb; ++kb) {
         const int sb = kb & 1;
         mbar_wait(&emptyB[sb], ((kb >> 1) & 1) ^ 1);
-        mbar_expect_tx(&fullB[sb], (uint32_t)S * OZ_B_TILE);
+        mbar_expect_tx(&fullB[sb], (uint32_t)S * B_TILE);
         for (int q = 0; q < S; ++q)
-          tma_load_3d(sB + ((size_t)sb * OZ_MAXS + q) * OZ_B_TILE, &mapB, &fullB[sb],
-                      kb * OZ_BK, tn * OZ_BN, q);
+          tma_load_3d(sB + ((size_t)sb * NS + q) * B_TILE, &mapB, &fullB[sb],
+                      kb * OZ_BK, tn * BN, q);
         for (int p = 0; p < S; ++p, ++ia) {
           const int sa = ia % OZ_ASLOTS;
           mbar_wait(&emptyA[sa], ((ia / OZ_ASLOTS) & 1) ^ 1);
@@ -353,7 +404,7 @@ __global__ void __launch_bounds__(192, 1)
       // kind::i8: D = S32 (2<<4), A = INT8 (1<<7), B = INT8 (1<<10), K-major
       // both, N>>3 at [17,23), M>>4 at [24,29)
       const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) |
-                             ((uint32_t)(OZ_BN >> 3) << 17) | ((uint32_t)(OZ_BM >> 4) << 24);
+                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(OZ_BM >> 4) << 24);
       int ia = 0;
       for (int kb = 0; kb < nkb; ++kb) {
         const int sb = kb & 1;
@@ -366,8 +417,8 @@ __global__ void __launch_bounds__(192, 1)
           const uint64_t adesc = umma_desc_sw128(smem_u32(sA + (size_t)sa * OZ_A_TILE));
           for (int q = 0; q + p < S; ++q) {
             const uint64_t bdesc =
-                umma_desc_sw128(smem_u32(sB + ((size_t)sb * OZ_MAXS + q) * OZ_B_TILE));
-            const uint32_t dcol = tmem_base + (uint32_t)(p + q) * OZ_BN;
+                umma_desc_sw128(smem_u32(sB + ((size_t)sb * NS + q) * B_TILE));
+            const uint32_t dcol = tmem_base + (uint32_t)(p + q) * BN;
 #pragma unroll
             for (int k4 = 0; k4 < OZ_BK / 32; ++k4) {
               // first touch of accumulator d = p+q is (kb=0, p=0, k4=0)
@@ -390,16 +441,16 @@ __global__ void __launch_bounds__(192, 1)
     tc_fence_after();
     const int64_t om = offCm[row];
     const double sm = sclM[row] * P.c.alpha;
-    double *C = static_cast<double *>(P.c.C);
+    OutT *C = static_cast<OutT *>(P.c.C);
     const double beta = P.c.beta;
-    for (int cc = 0; cc < OZ_BN; cc += 16) {
+    for (int cc = 0; cc < BN; cc += 16) {
       double acc[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) acc[i] = 0.0;
       double w = ldexp(1.0, -7 * (S - 1));
       for (int d = S - 1; d >= 0; --d) {
         int32_t v[16];
-        tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(d * OZ_BN + cc), v);
+        tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(d * BN + cc), v);
 #pragma unroll
         for (int i = 0; i < 16; ++i) acc[i] += w * (double)v[i];
         w *= 128.0;
@@ -410,8 +461,8 @@ __global__ void __launch_bounds__(192, 1)
           const int64_t on = offCn[cc + i];
           if (on >= 0) {
             double val = acc[i] * sm * sclN[cc + i];
-            if (beta != 0.0) val += beta * C[om + on];
-            C[om + on] = val;
+            if (beta != 0.0) val += beta * (double)C[om + on];
+            C[om + on] = (OutT)val;
           }
         }
       }
@@ -468,26 +519,39 @@ static int make_slice_map(CUtensorMap *map, const int8_t *ptr, int64_t Kpad, int
 }
 
 struct OzGeom {
-  int S;
+  int S, BN, cplx, single;
+  int64_t Me, Ne, Ke;            // extents of the real GEMM
   int64_t Mpad, Npad, Kpad;
   int64_t off_rmA, off_rmB, off_scA, off_scB, off_slA, off_slB, total;  // bytes
 };
 
-static int oz_slices() {
-  static int s = [] {
+static int oz_slices(bool single) {
+  static int s8 = [] {
     const char *e = getenv("QB_OZAKI_SLICES");
     int v = e ? atoi(e) : 8;
     return std::max(2, std::min(v, OZ_MAXS));
   }();
-  return s;
+  static int s4 = [] {
+    const char *e = getenv("QB_OZAKI_SLICES_SINGLE");
+    int v = e ? atoi(e) : 4;
+    return std::max(2, std::min(v, 4));
+  }();
+  return single ? s4 : s8;
 }
 
-static void oz_geometry(const ContractParams &p, OzGeom &g) {
+static void oz_geometry(const PairPlan &plan, OzGeom &g) {
+  const ContractParams &p = plan.p;
   auto up = [](int64_t x, int64_t a) { return (x + a - 1) / a * a; };
-  g.S = oz_slices();
-  g.Mpad = up(p.M, OZ_BM);
-  g.Npad = up(p.N, OZ_BM);  // multiple of 128 so the split kernel tiles evenly
-  g.Kpad = up(p.K, OZ_BK);
+  g.single = (plan.dtype == QB_F32 || plan.dtype == QB_C64) ? 1 : 0;
+  g.cplx = dtype_is_complex(plan.dtype) ? 1 : 0;
+  g.S = oz_slices(g.single);
+  g.BN = g.single ? 128 : 64;
+  g.Me = p.M;
+  g.Ne = g.cplx ? 2 * p.N : p.N;
+  g.Ke = g.cplx ? 2 * p.K : p.K;
+  g.Mpad = up(g.Me, OZ_BM);
+  g.Npad = up(g.Ne, OZ_BM);  // multiple of 128 so the split kernel tiles evenly
+  g.Kpad = up(g.Ke, OZ_BK);
   int64_t off = 0;
   g.off_rmA = off; off += up(g.Mpad * 8, 1024);
   g.off_rmB = off; off += up(g.Npad * 8, 1024);
@@ -500,48 +564,67 @@ static void oz_geometry(const ContractParams &p, OzGeom &g) {
 
 bool ozaki_eligible(const PairPlan &plan) {
   const ContractParams &p = plan.p;
-  return plan.dtype == QB_F64 && p.nbatch == 1 && !p.dA && p.M >= 128 && p.N >= 64 &&
-         p.K >= 128 && p.K < 65536 && !plan.empty_out && !plan.zero_fill;
+  const int64_t f = dtype_is_complex(plan.dtype) ? 2 : 1;
+  return p.nbatch == 1 && !p.dA && p.M >= 128 && f * p.N >= 64 && f * p.K >= 128 &&
+         f * p.K < 65536 && !plan.empty_out && !plan.zero_fill;
 }
 
 int64_t ozaki_workspace_bytes(const PairPlan &plan) {
   OzGeom g;
-  oz_geometry(plan.p, g);
+  oz_geometry(plan, g);
   return g.total;
+}
+
+template <int BN, typename OutT>
+static int oz_launch_gemm(const CUtensorMap &mapA, const CUtensorMap &mapB,
+                          const OzGemmParams &gp, dim3 grid, cudaStream_t st) {
+  auto kern = ozaki_gemm_kernel<BN, OutT>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    QB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)OzSmem<BN>::BYTES));
+    attr_set = true;
+  }
+  kern<<<grid, 192, OzSmem<BN>::BYTES, st>>>(mapA, mapB, gp);
+  QB_LAUNCH_CHECK();
+  return 0;
 }
 
 int launch_contract_ozaki(const PairPlan &plan, void *workspace, cudaStream_t st) {
   const ContractParams &p = plan.p;
   OzGeom g;
-  oz_geometry(p, g);
+  oz_geometry(plan, g);
   unsigned char *ws = static_cast<unsigned char *>(workspace);
   if (((uintptr_t)ws & 255) != 0) {
     set_error("ozaki workspace must be 256-byte aligned");
     return -10;
   }
   QB_CUDA_CHECK(cudaMemsetAsync(ws, 0, g.off_scA, st));  // row/col maxima = 0
-  auto prep = [&](const double *src, const ModeGroup &rows, bool rows_second,
+  auto prep = [&](const void *src, int role, int conj, const ModeGroup &rows,
                   const ModeGroup &ks, bool k_second, int64_t R, int64_t Rpad,
                   int64_t off_rm, int64_t off_sc, int64_t off_sl) -> int {
     SplitParams sp;
     memset(&sp, 0, sizeof(sp));
     sp.src = src;
+    sp.single = g.single;
+    sp.role = role;
+    sp.conj = conj;
     sp.rows.n = rows.n; sp.ks.n = ks.n;
     for (int i = 0; i < rows.n; ++i) {
       sp.rows.ext[i] = rows.ext[i];
-      sp.rows.s0[i] = rows_second ? rows.s1[i] : rows.s0[i];
+      sp.rows.s0[i] = rows.s0[i];
     }
     for (int i = 0; i < ks.n; ++i) {
       sp.ks.ext[i] = ks.ext[i];
       sp.ks.s0[i] = k_second ? ks.s1[i] : ks.s0[i];
     }
-    sp.R = R; sp.K = p.K; sp.Rpad = Rpad; sp.Kpad = g.Kpad; sp.S = g.S;
+    sp.R = R; sp.K = g.Ke; sp.Rpad = Rpad; sp.Kpad = g.Kpad; sp.S = g.S;
     const int64_t ksm = ks.n ? sp.ks.s0[0] : 1, rsm = rows.n ? sp.rows.s0[0] : (int64_t)1 << 60;
     sp.k_contig = (ksm <= rsm) ? 1 : 0;
     sp.rowmax = reinterpret_cast<unsigned long long *>(ws + off_rm);
     sp.scale = reinterpret_cast<double *>(ws + off_sc);
     sp.slices = reinterpret_cast<int8_t *>(ws + off_sl);
-    dim3 g1((unsigned)((R + 63) / 64), (unsigned)((p.K + 255) / 256));
+    dim3 g1((unsigned)((R + 63) / 64), (unsigned)((g.Ke + 255) / 256));
     ozaki_rowmax_kernel<<<g1, 256, 0, st>>>(sp);
     QB_LAUNCH_CHECK();
     dim3 g2((unsigned)(Rpad / 32), (unsigned)(g.Kpad / 128));
@@ -551,11 +634,11 @@ int launch_contract_ozaki(const PairPlan &plan, void *workspace, cudaStream_t st
   };
   int rc;
   // A: rows = m modes (stride in A = s0), k modes (stride in A = s0)
-  if ((rc = prep(static_cast<const double *>(p.A), p.m, false, p.k, false, p.M, g.Mpad,
+  if ((rc = prep(p.A, g.cplx ? 1 : 0, p.conjA, p.m, p.k, false, g.Me, g.Mpad,
                  g.off_rmA, g.off_scA, g.off_slA)))
     return rc;
   // B: rows = n modes (stride in B = s0), k modes (stride in B = s1)
-  if ((rc = prep(static_cast<const double *>(p.B), p.n, false, p.k, true, p.N, g.Npad,
+  if ((rc = prep(p.B, g.cplx ? 2 : 0, p.conjB, p.n, p.k, true, g.Ne, g.Npad,
                  g.off_rmB, g.off_scB, g.off_slB)))
     return rc;
 
@@ -564,25 +647,19 @@ int launch_contract_ozaki(const PairPlan &plan, void *workspace, cudaStream_t st
                            g.S, OZ_BM)))
     return rc;
   if ((rc = make_slice_map(&mapB, reinterpret_cast<int8_t *>(ws + g.off_slB), g.Kpad, g.Npad,
-                           g.S, OZ_BN)))
+                           g.S, g.BN)))
     return rc;
   OzGemmParams gp;
   gp.c = p;
   gp.S = g.S;
   gp.nkb = (int)(g.Kpad / OZ_BK);
+  gp.cplx = g.cplx;
+  gp.Me = g.Me; gp.Ne = g.Ne;
   gp.scaleA = reinterpret_cast<const double *>(ws + g.off_scA);
   gp.scaleB = reinterpret_cast<const double *>(ws + g.off_scB);
-  static bool attr_set = false;
-  if (!attr_set) {
-    QB_CUDA_CHECK(cudaFuncSetAttribute(ozaki_gemm_kernel,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)OZ_SMEM));
-    attr_set = true;
-  }
-  dim3 grid((unsigned)(g.Mpad / OZ_BM), (unsigned)((p.N + OZ_BN - 1) / OZ_BN));
-  ozaki_gemm_kernel<<<grid, 192, OZ_SMEM, st>>>(mapA, mapB, gp);
-  QB_LAUNCH_CHECK();
-  return 0;
+  dim3 grid((unsigned)(g.Mpad / OZ_BM), (unsigned)((g.Ne + g.BN - 1) / g.BN));
+  if (g.single) return oz_launch_gemm<128, float>(mapA, mapB, gp, grid, st);
+  return oz_launch_gemm<64, double>(mapA, mapB, gp, grid, st);
 }
 
 }  // namespace qb

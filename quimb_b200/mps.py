@@ -79,11 +79,21 @@ def _is_host(x):
     return isinstance(x, torch.Tensor) and x.device.type == "cpu"
 
 
+_STAGE_RING = {}
+
+
 def stream_sites(sites, copy_stream=None, depth=3):
     """Iterate over site arrays, staging host-resident sites to the device
     ``depth`` sites ahead on a side stream so the H2D copies overlap the
     contraction of the previous sites (pinned host memory makes the copies
-    truly asynchronous)."""
+    truly asynchronous).
+
+    Host sites land in a fixed RING of ``depth + 1`` device staging buffers
+    (allocated once per device / dtype / size, reused across calls): no
+    allocator traffic on the path, and a buffer is overwritten only after the
+    main stream has passed the work that consumed it (event recorded when the
+    consumer asks for the next site).  The yielded device tensors are therefore
+    TRANSIENT views: valid until ``depth`` further sites have been requested."""
     import torch
     if not any(_is_host(s) for s in sites):
         yield from sites
@@ -92,31 +102,64 @@ def stream_sites(sites, copy_stream=None, depth=3):
     main = torch.cuda.current_stream(dev)
     side = copy_stream or torch.cuda.Stream(device=dev)
     side.wait_stream(main)
+    nbuf = depth + 1
+
+    def as_tensor(s):
+        return s if isinstance(s, torch.Tensor) else torch.from_numpy(s)
+
+    hosts = [as_tensor(s) if _is_host(s) else None for s in sites]
+    need = {}
+    for h in hosts:
+        if h is not None:
+            need[h.dtype] = max(need.get(h.dtype, 0), h.numel())
+    rings = {}
+    for dt, n in need.items():
+        key = (dev.index, dt, nbuf)
+        ring = _STAGE_RING.get(key)
+        if ring is None or ring[0].numel() < n:
+            ring = [torch.empty(n, dtype=dt, device=dev) for _ in range(nbuf)]
+            _STAGE_RING[key] = ring
+        rings[dt] = ring
+    consumed = {dt: [None] * nbuf for dt in need}     # main-stream events per slot
+    count = {dt: 0 for dt in need}
     pending = []
 
-    def issue(s):
-        if not _is_host(s):
-            return (s, None)
-        t = s if isinstance(s, torch.Tensor) else torch.from_numpy(s)
+    def issue(i):
+        h = hosts[i]
+        if h is None:
+            return (sites[i], None, None)
+        dt = h.dtype
+        slot = count[dt] % nbuf
+        count[dt] += 1
+        buf = rings[dt][slot][:h.numel()].view(h.shape)
         with torch.cuda.stream(side):
-            d = t.to(dev, non_blocking=True)
+            if consumed[dt][slot] is not None:
+                side.wait_event(consumed[dt][slot])
+            buf.copy_(h, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(side)
-        return (d, ev)
+        return (buf, ev, (dt, slot))
 
-    it = iter(sites)
-    for s in it:
-        pending.append(issue(s))
-        if len(pending) >= depth:
-            break
+    n = len(sites)
+    nxt = 0
+    while nxt < n and len(pending) < depth:
+        pending.append(issue(nxt))
+        nxt += 1
+    prev = None
     while pending:
-        d, ev = pending.pop(0)
-        nxt = next(it, None)
-        if nxt is not None:
+        d, ev, where = pending.pop(0)
+        if prev is not None:
+            # everything the consumer enqueued for the previous site is on the
+            # main stream by now: its staging slot may be refilled after that
+            e = torch.cuda.Event()
+            e.record(main)
+            consumed[prev[0]][prev[1]] = e
+        if nxt < n:
             pending.append(issue(nxt))
+            nxt += 1
         if ev is not None:
             main.wait_event(ev)
-            d.record_stream(main)
+        prev = where
         yield d
 
 

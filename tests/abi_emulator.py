@@ -126,11 +126,14 @@ class EmulatedLib:
         la, lb, lc = (_labels(l, v.ndim) for l, v in ((la, a), (lb, b), (lc, c)))
         if a.dtype != b.dtype or a.dtype != c.dtype:
             return self._fail(-3, "dtype mismatch between operands")
-        if a.dtype not in (np.float64, np.complex128):
-            return self._fail(-1, "dtype is not supported by the contraction "
-                              "engine yet (supported: f64, c128)")
         if c.size == 0:
             return 0
+        single = a.dtype in (np.float32, np.complex64)
+        if single:
+            # the native single-precision engine accumulates exactly and rounds
+            # once (eligibility was decided by the real planner beforehand)
+            wide = np.float64 if a.dtype == np.float32 else np.complex128
+            a, b = a.astype(wide), b.astype(wide)
         remap = {}
         for l in la + lb + lc:
             remap.setdefault(l, len(remap))
@@ -141,6 +144,10 @@ class EmulatedLib:
             res = np.zeros(c.shape, c.dtype)
         else:
             res = np.einsum(x, sa, y, sb, sc, optimize=True)
+        if single and beta != 0.0:
+            res = alpha * res + beta * c.astype(res.dtype)
+            c[...] = res.astype(c.dtype)
+            return 0
         if beta == 0.0:
             c[...] = alpha * res if alpha != 1.0 else res
         else:
@@ -173,6 +180,10 @@ class EmulatedLib:
 
     def qb_contract_batched(self, A0, la, B0, lb, C0, lc, dA, dB, dC, count,
                             conjA, conjB, stream):
+        a0 = A0.contents if hasattr(A0, "contents") else A0
+        if a0.dtype in (_lib.QB_F32, _lib.QB_C64):
+            return self._fail(-101, "qb_contract_batched: single precision has no "
+                              "batched engine: widen")
         out = (ctypes.c_int64 * 16)()
         rc = self._real.qb_contract_pair_plan(A0, la, B0, lb, C0, lc, out)
         if rc:

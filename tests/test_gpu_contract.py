@@ -320,3 +320,64 @@ def test_single_precision_dtype_preserved(dtype, tol):
     ref2 = np.tensordot(a.transpose(2, 1, 0).conj(), b, axes=((0, 1), (0, 1)))
     assert out2.dtype == np.dtype(dtype)
     assert np.max(np.abs(out2.to_numpy() - ref2)) <= 10 * tol * np.max(np.abs(ref2))
+
+
+# ---- native single precision / complex on the tcgen05 engine ---------------
+SINGLE_CASES = [
+    ("ab,bc->ac", dict(a=256, b=192, c=160)),
+    ("ba,bc->ca", dict(a=300, b=200, c=150)),
+    ("apb,bqc->apqc", dict(a=130, p=2, b=140, q=2, c=70)),        # MPS-like
+    ("xyab,abcd->xycd", dict(x=16, y=16, a=12, b=12, c=9, d=9)),  # boundary absorb-like
+]
+
+
+@pytest.mark.parametrize("dtype", ["float32", "complex64"])
+@pytest.mark.parametrize("eq,sizes", SINGLE_CASES)
+def test_native_single_precision_engine(eq, sizes, dtype):
+    """float32 / complex64 contractions above the tile minimum run on the
+    tcgen05 engine directly (4 int8 slices, float epilogue): 5 launches, no
+    conversion passes; result at fp32 accuracy of the exact product (the
+    reference's numpy path rounds every partial sum to fp32, this rounds once)."""
+    rng = np.random.default_rng(abs(hash(eq + dtype)) % 2**31)
+    lhs, rhs = eq.split("->")
+    ta, tb = lhs.split(",")
+    a = _rand(rng, [sizes[c] for c in ta], dtype)
+    b = _rand(rng, [sizes[c] for c in tb], dtype)
+    sym = {c: i for i, c in enumerate(dict.fromkeys(ta + tb + rhs))}
+    A, B = qb.asarray(a), qb.asarray(b)
+    n0 = qb.launch_count()
+    out = qb.contract_pair(A.t, [sym[c] for c in ta], B.t, [sym[c] for c in tb],
+                           [sym[c] for c in rhs])
+    assert qb.launch_count() - n0 == 5
+    assert out.dtype == A.t.dtype
+    wide = np.result_type(dtype, np.float64)
+    ref = np.einsum(eq, a.astype(wide), b.astype(wide))
+    assert np.max(np.abs(out.cpu().numpy() - ref)) <= 2e-6 * np.max(np.abs(ref))
+    # conjugation flags are signs inside the split gather
+    outc = qb.contract_pair(A.t, [sym[c] for c in ta], B.t, [sym[c] for c in tb],
+                            [sym[c] for c in rhs], conj_a=True, conj_b=False)
+    refc = np.einsum(eq, a.astype(wide).conj(), b.astype(wide))
+    assert np.max(np.abs(outc.cpu().numpy() - refc)) <= 2e-6 * np.max(np.abs(refc))
+
+
+def test_native_single_accumulate_and_strided_output():
+    rng = np.random.default_rng(21)
+    a = _rand(rng, (200, 150), "complex64"); b = _rand(rng, (150, 180), "complex64")
+    c0 = _rand(rng, (180, 200), "complex64")
+    C = qb.asarray(c0.copy())
+    # out is written through its transpose (a strided view), accumulating
+    qb.contract_pair(qb.asarray(a).t, [0, 1], qb.asarray(b).t, [1, 2], [0, 2],
+                     out=C.t.t(), alpha=0.5, beta=2.0, conj_b=True)
+    ref = 0.5 * (a.astype(np.complex128) @ b.astype(np.complex128).conj()) + 2.0 * c0.T
+    assert np.max(np.abs(C.to_numpy().T - ref)) <= 3e-6 * np.max(np.abs(ref))
+
+
+def test_tcgen05_engine_complex128_embedding():
+    """complex128 through the same engine (8 slices): the complex operands are
+    embedded into the real GEMM inside the split gather."""
+    rng = np.random.default_rng(22)
+    a = _rand(rng, (160, 6, 40), "complex128"); b = _rand(rng, (40, 6, 130), "complex128")
+    out = qb.contract_pair(qb.asarray(a).t, [0, 1, 2], qb.asarray(b).t, [2, 1, 3], [3, 0],
+                           conj_a=True, engine=2)
+    ref = np.einsum("abc,cbd->da", a.conj(), b)
+    assert np.max(np.abs(out.cpu().numpy() - ref)) <= 1e-12 * np.max(np.abs(ref))

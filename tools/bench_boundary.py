@@ -57,6 +57,9 @@ def main():
     ap.add_argument("--dtype", default="complex64")
     ap.add_argument("--reps", type=int, default=1)
     ap.add_argument("--two-sided", action="store_true")
+    ap.add_argument("--profile", action="store_true",
+                    help="synchronised timers around qr / svd / contraction / permute calls "
+                         "(serialises the streams: use for the split, not for the total)")
     args = ap.parse_args()
     import torch
     import quimb_b200 as qb
@@ -67,6 +70,34 @@ def main():
         rank = int(os.environ["RANK"])
         torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
         dist.init_process_group("nccl")
+    prof = {}
+    if args.profile:
+        from quimb_b200 import contract as qc, linalg as ql, ops as qo, split as qs
+
+        def wrap(mod, name, tag, shape_of):
+            fn = getattr(mod, name)
+
+            def timed(*a, **k):
+                torch.cuda.synchronize(); t0 = time.perf_counter()
+                r = fn(*a, **k)
+                torch.cuda.synchronize(); dt = time.perf_counter() - t0
+                key = (tag, shape_of(*a, **k))
+                e = prof.setdefault(key, [0, 0.0])
+                e[0] += 1; e[1] += dt
+                return r
+            setattr(mod, name, timed)
+        mat = lambda x, *a, **k: (tuple(qo.asarray(x).shape), str(qo.asarray(x).dtype))
+        wrap(ql, "qr", "qr", mat)
+        wrap(ql, "svd", "svd", mat)
+        wrap(ql, "svd_trunc", "svd_trunc", mat)
+        wrap(qc, "contract_pair", "contract",
+             lambda a, la, b, lb, lc, *r, **k: (tuple(a.shape), tuple(b.shape), str(a.dtype)))
+        wrap(qc, "convert", "convert", lambda t, dt: (tuple(t.shape), str(t.dtype)))
+        # modules that imported the names directly
+        for m in (qs, bd, qo):
+            for nm in ("contract_pair", "convert"):
+                if hasattr(m, nm):
+                    setattr(m, nm, getattr(qc, nm))
     arrays = rand_peps(args.Lx, args.Ly, args.D, 2, args.dtype, seed=4)
     dev = [[qb.asarray(a) for a in row] for row in arrays]
     tensors, Lx, Ly = bd.peps_norm_tensors(dev)
@@ -87,6 +118,14 @@ def main():
                             "launches": qb.launch_count() - n0,
                             "value": [float(np.real(val)), float(np.imag(val))],
                             "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30})
+    if prof:
+        tot = {}
+        for (tag, shp), (n, t) in prof.items():
+            e = tot.setdefault(tag, [0, 0.0]); e[0] += n; e[1] += t
+        out["profile_totals"] = {k: {"calls": v[0], "seconds": round(v[1], 3)} for k, v in tot.items()}
+        top = sorted(prof.items(), key=lambda kv: -kv[1][1])[:12]
+        out["profile_top"] = [{"what": k[0], "shape": str(k[1]), "calls": v[0],
+                               "seconds": round(v[1], 3)} for k, v in top]
     if rank == 0:
         print(json.dumps(out), flush=True)
         os.makedirs("gpurun_out", exist_ok=True)
