@@ -24,7 +24,7 @@ from . import dist  # noqa: F401
 from .tree import (ContractExpression, GraphedContraction, Tree,  # noqa: F401
                    array_contract, find_sliced_tree, find_slices, find_tree,
                    gen_output_inds, tensor_contract)
-from .mps import (MovingEnvironment, compute_left_environments,  # noqa: F401
+from .mps import (ChainPlan, MovingEnvironment, compute_left_environments,  # noqa: F401
                   compute_right_environments, env_left_step, env_right_step,
                   mpo_ham_heis, mps_expec, mps_norm, mps_norm2)
 from .split import (array_split, array_svals, cholesky_regularized,  # noqa: F401

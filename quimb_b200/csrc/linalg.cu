@@ -69,7 +69,7 @@ constexpr int QR_THREADS = 256;
 template <int NB, int RPT>
 __global__ void __cluster_dims__(QR_CLUSTER, 1, 1) __launch_bounds__(QR_THREADS, 1)
     qr_panel_kernel(double *__restrict__ A, int64_t lda, int m, int nbw,
-                    double *__restrict__ Vout, double *__restrict__ Tout) {
+                    double *__restrict__ Vout, int64_t ldv, double *__restrict__ Tout) {
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
@@ -203,9 +203,7 @@ __global__ void __cluster_dims__(QR_CLUSTER, 1, 1) __launch_bounds__(QR_THREADS,
         if (c < nbw) {
           A[(int64_t)row * lda + c] = a[i][c];
           double v = (row > c) ? a[i][c] : (row == c ? 1.0 : 0.0);
-          Vout[(int64_t)row * NB + c] = v;
-        } else {
-          Vout[(int64_t)row * NB + c] = 0.0;
+          Vout[(int64_t)row * ldv + c] = v;
         }
       }
     }
@@ -258,16 +256,22 @@ __global__ void qr_phase_kernel(double *__restrict__ Q, int64_t m, int64_t kq,
 }
 
 template <int NB, int RPT>
-static int launch_panel(double *A, int64_t lda, int m, int nbw, double *V,
+static int launch_panel(double *A, int64_t lda, int m, int nbw, double *V, int64_t ldv,
                         double *T, cudaStream_t st) {
-  qr_panel_kernel<NB, RPT><<<QR_CLUSTER, QR_THREADS, 0, st>>>(A, lda, m, nbw, V, T);
+  qr_panel_kernel<NB, RPT><<<QR_CLUSTER, QR_THREADS, 0, st>>>(A, lda, m, nbw, V, ldv, T);
   QB_LAUNCH_CHECK();
   return 0;
 }
 
+// Outer (aggregated) panel width: the narrow register-resident panels (8-32
+// columns) only update the rest of their own outer panel; the trailing matrix
+// is updated once per outer panel with K = QR_NBO GEMMs (compact WY form of the
+// whole outer panel), so it is streamed n / QR_NBO times instead of n / nb.
+constexpr int QR_NBO = 128;
+
 struct QrGeom {
   int nb;
-  int64_t f_off, v_off, t_off, w_off, w2_off, sk_off, sk_elems, total;  // in doubles
+  int64_t f_off, v_off, t_off, to_off, g_off, w_off, w2_off, sk_off, sk_elems, total;  // doubles
 };
 
 static bool qr_geometry(int64_t m, int64_t n, QrGeom &g) {
@@ -277,23 +281,64 @@ static bool qr_geometry(int64_t m, int64_t n, QrGeom &g) {
   else if (m <= 16384) g.nb = 8;   // (8,8)
   else return false;
   const int64_t npan = (k + g.nb - 1) / g.nb;
+  const int64_t nout = (k + QR_NBO - 1) / QR_NBO;
   auto al = [](int64_t x) { return (x + 31) / 32 * 32; };  // 256-byte sections
   int64_t off = 0;
   g.f_off = off; off += al(m * n);                 // factored copy of X
-  g.v_off = off; off += al(npan * m * g.nb);       // explicit V per panel
-  g.t_off = off; off += al(npan * g.nb * g.nb);    // T per panel
-  g.w_off = off; off += al((int64_t)g.nb * std::max(n, k));
-  g.w2_off = off; off += al((int64_t)g.nb * std::max(n, k));
-  g.sk_elems = al((int64_t)16 * g.nb * std::max(n, k));  // split-K partials
+  g.v_off = off; off += al(m * (nout * QR_NBO));   // explicit V, one m x w slab per outer panel
+  g.t_off = off; off += al(npan * g.nb * g.nb);    // T per inner panel (tau on the diagonal)
+  g.to_off = off; off += al(nout * QR_NBO * QR_NBO);  // T per outer panel
+  g.g_off = off; off += al((int64_t)QR_NBO * QR_NBO);
+  g.w_off = off; off += al((int64_t)QR_NBO * std::max(n, k));
+  g.w2_off = off; off += al((int64_t)QR_NBO * std::max(n, k));
+  g.sk_elems = al((int64_t)16 * QR_NBO * std::max(n, k));  // split-K partials
   g.sk_off = off; off += g.sk_elems;
   g.total = off;
   return true;
 }
 
+// T of the compact WY form of w aggregated reflectors from the Gram matrix of
+// their vectors:  T^-1 = striu(V^T V) + diag(1 / tau)  (Puglisi 1992; Joffrain
+// et al. 2006).  One CTA, thread j back-substitutes column j of T.  tau_i sits
+// on the diagonal of the inner panels' T (tin: [panel][nb][nb]); tau_i = 0
+// (H_i = I) drops reflector i.
+__global__ void __launch_bounds__(QR_NBO)
+    wy_t_kernel(const double *__restrict__ G, int w, const double *__restrict__ tin, int nb,
+                double *__restrict__ T) {
+  extern __shared__ double ti[];       // [w][w + 1]: T^-1 (upper), dropped rows = identity
+  const int j = threadIdx.x;
+  const int ld = w + 1;
+  if (j < w) {
+    const double tj = tin[(int64_t)(j / nb) * nb * nb + (j % nb) * nb + (j % nb)];
+    for (int i = 0; i < w; ++i) {
+      const double tau_i = tin[(int64_t)(i / nb) * nb * nb + (i % nb) * nb + (i % nb)];
+      double v = 0.0;
+      if (i == j) v = (tj != 0.0) ? 1.0 / tj : 1.0;
+      else if (i < j && tj != 0.0 && tau_i != 0.0) v = G[(int64_t)i * w + j];
+      ti[i * ld + j] = v;
+    }
+  }
+  __syncthreads();
+  if (j < w) {
+    const double tj = tin[(int64_t)(j / nb) * nb * nb + (j % nb) * nb + (j % nb)];
+    // column j of T: solve (T^-1) x = e_j, x_i = 0 for i > j
+    double x[QR_NBO];
+#pragma unroll 1
+    for (int i = j; i >= 0; --i) {
+      double acc = (i == j) ? 1.0 : 0.0;
+#pragma unroll 1
+      for (int k = i + 1; k <= j; ++k) acc -= ti[i * ld + k] * x[k];
+      x[i] = acc / ti[i * ld + i];
+    }
+    if (tj == 0.0) x[j] = 0.0;   // dropped reflector
+    for (int i = 0; i < w; ++i) T[(int64_t)i * w + j] = (i <= j) ? x[i] : 0.0;
+  }
+}
+
 // Householder QR of row-major X (m x n) -> factored F (in workspace), V, T.
 // Q (m x k) and/or R (k x n) formed on request.  k = min(m, n).
 int qr_f64(int64_t m, int64_t n, const double *X, double *Q, double *R,
-                  int stabilized, double *ws, cudaStream_t st) {
+           int stabilized, double *ws, cudaStream_t st) {
   QrGeom g;
   if (!qr_geometry(m, n, g)) {
     set_error("qb_qr_stab: m = %lld exceeds the register-panel limit 16384",
@@ -302,34 +347,60 @@ int qr_f64(int64_t m, int64_t n, const double *X, double *Q, double *R,
   }
   const int64_t k = std::min(m, n);
   const int nb = g.nb;
-  double *F = ws + g.f_off, *V = ws + g.v_off, *T = ws + g.t_off;
+  double *F = ws + g.f_off, *V = ws + g.v_off, *T = ws + g.t_off, *TO = ws + g.to_off;
+  double *G = ws + g.g_off;
   double *W = ws + g.w_off, *W2 = ws + g.w2_off;
   double *SK = ws + g.sk_off;
   const int64_t SKN = g.sk_elems;
+  static bool attr_set = false;
+  if (!attr_set) {
+    QB_CUDA_CHECK(cudaFuncSetAttribute(wy_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       QR_NBO * (QR_NBO + 1) * 8));
+    attr_set = true;
+  }
   QB_CUDA_CHECK(cudaMemcpyAsync(F, X, sizeof(double) * m * n,
                                 cudaMemcpyDeviceToDevice, st));
   int rc;
-  int64_t pi = 0;
-  for (int64_t j0 = 0; j0 < k; j0 += nb, ++pi) {
-    const int nbw = (int)std::min<int64_t>(nb, k - j0);
-    const int mp = (int)(m - j0);
-    double *Fp = F + j0 * n + j0;
-    double *Vp = V + pi * m * nb;  // (m - j0) x nb used
-    double *Tp = T + pi * nb * nb;
-    if (nb == 32 && mp <= 2048) rc = launch_panel<32, 1>(Fp, n, mp, nbw, Vp, Tp, st);
-    else if (nb == 32) rc = launch_panel<32, 2>(Fp, n, mp, nbw, Vp, Tp, st);
-    else if (nb == 16) rc = launch_panel<16, 4>(Fp, n, mp, nbw, Vp, Tp, st);
-    else rc = launch_panel<8, 8>(Fp, n, mp, nbw, Vp, Tp, st);
-    if (rc) return rc;
-    const int64_t nt = n - (j0 + nbw);
+  int64_t po = 0;
+  for (int64_t j0 = 0; j0 < k; j0 += QR_NBO, ++po) {
+    const int w = (int)std::min<int64_t>(QR_NBO, k - j0);   // outer panel width
+    const int64_t mp = m - j0;
+    double *Vo = V + po * m * QR_NBO;   // (m - j0) x w, leading dimension w
+    double *To = TO + po * QR_NBO * QR_NBO;   // w x w, leading dimension w
+    double *Ti = T + (j0 / nb) * nb * nb;     // inner T's of this outer panel (w / nb of them)
+    QB_CUDA_CHECK(cudaMemsetAsync(Vo, 0, sizeof(double) * mp * w, st));
+    for (int ji = 0; ji < w; ji += nb) {
+      const int64_t col = j0 + ji;
+      const int nbw = (int)std::min<int64_t>(nb, w - ji);
+      const int mpi = (int)(m - col);
+      double *Fp = F + col * n + col;
+      double *Vp = Vo + (int64_t)ji * w + ji;   // rows from `col`, columns ji.., ld w
+      double *Tp = Ti + (int64_t)(ji / nb) * nb * nb;
+      if (nb == 32 && mpi <= 2048) rc = launch_panel<32, 1>(Fp, n, mpi, nbw, Vp, w, Tp, st);
+      else if (nb == 32) rc = launch_panel<32, 2>(Fp, n, mpi, nbw, Vp, w, Tp, st);
+      else if (nb == 16) rc = launch_panel<16, 4>(Fp, n, mpi, nbw, Vp, w, Tp, st);
+      else rc = launch_panel<8, 8>(Fp, n, mpi, nbw, Vp, w, Tp, st);
+      if (rc) return rc;
+      const int64_t nti = w - (ji + nbw);   // rest of the OUTER panel only
+      if (nti > 0) {
+        double *A2 = F + col * n + col + nbw;
+        // W = Vp^T A2 (nbw x nti); W2 = Tp^T W; A2 -= Vp W2
+        if ((rc = gemm_f64(Vp, 1, w, A2, n, 1, W, nti, 1, nbw, nti, mpi, 1.0, 0.0, st, SK, SKN, 16))) return rc;
+        if ((rc = gemm_f64(Tp, 1, nb, W, nti, 1, W2, nti, 1, nbw, nti, nbw, 1.0, 0.0, st))) return rc;
+        if ((rc = gemm_f64(Vp, w, 1, W2, nti, 1, A2, n, 1, mpi, nti, nbw, -1.0, 1.0, st))) return rc;
+      }
+    }
+    // compact WY form of the whole outer panel: G = Vo^T Vo, T from its inverse
+    if ((rc = gemm_f64(Vo, 1, w, Vo, w, 1, G, w, 1, w, w, mp, 1.0, 0.0, st, SK, SKN, 16))) return rc;
+    wy_t_kernel<<<1, QR_NBO, (size_t)w * (w + 1) * 8, st>>>(G, w, Ti, nb, To);
+    QB_LAUNCH_CHECK();
+    const int64_t nt = n - (j0 + w);
     if (nt > 0) {
-      double *A2 = F + j0 * n + j0 + nbw;
-      // W = V^T A2            (nb x nt)
-      if ((rc = gemm_f64(Vp, 1, nb, A2, n, 1, W, nt, 1, nb, nt, mp, 1.0, 0.0, st, SK, SKN, 16))) return rc;
-      // W2 = T^T W            (nb x nt)
-      if ((rc = gemm_f64(Tp, 1, nb, W, nt, 1, W2, nt, 1, nb, nt, nb, 1.0, 0.0, st))) return rc;
-      // A2 -= V W2
-      if ((rc = gemm_f64(Vp, nb, 1, W2, nt, 1, A2, n, 1, mp, nt, nb, -1.0, 1.0, st))) return rc;
+      double *C = F + j0 * n + j0 + w;
+      // C <- (I - Vo To Vo^T)^T C = C - Vo (To^T (Vo^T C))
+      if ((rc = gemm_f64(Vo, 1, w, C, n, 1, W, nt, 1, w, nt, mp, 1.0, 0.0, st, SK, SKN, 16))) return rc;
+      if ((rc = gemm_f64(To, 1, w, W, nt, 1, W2, nt, 1, w, nt, w, 1.0, 0.0, st))) return rc;
+      if ((rc = gemm_f64(Vo, w, 1, W2, nt, 1, C, n, 1, mp, nt, w, -1.0, 1.0, st))) return rc;
     }
   }
   const int blocks = sm_count() * 4;
@@ -340,17 +411,18 @@ int qr_f64(int64_t m, int64_t n, const double *X, double *Q, double *R,
   if (Q) {
     set_identity_kernel<<<blocks, 256, 0, st>>>(Q, m, k);
     QB_LAUNCH_CHECK();
-    // Q = H_1 ... H_p [I; 0], panels applied last to first on Q[j0:, j0:]
-    const int64_t npan = (k + nb - 1) / nb;
-    for (int64_t pj = npan - 1; pj >= 0; --pj) {
-      const int64_t j0 = pj * nb;
-      const int mp = (int)(m - j0);
+    // Q = H_1 ... H_p [I; 0], outer panels applied last to first on Q[j0:, j0:]
+    const int64_t nout = (k + QR_NBO - 1) / QR_NBO;
+    for (int64_t pj = nout - 1; pj >= 0; --pj) {
+      const int64_t j0 = pj * QR_NBO;
+      const int w = (int)std::min<int64_t>(QR_NBO, k - j0);
+      const int64_t mp = m - j0;
       const int64_t nq = k - j0;
-      double *Vp = V + pj * m * nb, *Tp = T + pj * nb * nb;
+      double *Vo = V + pj * m * QR_NBO, *To = TO + pj * QR_NBO * QR_NBO;
       double *Qs = Q + j0 * k + j0;
-      if ((rc = gemm_f64(Vp, 1, nb, Qs, k, 1, W, nq, 1, nb, nq, mp, 1.0, 0.0, st, SK, SKN, 16))) return rc;
-      if ((rc = gemm_f64(Tp, nb, 1, W, nq, 1, W2, nq, 1, nb, nq, nb, 1.0, 0.0, st))) return rc;
-      if ((rc = gemm_f64(Vp, nb, 1, W2, nq, 1, Qs, k, 1, mp, nq, nb, -1.0, 1.0, st))) return rc;
+      if ((rc = gemm_f64(Vo, 1, w, Qs, k, 1, W, nq, 1, w, nq, mp, 1.0, 0.0, st, SK, SKN, 16))) return rc;
+      if ((rc = gemm_f64(To, w, 1, W, nq, 1, W2, nq, 1, w, nq, w, 1.0, 0.0, st))) return rc;
+      if ((rc = gemm_f64(Vo, w, 1, W2, nq, 1, Qs, k, 1, mp, nq, w, -1.0, 1.0, st))) return rc;
     }
   }
   if (stabilized && (Q || R)) {

@@ -460,6 +460,14 @@ __global__ void __launch_bounds__(256, MINB) jacobi_round_kernel(const Params P)
   J2_TRACE(6);
 }
 
+// de-phases the independent streams of a sweep: stream g starts its rounds
+// g * stagger later, so that the L2-bound Gram / apply phases of one stream
+// fall into the eigen-solve phase of another instead of all coinciding
+__global__ void delay_kernel(unsigned long long ns) {
+  const unsigned long long t0 = now_ns();
+  while (now_ns() - t0 < ns) __nanosleep(200);
+}
+
 // ---------------------------------------------------------------- schedule ---
 // A sweep as a list of phases; inside a phase `ngroups` independent launch
 // sequences (one per stream), each a list of rounds, each round a list of
@@ -763,6 +771,7 @@ static int jacobi_iterate(double *W, double *Z, int64_t n, int64_t npad, int2 *d
   P.offmax = reinterpret_cast<unsigned long long *>(flag + 2);
   P.trace = trace_buffer() ? trace_buffer() + 16 * 8192 : nullptr;
   static const int inner0 = [] { const char *e = getenv("QB_JAC_INNER"); return e ? atoi(e) : 1; }();
+  static const long stagger_ns = [] { const char *e = getenv("QB_JAC_STAGGER"); return e ? atol(e) : 0L; }();
   SideStreams &SS = side_streams();
   const bool multi = sched.ngroups > 1;
   int sweeps = 0;
@@ -777,6 +786,10 @@ static int jacobi_iterate(double *W, double *Z, int64_t n, int64_t npad, int2 *d
       for (size_t g = 0; g < ph.rounds.size(); ++g) {
         cudaStream_t gs = multi ? SS.s[g % 4] : st;
         if (multi) QB_CUDA_CHECK(cudaStreamWaitEvent(gs, SS.fork, 0));
+        if (multi && g > 0 && stagger_ns > 0) {
+          delay_kernel<<<1, 1, 0, gs>>>((unsigned long long)g * stagger_ns);
+          QB_LAUNCH_CHECK();
+        }
         for (const auto &rd : ph.rounds[g]) {
           P.pairs = d_pairs + rd.first;
           P.trace_slot = (slot++) & 1023;

@@ -365,3 +365,63 @@ def mpo_ham_heis(L, j=1.0, bz=0.0, dtype="float64"):
         w = W[4:5] if i == 0 else (W[:, 0:1] if i == L - 1 else W)
         sites.append(np.ascontiguousarray(w.astype(dtype)))
     return sites
+
+
+class ChainPlan:
+    """A structured chain contraction captured ONCE into a CUDA graph and
+    replayed: the device-resident plan for ``contract_structured`` /
+    ``compute_left/right_environments`` / ``MovingEnvironment.init_segment``
+    (quimb/tensor/tn1d/core.py:502-607, tn1d/dmrg.py:281-322).
+
+    ``kind``: 'norm' (<psi|psi>), 'expec' (<psi|H|psi>), 'left_envs' /
+    'right_envs' (all environments, of the norm network when ``mpo`` is None).
+    The site (and MPO) arrays are copied into static device buffers owned by
+    the plan; ``update(i, array)`` / ``update_all(sites)`` refresh them in place
+    and ``__call__`` replays the whole chain -- hundreds of launches of the
+    contraction kernel, their workspaces and intermediates -- with one graph
+    launch and no host work per site.  Outputs are the plan's own buffers
+    (clone to keep across replays)."""
+
+    def __init__(self, sites, mpo=None, shape="lrp", mpo_shape="lrud", kind="norm"):
+        import torch
+        if kind not in ("norm", "expec", "left_envs", "right_envs"):
+            raise ValueError(f"unknown plan kind {kind!r}")
+        if kind == "expec" and mpo is None:
+            raise ValueError("kind='expec' needs an MPO")
+        self.kind, self.shape, self.mpo_shape = kind, shape, mpo_shape
+        self.sites = [ops.materialize(ops.asarray(s), force=True) for s in sites]
+        self.mpo = None if mpo is None else [ops.materialize(ops.asarray(w), force=True)
+                                             for w in mpo]
+        self._run()                       # warm-up: workspaces, kernel attributes
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = self._run()
+        self.replays = 0
+
+    def _run(self):
+        if self.kind == "norm":
+            return mps_norm2(self.sites, self.shape)
+        if self.kind == "expec":
+            return mps_expec(self.sites, self.mpo, self.shape, self.mpo_shape)
+        fn = compute_left_environments if self.kind == "left_envs" else compute_right_environments
+        return fn(self.sites, self.mpo, self.shape, self.mpo_shape)
+
+    def update(self, i, array):
+        a = ops.asarray(array)
+        if tuple(a.shape) != tuple(self.sites[i].shape):
+            raise ValueError("shape mismatch with the captured plan")
+        self.sites[i].t.copy_(a.resolve())
+
+    def update_all(self, sites):
+        if len(sites) != len(self.sites):
+            raise ValueError("wrong number of sites")
+        for i, s in enumerate(sites):
+            self.update(i, s)
+
+    def __call__(self, sites=None):
+        if sites is not None:
+            self.update_all(sites)
+        self.graph.replay()
+        self.replays += 1
+        return self.out

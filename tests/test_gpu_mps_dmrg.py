@@ -292,3 +292,35 @@ def test_dmrg1_matches_reference_and_oracle(golden_mps):
     d.solve(tol=1e-8, max_sweeps=10, sweep_sequence="RL")
     assert d.state[0].dtype == np.complex128
     assert abs(d.energy - np.linalg.eigvalsh(dm.mpo_to_dense(mpo))[0]) < 1e-7
+
+
+def test_chain_plans_replay_as_cuda_graphs():
+    """Norm, expectation and the environment chain as persistent device plans
+    (SURVEY 8f rank 2): captured once, replayed with new site data, zero
+    host-side launches per replay, values equal to the eager path / oracle."""
+    L, chi = 14, 24
+    mpo = dm.mpo_heis(L)
+    s1 = dm.mps_rand(L, chi, seed=4)
+    s2 = dm.mps_rand(L, chi, seed=5)
+    plan_n = qb.ChainPlan(s1, shape="lpr", kind="norm")
+    plan_e = qb.ChainPlan(s1, mpo, shape="lpr", mpo_shape="lrdu", kind="expec")
+    plan_r = qb.ChainPlan(s1, mpo, shape="lpr", mpo_shape="lrdu", kind="right_envs")
+    plan_l = qb.ChainPlan(s1, shape="lpr", kind="left_envs")
+    for sites in (s1, s2):
+        dev = [qb.asarray(a) for a in sites]
+        n0 = qb.launch_count()
+        n2 = plan_n(dev).item()
+        ex = plan_e(dev).item()
+        envs = plan_r(dev)
+        lenv = plan_l(dev)
+        assert qb.launch_count() == n0          # graph replays only
+        assert abs(n2 - dm.mps_norm2(sites)) <= 1e-11 * abs(n2)
+        assert abs(ex - dm.mps_expec(sites, mpo)) <= 1e-10 * max(1.0, abs(ex))
+        eager = qb.compute_right_environments(dev, [qb.asarray(w) for w in mpo], "lpr", "lrdu")
+        for k, E in eager.items():
+            np.testing.assert_allclose(envs[k].to_numpy(), E.to_numpy(), rtol=1e-12, atol=1e-13)
+        eager_l = qb.compute_left_environments(dev, None, "lpr")
+        for k, E in eager_l.items():
+            np.testing.assert_allclose(lenv[k].to_numpy(), E.to_numpy(), rtol=1e-12, atol=1e-13)
+    with pytest.raises(ValueError):
+        plan_n.update(3, np.zeros((2, 2, 2)))
