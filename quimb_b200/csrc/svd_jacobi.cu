@@ -27,6 +27,7 @@
 #include <cooperative_groups.h>
 #include <math.h>
 #include <stdlib.h>
+#include <time.h>
 
 #include <algorithm>
 #include <vector>
@@ -737,6 +738,7 @@ static int launch_round_cfg(const Config &c, const Params &P, int npairs, cudaSt
 }
 
 struct SideStreams {
+  cudaStream_t cap = nullptr;      // origin stream of the sweep-graph capture
   cudaStream_t s[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t fork = nullptr, join[4] = {nullptr, nullptr, nullptr, nullptr};
   bool ok = false;
@@ -749,6 +751,7 @@ static SideStreams &side_streams() {
       cudaEventCreateWithFlags(&S.join[i], cudaEventDisableTiming);
     }
     cudaEventCreateWithFlags(&S.fork, cudaEventDisableTiming);
+    cudaStreamCreateWithFlags(&S.cap, cudaStreamNonBlocking);
     S.ok = true;
   }
   return S;
@@ -778,13 +781,21 @@ static int jacobi_iterate(double *W, double *Z, int64_t n, int64_t npad, int2 *d
   const int max_sweeps = 60;
   int slot = 0;
   bool done = false;
-  for (; sweeps < max_sweeps && !done; ++sweeps) {
-    P.inner_max = (sweeps < 25) ? inner0 : std::max(inner0, 4);
-    QB_CUDA_CHECK(cudaMemsetAsync(flag, 0, 16, st));
+  static const bool prof = getenv("QB_JAC_PROFILE") != nullptr;
+  double t_issue = 0.0, t_wait = 0.0;
+  auto wall = [] {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec + 1e-9 * ts.tv_nsec;
+  };
+  // one sweep = every phase forked over the group streams and joined again;
+  // `origin` is the stream the forks hang off (the caller's, or the capture
+  // stream when the sweep is recorded into a CUDA graph)
+  auto enqueue_sweep = [&](cudaStream_t origin) -> int {
     for (const Phase &ph : sched.phases) {
-      if (multi) QB_CUDA_CHECK(cudaEventRecord(SS.fork, st));
+      if (multi) QB_CUDA_CHECK(cudaEventRecord(SS.fork, origin));
       for (size_t g = 0; g < ph.rounds.size(); ++g) {
-        cudaStream_t gs = multi ? SS.s[g % 4] : st;
+        cudaStream_t gs = multi ? SS.s[g % 4] : origin;
         if (multi) QB_CUDA_CHECK(cudaStreamWaitEvent(gs, SS.fork, 0));
         if (multi && g > 0 && stagger_ns > 0) {
           delay_kernel<<<1, 1, 0, gs>>>((unsigned long long)g * stagger_ns);
@@ -794,17 +805,80 @@ static int jacobi_iterate(double *W, double *Z, int64_t n, int64_t npad, int2 *d
           P.pairs = d_pairs + rd.first;
           P.trace_slot = (slot++) & 1023;
           int rc = launch_round_cfg(cfg, P, rd.second, gs);
-          if (rc) return -rc;
+          if (rc) return rc;
         }
         if (multi) {
           QB_CUDA_CHECK(cudaEventRecord(SS.join[g % 4], gs));
-          QB_CUDA_CHECK(cudaStreamWaitEvent(st, SS.join[g % 4], 0));
+          QB_CUDA_CHECK(cudaStreamWaitEvent(origin, SS.join[g % 4], 0));
         }
       }
     }
+    return 0;
+  };
+  // Sweeps after the first replay a CUDA graph of the sweep (the launch
+  // sequence of a sweep is fixed: ~500 cluster launches on 4 streams cost more
+  // host time than the device needs to run them).  The executable graph is
+  // cached per (buffers, size, configuration): a DMRG sweep factors the same
+  // shape in the same workspace at every site.
+  struct SweepGraph {
+    cudaGraphExec_t exec = nullptr;
+    const void *W = nullptr, *Z = nullptr, *pairs = nullptr;
+    int64_t n = 0, npad = 0;
+    Config cfg{0, 0, 0, 0};
+    int inner = 0;
+    long stagger = 0;
+  };
+  static thread_local SweepGraph SG;
+  static const bool use_graph = [] {
+    const char *e = getenv("QB_JAC_GRAPH");
+    return !(e && atoi(e) == 0);
+  }();
+  const bool graph_ok = use_graph && !P.trace && multi;
+  auto graph_matches = [&]() {
+    return SG.exec && SG.W == W && SG.Z == Z && SG.pairs == d_pairs && SG.n == n &&
+           SG.npad == npad && SG.cfg.cs == cfg.cs && SG.cfg.ch == cfg.ch &&
+           SG.cfg.stg == cfg.stg && SG.cfg.groups == cfg.groups && SG.inner == inner0 &&
+           SG.stagger == stagger_ns;
+  };
+  for (; sweeps < max_sweeps && !done; ++sweeps) {
+    const double t0 = wall();
+    P.inner_max = (sweeps < 25) ? inner0 : std::max(inner0, 4);
+    QB_CUDA_CHECK(cudaMemsetAsync(flag, 0, 16, st));
+    bool launched = false;
+    if (graph_ok && sweeps >= 1 && sweeps < 25) {
+      if (!graph_matches()) {
+        if (SG.exec) { cudaGraphExecDestroy(SG.exec); SG.exec = nullptr; }
+        cudaGraph_t gr = nullptr;
+        bool ok = cudaStreamBeginCapture(SS.cap, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+        if (ok) {
+          const int rc = enqueue_sweep(SS.cap);
+          ok = (cudaStreamEndCapture(SS.cap, &gr) == cudaSuccess) && rc == 0 && gr;
+        }
+        if (ok) ok = cudaGraphInstantiate(&SG.exec, gr, 0) == cudaSuccess;
+        if (gr) cudaGraphDestroy(gr);
+        if (ok) {
+          SG.W = W; SG.Z = Z; SG.pairs = d_pairs; SG.n = n; SG.npad = npad; SG.cfg = cfg;
+          SG.inner = inner0; SG.stagger = stagger_ns;
+        } else {
+          cudaGetLastError();     // clear; fall back to direct launches
+          SG.exec = nullptr;
+        }
+      }
+      if (SG.exec) {
+        QB_CUDA_CHECK(cudaGraphLaunch(SG.exec, st));
+        g_launch_count.fetch_add(1, std::memory_order_relaxed);
+        launched = true;
+      }
+    }
+    if (!launched) {
+      int rc = enqueue_sweep(st);
+      if (rc) return -rc;
+    }
     struct { int flag; int pad; unsigned long long off; } h = {0, 0, 0};
     QB_CUDA_CHECK(cudaMemcpyAsync(&h, flag, 16, cudaMemcpyDeviceToHost, st));
+    const double t1 = wall();
     QB_CUDA_CHECK(cudaStreamSynchronize(st));
+    t_issue += t1 - t0; t_wait += wall() - t1;
     // converged when a whole sweep rotated nothing.  (Stopping one sweep
     // earlier because the largest scaled off-diagonal was tiny is NOT safe:
     // for close singular values the rotation ANGLES stay large however small
@@ -812,6 +886,10 @@ static int jacobi_iterate(double *W, double *Z, int64_t n, int64_t npad, int2 *d
     // measured: 1e-11 .. 2e-10 loss of orthogonality on degenerate spectra.)
     if (!h.flag) done = true;
   }
+  if (prof)
+    fprintf(stderr, "[qb jacobi] n=%lld sweeps=%d groups=%d cs=%d: host issue %.1f ms, "
+            "waiting for the device %.1f ms\n", (long long)n, sweeps, sched.ngroups, cfg.cs,
+            t_issue * 1e3, t_wait * 1e3);
   if (sweeps_out) *sweeps_out = sweeps;
   if (!done) {
     set_error("qb_svd: Jacobi did not converge in %d sweeps", max_sweeps);
