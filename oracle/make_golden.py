@@ -525,6 +525,82 @@ def boundary_cases():
     json.dump(meta, open(os.path.join(OUT, "boundary.json"), "w"), indent=1)
 
 
+def compressed_cases():
+    """_contract_compressed_tid_sequence of the reference (compress_mode
+    'basic', tree_gauge_distance=0: no tree gauging) on small networks along a
+    fixed sequence: final values for several option sets."""
+    store, meta = {}, {}
+    nets = {
+        "flat44": qtn.TN2D_rand(4, 4, D=3, seed=5),
+        "flat53_c": qtn.TN2D_rand(5, 3, D=2, seed=6, dtype="complex128"),
+        "norm33": qtn.PEPS.rand(3, 3, bond_dim=2, phys_dim=2, seed=8).make_norm(),
+        "reg10": qtn.TN_rand_reg(10, 3, D=3, seed=11),
+    }
+    for name, tn in nets.items():
+        tids = list(tn.tensor_map)
+        arrays = [np.asarray(tn.tensor_map[t].data) for t in tids]
+        inputs = [list(map(str, tn.tensor_map[t].inds)) for t in tids]
+        output = list(map(str, tn.outer_inds()))
+        # a greedy pairwise sequence (smallest result first): (tid1, tid2) steps,
+        # the result lives on under the second id
+        sizes = {}
+        for a, t in zip(arrays, inputs):
+            for ix, d in zip(t, a.shape):
+                sizes[ix] = d
+        live = {k: set(t) for k, t in enumerate(inputs)}
+        seq = []
+        while len(live) > 1:
+            best = None
+            keys = list(live)
+            for x in range(len(keys)):
+                for y in range(x + 1, len(keys)):
+                    a, b = keys[x], keys[y]
+                    if not (live[a] & live[b]):
+                        continue
+                    other = set(output)
+                    for k2, v in live.items():
+                        if k2 not in (a, b):
+                            other |= v
+                    res = {ix for ix in (live[a] | live[b]) if ix in other}
+                    cost = int(np.prod([sizes[ix] for ix in res])) if res else 1
+                    if best is None or cost < best[0]:
+                        best = (cost, a, b, res)
+            if best is None:          # disconnected: outer product of the first two
+                a, b = keys[0], keys[1]
+                best = (0, a, b, live[a] | live[b])
+            _, a, b, res = best
+            seq.append((a, b))
+            del live[a]
+            del live[b]
+            live[b] = res
+        exact = tn.contract(all, optimize="auto-hq", output_inds=tn.outer_inds())
+        exact = np.asarray(exact.data if hasattr(exact, "data") else exact)
+        for k, a in enumerate(arrays):
+            store[f"{name}__t{k}"] = a
+        runs = []
+        for kw in [dict(max_bond=4, cutoff=0.0), dict(max_bond=8, cutoff=0.0),
+                   dict(max_bond=6, cutoff=1e-6), dict(max_bond=5, cutoff=0.0, compress_late=False),
+                   dict(max_bond=6, cutoff=0.0, compress_span=2),
+                   dict(max_bond=6, cutoff=0.0, compress_matrices=False),
+                   dict(max_bond=4, cutoff=0.0, equalize_norms=True),
+                   dict(max_bond=7, cutoff=0.0, compress_min_size=64)]:
+            tn2 = tn.copy()
+            res = tn2._contract_compressed_tid_sequence(
+                [(tids[a], tids[b]) for a, b in seq], output_inds=tn.outer_inds(),
+                tree_gauge_distance=0, compress_mode="basic", **kw)
+            val = np.asarray(res.data if hasattr(res, "data") else res)
+            if hasattr(res, "inds"):
+                val = np.asarray(res.transpose(*tn.outer_inds()).data)
+            key = f"{name}__run{len(runs)}"
+            store[key] = val
+            runs.append({"kw": kw, "key": key})
+        store[f"{name}__exact"] = exact
+        meta[name] = {"inputs": inputs, "output": output, "seq": [list(s) for s in seq],
+                      "runs": runs, "dtype": str(tn.dtype)}
+    np.savez_compressed(os.path.join(OUT, "compressed.npz"), **store)
+    json.dump(meta, open(os.path.join(OUT, "compressed.json"), "w"), indent=1)
+
+
 def tebd_cases():
     """gate_split / gate_with_auto_swap / TEBD of the reference (numpy)."""
     store, meta = {}, {}
@@ -678,8 +754,8 @@ def mps_dmrg_cases():
 
 if __name__ == "__main__":
     only = set(sys.argv[1:])
-    for fn in (contract_cases, decomp_cases, decomp2_cases, decomp3_cases, boundary_cases, tebd_cases, mps_ops_cases,
-               mps_dmrg_cases):
+    for fn in (contract_cases, decomp_cases, decomp2_cases, decomp3_cases, boundary_cases, compressed_cases,
+               tebd_cases, mps_ops_cases, mps_dmrg_cases):
         if not only or fn.__name__ in only:
             fn()
     print("golden fixtures written to", OUT)

@@ -39,6 +39,7 @@ from .tebd import TEBD, LocalHam1D, gate_split, gate_with_auto_swap  # noqa: F40
 from .boundary import (BoundaryContractor2D, contract_boundary,  # noqa: F401
                        contract_boundary_two_sided, peps_norm_tensors)
 from .dmrg import DMRG1, DMRG2  # noqa: F401
+from .compressed import contract_compressed, path_to_sequence  # noqa: F401
 from .integration import register_with_quimb  # noqa: F401
 
 

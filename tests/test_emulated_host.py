@@ -38,6 +38,7 @@ _SKIP = {
     "test_gpu_tebd": set(),
     "test_gpu_linop": set(),
     "test_gpu_zz_edge_cases": set(),
+    "test_gpu_compressed": set(),
 }
 
 
