@@ -333,6 +333,8 @@ def run_unit(qb, shard, prob, steps, warmup, barrier, events=True):
     barrier()
     nmv = (H.nmatvec - n0) / steps
     assert nmv == UNIT_MATVECS, nmv
+    if shard is not None:
+        shard.check()           # a peer-memory kernel that gave up waiting would show here
     return ev0.elapsed_time(ev1) / steps, theta, H
 
 

@@ -287,6 +287,7 @@ class DMRG2:
                                 self.renv[i + 1], dims, self.shard)
             loc_en, gs_local, info = self._eigs(Hs, Hs.local_slab(v0), comm=self.shard)
             loc_gs = Hs.gather(gs_local)
+            self.shard.check()
             Heff.nmatvec = Hs.nmatvec
         else:
             loc_en, loc_gs, info = self._eigs(Heff, v0)
