@@ -78,9 +78,13 @@ def build(force=False, verbose=False):
             sys.stderr.write(f"[quimb_b200.build] {s}:\n{out}\n")
     if failed:
         raise RuntimeError("nvcc compilation failed")
+    # link next to the target and rename: the library is replaced atomically
+    # (a snapshot of the tree never sees a half-written .so)
+    tmp = LIB + ".tmp"
     cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a",
-           "-cudart", "static", "-o", LIB, *objs]
+           "-cudart", "static", "-o", tmp, *objs]
     subprocess.run(cmd, check=True)
+    os.replace(tmp, LIB)
     with open(STAMP, "w") as fh:
         fh.write(dig)
     return LIB

@@ -177,9 +177,11 @@ __global__ void __launch_bounds__(256)
   R f = ar, g = ai;
   if (div) {
     // divide by a device scalar (real part only is used: norms are real)
+    // an exactly zero divisor (norm of an exactly zero vector: Krylov
+    // breakdown) leaves a zero vector, not NaNs
     R d = div[0];
-    f = ar / d;
-    g = ai / d;
+    f = (d == R(0)) ? R(0) : ar / d;
+    g = (d == R(0)) ? R(0) : ai / d;
   }
   if (!cplx || g == R(0)) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nreal;

@@ -69,11 +69,9 @@ def _norm_c(x, comm):
 _MD_MAX = 16        # rows per call of the fused Krylov kernels (csrc: MD_MAX)
 
 
-def _safe(nrm):
-    """Divisor for a normalisation queued before the host has seen the norm:
-    an exact Krylov breakdown (norm 0: the vector is exactly zero) must give
-    a zero vector, not NaNs; the host drops everything behind that step."""
-    return Array(torch.clamp_min(nrm.t, 1e-300))
+# (a normalisation queued before the host has seen the norm divides by a
+# device scalar; qb_scale maps an exactly zero divisor -- exact Krylov
+# breakdown -- to a zero vector, and the host drops everything behind that step)
 
 
 def _combine(V, m, coeffs, out, alpha=1.0):
@@ -237,7 +235,7 @@ def eigh_lanczos(matvec, v0, which="SA", ncv=4, tol=1e-3, maxiter=None,
                 # columns of these steps are read together with the next one
                 skip -= 1
                 V[j + 1].copy_(w)
-                ops.scale_(Array(V[j + 1]), 1.0, div_by=_safe(bnorm))
+                ops.scale_(Array(V[j + 1]), 1.0, div_by=bnorm)
                 continue
             rows = colbuf[pending:j + 1, :j + 2].cpu().numpy()
             info["host_reads"] += 1
@@ -282,7 +280,7 @@ def eigh_lanczos(matvec, v0, which="SA", ncv=4, tol=1e-3, maxiter=None,
                 if nmv + skip + 1 < min_steps:
                     skip = max(skip, min(2, min_steps - nmv - 2))
             V[j + 1].copy_(w)
-            ops.scale_(Array(V[j + 1]), 1.0, div_by=_safe(bnorm))
+            ops.scale_(Array(V[j + 1]), 1.0, div_by=bnorm)
         m = meff
 
         def ritz(yvec, out_v, out_w):

@@ -228,7 +228,7 @@ class EmulatedLib:
         f, g = alpha[0], alpha[1]
         if _addr(div):
             d = _flat(div, 1, _REAL[dtype])[0]
-            f, g = f / d, g / d
+            f, g = (0.0, 0.0) if d == 0 else (f / d, g / d)
         xv = _flat(x, n, _NP[dtype])
         if dtype in (_lib.QB_C64, _lib.QB_C128) and g != 0.0:
             xv[...] = (xv * complex(f, g)).astype(xv.dtype)
