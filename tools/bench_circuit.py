@@ -39,6 +39,9 @@ def main():
     ap.add_argument("--max-gb", type=float, default=140.0,
                     help="refuse trees whose live intermediates exceed this many GB")
     ap.add_argument("--out", default=None)
+    ap.add_argument("--tree-file", default=None,
+                    help="JSON with a previously found sliced tree (ssa steps + sliced index "
+                         "positions) for exactly this circuit: skips the host search")
     args = ap.parse_args()
     import numpy as np
     import torch
@@ -56,8 +59,25 @@ def main():
         args.Lx, args.Ly, args.depth, seed=3, dense=nq <= 20)
     sd = {ix: 2 for t in inputs for ix in t}
     t0 = time.perf_counter()
-    tr, sliced = T.find_sliced_tree(inputs, output, sd, args.target_width,
-                                    min_slices=world if world > 1 else None)
+    loaded = None
+    if args.tree_file and os.path.exists(args.tree_file):
+        rec = json.load(open(args.tree_file))
+        if (rec.get("config") == [args.Lx, args.Ly, args.depth, args.target_width]
+                and rec.get("n_inputs") == len(inputs)):
+            loaded = rec
+    if loaded is not None:
+        sliced = [ix for ix in loaded["sliced"]]
+        s_ = set(sliced)
+        red = [tuple(ix for ix in t if ix not in s_) for t in inputs]
+        tr = T.Tree(red, tuple(output), sd, [tuple(st) for st in loaded["ssa"]])
+    else:
+        tr, sliced = T.find_sliced_tree(inputs, output, sd, args.target_width,
+                                        min_slices=world if world > 1 else None)
+        if args.tree_file and rank == 0:
+            json.dump({"config": [args.Lx, args.Ly, args.depth, args.target_width],
+                       "n_inputs": len(inputs), "sliced": list(sliced),
+                       "ssa": [[i, j] for i, j, _, _ in tr.steps]},
+                      open(args.tree_file, "w"))
     t_find = time.perf_counter() - t0
     n_slices = 2 ** len(sliced)
     macs_slice = tr.contraction_cost()
