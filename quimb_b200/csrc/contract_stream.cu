@@ -177,7 +177,11 @@ contract_stream_kernel(const __grid_constant__ ContractParams p) {
 
 bool stream_eligible(const PairPlan &plan) {
   const ContractParams &p = plan.p;
-  return p.N >= 1 && p.K >= 1 && p.N <= 16 && p.K <= 16 && p.M >= 1;
+  // real operators up to 32 x 32 (the (w d d) = 20-wide MPO step of the DMRG
+  // two-site matvec), complex ones up to 16 x 16 (register budget)
+  const int lim = plan.dtype == QB_F64 ? 32 : 16;
+  return (plan.dtype == QB_F64 || plan.dtype == QB_C128) && p.N >= 1 && p.K >= 1 &&
+         p.N <= lim && p.K <= lim && p.M >= 1;
 }
 
 template <bool CPLX, int KMAX, int NMAX>
@@ -198,14 +202,16 @@ static int launch_stream_c(const PairPlan &plan, cudaStream_t st) {
   p.splitk = 1;
   p.partial = nullptr;
   if (p.N <= 4 && p.K <= 4) return launch_stream_t<CPLX, 4, 4>(p, st);
-  if (p.N <= 4) return launch_stream_t<CPLX, 16, 4>(p, st);
-  if (p.K <= 4) return launch_stream_t<CPLX, 4, 16>(p, st);
-  return launch_stream_t<CPLX, 16, 16>(p, st);
+  if (p.N <= 4 && p.K <= 16) return launch_stream_t<CPLX, 16, 4>(p, st);
+  if (p.K <= 4 && p.N <= 16) return launch_stream_t<CPLX, 4, 16>(p, st);
+  if (p.N <= 16 && p.K <= 16) return launch_stream_t<CPLX, 16, 16>(p, st);
+  if constexpr (!CPLX) return launch_stream_t<false, 32, 32>(p, st);
+  return -9;
 }
 
 int launch_contract_stream(const PairPlan &plan, cudaStream_t st) {
   if (!stream_eligible(plan)) {
-    set_error("streaming engine: needs N <= 16 and K <= 16 (got N = %lld, K = %lld)",
+    set_error("streaming engine: needs N, K <= 32 (real) / 16 (complex) (got N = %lld, K = %lld)",
               (long long)plan.p.N, (long long)plan.p.K);
     return -9;
   }
@@ -217,8 +223,8 @@ int launch_contract_stream(const PairPlan &plan, cudaStream_t st) {
 template <bool CPLX>
 static void stream_host_t(const ContractParams &p) {
   constexpr int ES = CPLX ? 2 : 1;
-  double Bs[16 * 16 * ES];
-  int64_t kOffA[16], nOffC[16];
+  double Bs[32 * 32 * ES];
+  int64_t kOffA[32], nOffC[32];
   for (int64_t zb = 0; zb < p.nbatch; ++zb) {
     const double *A, *B;
     double *C;
@@ -226,9 +232,10 @@ static void stream_host_t(const ContractParams &p) {
     stream_fill_tables<CPLX>(p, B, 0, 1, Bs, kOffA, nOffC);
     for (int64_t m = 0; m < p.M; ++m) {
       if (p.N <= 4 && p.K <= 4) stream_row<CPLX, 4, 4>(p, A, C, m, Bs, kOffA, nOffC);
-      else if (p.N <= 4) stream_row<CPLX, 16, 4>(p, A, C, m, Bs, kOffA, nOffC);
-      else if (p.K <= 4) stream_row<CPLX, 4, 16>(p, A, C, m, Bs, kOffA, nOffC);
-      else stream_row<CPLX, 16, 16>(p, A, C, m, Bs, kOffA, nOffC);
+      else if (p.N <= 4 && p.K <= 16) stream_row<CPLX, 16, 4>(p, A, C, m, Bs, kOffA, nOffC);
+      else if (p.K <= 4 && p.N <= 16) stream_row<CPLX, 4, 16>(p, A, C, m, Bs, kOffA, nOffC);
+      else if (p.N <= 16 && p.K <= 16) stream_row<CPLX, 16, 16>(p, A, C, m, Bs, kOffA, nOffC);
+      else stream_row<CPLX, 32, 32>(p, A, C, m, Bs, kOffA, nOffC);
     }
   }
 }
