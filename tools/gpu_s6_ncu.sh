@@ -17,4 +17,5 @@ timeout 300 $NCU -k regex:qr_panel -s 20 -c 2 -f -o $out/prof_qr_panel_${tag} \
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv \
     --log-file $out/launches_${tag}.csv python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline --no-dmrg \
     > $out/${tag}_bench_under_ncu.log 2>&1
+timeout 300 python tools/bench_dmrg.py --L 100 --chi 1024 --no-cpu > $out/${tag}_dmrg_sweep_L100.log 2>&1; tail -2 $out/${tag}_dmrg_sweep_L100.log | cut -c1-600
 ls -la $out/*.ncu-rep $out/launches_${tag}.csv
