@@ -102,9 +102,18 @@ static int env_engine() {
   }();
   return v;
 }
+// float64 GEMM-shaped contractions from this many flops up take the tcgen05
+// engine under QB_ENGINE_AUTO: measured on a B200 (profiles/r02_matvec_probe.json)
+// it wins at 4096^3 (41.4 vs 32.9 TFLOP/s for the DMMA kernel, cuBLAS dgemm 35.4)
+// and loses at 2048^3 (28.2 vs 31.2) and on the 4.3e10-flop DMRG GEMMs (within
+// +-9 %); BASELINE configs[0] (two rank-4 chi=64 tensors = 4096^3) is above it.
+constexpr double kOzakiAutoFlops = 1.0e11;
 static bool want_ozaki(int engine, const PairPlan &plan) {
   if (is_single(plan.dtype)) return ozaki_eligible(plan);   // the only native engine
   if (engine == QB_ENGINE_AUTO) engine = env_engine();
+  if (engine == QB_ENGINE_AUTO && plan.dtype == QB_F64 &&
+      2.0 * (double)plan.p.M * (double)plan.p.N * (double)plan.p.K >= kOzakiAutoFlops)
+    return ozaki_eligible(plan);
   return engine == QB_ENGINE_OZAKI && ozaki_eligible(plan);
 }
 // streaming engine (contract_stream.cu): small-operator steps, N, K <= 16

@@ -153,3 +153,23 @@ def test_dmrg2_two_site_update_at_chi1024_vs_numpy():
     Eref = np.tensordot(An, T, axes=((0, 1), (0, 2)))                # b' w1 b
     assert E.shape == Eref.shape
     assert _rel(E, Eref) < 1e-11
+
+
+def test_cfg1_4096_cubed_takes_the_tcgen05_engine_by_default():
+    """BASELINE configs[0] at full size: two rank-4 chi=64 tensors sharing two
+    indices = a 4096^3 GEMM.  Above 1e11 flops `engine=auto` is the tcgen05
+    int8-split engine (5 launches: row maxima + split of each operand, GEMM);
+    result at fp64 level against numpy."""
+    rng = np.random.default_rng(15)
+    a = rng.standard_normal((64, 64, 64, 64))
+    b = rng.standard_normal((64, 64, 64, 64))
+    A, B = qb.asarray(a), qb.asarray(b)
+    n0 = qb.launch_count()
+    out = qb.tensordot(A, B, axes=((2, 3), (0, 1)))
+    assert qb.launch_count() - n0 == 5
+    ref = np.tensordot(a, b, axes=((2, 3), (0, 1)))
+    assert _rel(out.to_numpy(), ref) < 1e-12
+    # permuted operands (the index permutation is folded into the split gather)
+    out2 = qb.tensordot(A.transpose(0, 2, 1, 3), B.transpose(3, 1, 2, 0), axes=((1, 3), (3, 2)))
+    ref2 = np.tensordot(a.transpose(0, 2, 1, 3), b.transpose(3, 1, 2, 0), axes=((1, 3), (3, 2)))
+    assert _rel(out2.to_numpy(), ref2) < 1e-12
