@@ -768,7 +768,7 @@ static int jacobi_iterate(double *W, double *Z, int64_t n, int64_t npad, int2 *d
   QB_CUDA_CHECK(cudaMemcpyAsync(d_pairs, sched.pairs.data(), sizeof(int2) * sched.pairs.size(),
                                 cudaMemcpyHostToDevice, st));
   Params P;
-  P.W = W; P.V = Z; P.ld = npad; P.rows_w = (int)n; P.rows_v = (int)npad;
+  P.W = W; P.V = Z; P.ld = npad; P.rows_w = (int)n; P.rows_v = Z ? (int)npad : 0;
   P.tol = 1e-15 * sqrt((double)n) * 8.0;
   P.flag = flag;
   P.offmax = reinterpret_cast<unsigned long long *>(flag + 2);
@@ -944,14 +944,36 @@ static int svd_trunc_tall(int64_t m, int64_t n, const double *X, double cutoff,
   int2 *d_pairs = reinterpret_cast<int2 *>(ws + g.pairs_off);
   double *d_scale = ws + g.scale_off;
   const int blocks = sm_count() * 4;
+  // Modes whose RIGHT factor is the isometry (left / lfactor / rorthog) and the
+  // values-only mode need no accumulated rotations: with W = R^T the rotated
+  // columns are W Z = Y S, so V = Y is read off the normalised columns and
+  // U (f S) = f X Y is one GEMM on the original matrix -- the apply phase
+  // touches half the rows, Z is never formed and neither is Q1.  (The mirror
+  // family -- right / lorthog / rfactor -- reaches this path through the
+  // transpose in the host layer for square input.)  Modes that return BOTH
+  // isometries (None, both, lsqrt, rsqrt) keep the accumulation: dividing the
+  // other factor by tiny singular values would lose its orthogonality.
+  const bool left_family = absorb == QB_ABSORB_LEFT || absorb == QB_ABSORB_LFACTOR ||
+                           absorb == QB_ABSORB_RORTHOG;
+  const bool vals_only = absorb == QB_ABSORB_S;
+  static const bool no_accum_ok = [] {
+    const char *e = getenv("QB_SVD_ACCUMULATE");
+    return !(e && atoi(e) == 1);
+  }();
+  const bool accumulate = !((left_family || vals_only) && no_accum_ok);
   const bool need_u = ap.want_l && U;
-  int rc = qr_f64(m, n, X, need_u ? Q1 : nullptr, R, /*stabilized=*/0, ws + g.qr_off, st);
+  int rc = qr_f64(m, n, X, (need_u && accumulate) ? Q1 : nullptr, R, /*stabilized=*/0,
+                  ws + g.qr_off, st);
   if (rc) return rc;
   const int64_t npad = g.npad;
   pad_copy_kernel<<<blocks, 256, 0, st>>>(R, n, n, n, W, npad, n, 2);  // W = R^T
   QB_LAUNCH_CHECK();
-  pad_copy_kernel<<<blocks, 256, 0, st>>>(nullptr, 0, 0, 0, Z, npad, npad, 1);
-  QB_LAUNCH_CHECK();
+  if (accumulate) {
+    pad_copy_kernel<<<blocks, 256, 0, st>>>(nullptr, 0, 0, 0, Z, npad, npad, 1);
+    QB_LAUNCH_CHECK();
+  } else {
+    Z = nullptr;
+  }
   int sw = jacobi_iterate(W, Z, n, npad, d_pairs, flag, sweeps_out, st);
   if (sw < 0) return -sw;
   colnorm_kernel<<<(unsigned)(npad / 32), 256, 0, st>>>(W, npad, (int)n, (int)npad, sv);
@@ -995,6 +1017,25 @@ static int svd_trunc_tall(int64_t m, int64_t n, const double *X, double cutoff,
   if (S && ap.want_s)
     QB_CUDA_CHECK(cudaMemcpyAsync(S, sk.data(), sizeof(double) * nk, cudaMemcpyHostToDevice, st));
   const bool need_v = ap.want_r && VH;
+  if (!accumulate) {
+    if (vals_only) {
+      QB_CUDA_CHECK(cudaStreamSynchronize(st));
+      return 0;
+    }
+    // Y^T (nk x n, rows = normalised rotated columns): the caller's VH, or
+    // scratch when only the left factor is wanted
+    double *Yt = need_v ? VH : UR;
+    gather_scaled_kernel<<<blocks, 256, 0, st>>>(W, W, npad, (int)n, (int)nk, perm, sv,
+                                                 d_scale, d_scale + nk, nullptr, Yt);
+    QB_LAUNCH_CHECK();
+    QB_CUDA_CHECK(cudaStreamSynchronize(st));  // host vectors go out of scope
+    if (need_u) {
+      // U (f S) = f X Y :  (m x n) . (n x nk), Y[i, j] = Yt[j, i]
+      rc = gemm_f64(X, n, 1, Yt, 1, n, U, nk, 1, m, nk, n, f, 0.0, st);
+      if (rc) return rc;
+    }
+    return 0;
+  }
   if (need_u || need_v) {
     gather_scaled_kernel<<<blocks, 256, 0, st>>>(W, Z, npad, (int)n, (int)nk, perm, sv,
                                                  d_scale, d_scale + nk,

@@ -351,8 +351,14 @@ def svd_trunc(x, cutoff=-1.0, cutoff_mode=4, max_bond=-1, absorb=0, renorm=0, in
         raise TypeError("svd_trunc: float64 only (other dtypes go through svd())")
     m, n = x.shape
     code = 100 if absorb is None else int(absorb)
-    if m < n:
-        # X^T = V s U^T: factor the transpose, swap the roles of the factors
+    if m < n or (m == n and code in (1, 10, 11)):
+        # X^T = V s U^T: factor the transpose, swap the roles of the factors.
+        # Also taken for SQUARE input whose LEFT factor is to be the isometry
+        # ('right' / 'lorthog' / 'rfactor': DMRG's right-moving sweep): the
+        # mirrored mode needs no accumulated rotations in the kernel (the
+        # isometry is read off the rotated columns, the other factor is one GEMM
+        # with the original matrix), which halves the rows the Jacobi apply
+        # phase streams; the transpose itself is one 32 MiB permute-copy.
         xt = ops.materialize(Array(x.t.t()))
         l, s, r = svd_trunc(xt, cutoff, cutoff_mode, max_bond, _MIRROR_ABSORB[code],
                             renorm, info)
