@@ -38,11 +38,16 @@ out = {"n": n, "sweeps": sw, "ms": min(ts), "ms_all": ts,
                                                "QB_JAC_STG", "QB_JAC_GROUPS", "QB_JAC_INNER")
                if os.environ.get(k)}}
 # fused truncated split (DMRG shape: keep half, absorb right)
-e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-e0.record()
+for name, code in (("trunc_ms", 1), ("trunc_left_ms", -1), ("trunc_both_ms", 0)):
+    ts2 = []
+    for _ in range(2):
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        l, _, r = qb.linalg.svd_trunc(X, cutoff=0.0, cutoff_mode=3, max_bond=n // 2, absorb=code)
+        e1.record(); torch.cuda.synchronize()
+        ts2.append(e0.elapsed_time(e1))
+    out[name] = min(ts2)
 l, _, r = qb.linalg.svd_trunc(X, cutoff=0.0, cutoff_mode=3, max_bond=n // 2, absorb=1)
-e1.record(); torch.cuda.synchronize()
-out["trunc_ms"] = e0.elapsed_time(e1)
 if check:
     x = X.to_numpy()
     sref = np.linalg.svd(x, compute_uv=False)
@@ -51,6 +56,7 @@ if check:
     out["u_orth"] = float(np.abs(u.T @ u - np.eye(n)).max())
     out["v_orth"] = float(np.abs(v @ v.T - np.eye(n)).max())
     out["recon"] = float(np.abs((u * s.to_numpy()) @ v - x).max() / sref[0])
+    out["trunc_l_orth"] = float(np.abs(l.to_numpy().T @ l.to_numpy() - np.eye(n // 2)).max())
     out["trunc_recon"] = float(np.abs(l.to_numpy() @ r.to_numpy() - (u[:, :n // 2] * sref[:n // 2]) @ v[:n // 2]).max() / sref[0])
 print(json.dumps(out), flush=True)
 if os.environ.get("QB_TRACE"):
