@@ -637,14 +637,14 @@ __global__ void __launch_bounds__(256)
 __global__ void pad_copy_kernel(const double *__restrict__ src, int64_t rows,
                                 int64_t cols, int64_t ld_src, double *__restrict__ dst,
                                 int64_t ld_dst, int64_t rows_dst, int mode) {
-  // mode 1: identity; mode 2: dst = [src^T | 0]
+  // mode 1: identity; mode 2: dst = [src^T | 0]; mode 3: dst = [src | 0]
   const int64_t tot = rows_dst * ld_dst;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < tot;
        i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / ld_dst, c = i - r * ld_dst;
     double v = 0.0;
     if (mode == 1) v = (r == c) ? 1.0 : 0.0;
-    else if (r < rows && c < cols) v = src[c * ld_src + r];
+    else if (r < rows && c < cols) v = (mode == 3) ? src[r * ld_src + c] : src[c * ld_src + r];
     dst[i] = v;
   }
 }
@@ -955,18 +955,24 @@ static int svd_trunc_tall(int64_t m, int64_t n, const double *X, double cutoff,
   // other factor by tiny singular values would lose its orthogonality.
   const bool left_family = absorb == QB_ABSORB_LEFT || absorb == QB_ABSORB_LFACTOR ||
                            absorb == QB_ABSORB_RORTHOG;
+  // mirror family (U the isometry): rotate the columns of R itself, R Z' = U_R S,
+  // so U = Q1 U_R from the normalised columns and (f S) V^T = f U_R^T R by one GEMM
+  const bool right_family = absorb == QB_ABSORB_RIGHT || absorb == QB_ABSORB_LORTHOG ||
+                            absorb == QB_ABSORB_RFACTOR;
   const bool vals_only = absorb == QB_ABSORB_S;
   static const bool no_accum_ok = [] {
     const char *e = getenv("QB_SVD_ACCUMULATE");
     return !(e && atoi(e) == 1);
   }();
-  const bool accumulate = !((left_family || vals_only) && no_accum_ok);
+  const bool accumulate = !((left_family || right_family || vals_only) && no_accum_ok);
   const bool need_u = ap.want_l && U;
-  int rc = qr_f64(m, n, X, (need_u && accumulate) ? Q1 : nullptr, R, /*stabilized=*/0,
-                  ws + g.qr_off, st);
+  int rc = qr_f64(m, n, X, (need_u && (accumulate || right_family)) ? Q1 : nullptr, R,
+                  /*stabilized=*/0, ws + g.qr_off, st);
   if (rc) return rc;
   const int64_t npad = g.npad;
-  pad_copy_kernel<<<blocks, 256, 0, st>>>(R, n, n, n, W, npad, n, 2);  // W = R^T
+  // W = R^T, or R itself for the accumulation-free right family
+  pad_copy_kernel<<<blocks, 256, 0, st>>>(R, n, n, n, W, npad, n,
+                                          (right_family && !accumulate) ? 3 : 2);
   QB_LAUNCH_CHECK();
   if (accumulate) {
     pad_copy_kernel<<<blocks, 256, 0, st>>>(nullptr, 0, 0, 0, Z, npad, npad, 1);
@@ -1020,6 +1026,27 @@ static int svd_trunc_tall(int64_t m, int64_t n, const double *X, double cutoff,
   if (!accumulate) {
     if (vals_only) {
       QB_CUDA_CHECK(cudaStreamSynchronize(st));
+      return 0;
+    }
+    if (right_family) {
+      // U_R (n x nk) = normalised rotated columns of R (scale 1 / s, null
+      // columns stay zero); U = Q1 U_R; (f S) V^T = f U_R^T R
+      std::vector<double> inv(nk);
+      for (int64_t i = 0; i < nk; ++i) inv[i] = ss[i] > 0.0 ? 1.0 / ss[i] : 0.0;
+      QB_CUDA_CHECK(cudaMemcpyAsync(d_scale, inv.data(), sizeof(double) * nk,
+                                    cudaMemcpyHostToDevice, st));
+      gather_scaled_kernel<<<blocks, 256, 0, st>>>(W, W, npad, (int)n, (int)nk, perm, sv,
+                                                   d_scale, d_scale, UR, nullptr);
+      QB_LAUNCH_CHECK();
+      QB_CUDA_CHECK(cudaStreamSynchronize(st));  // host vectors go out of scope
+      if (need_u) {
+        rc = gemm_f64(Q1, n, 1, UR, nk, 1, U, nk, 1, m, nk, n, 1.0, 0.0, st);
+        if (rc) return rc;
+      }
+      if (need_v) {
+        rc = gemm_f64(UR, 1, nk, R, n, 1, VH, n, 1, nk, n, n, f, 0.0, st);
+        if (rc) return rc;
+      }
       return 0;
     }
     // Y^T (nk x n, rows = normalised rotated columns): the caller's VH, or

@@ -408,6 +408,11 @@ def svd_trunc(x, cutoff=-1.0, cutoff_mode=4, max_bond=-1, absorb=0, renorm=0, in
         # reference's LAPACK V always is one)
         miss = list(range(k - int(nnull.value), k))
         _complete_isometry(right, miss, rows=True)
+    if nnull.value and left is not None and code in (1, 10):
+        # same for the left isometry of the accumulation-free right family
+        # (U = Q1 U_R with U_R the normalised rotated columns: null for s = 0)
+        miss = list(range(k - int(nnull.value), k))
+        _complete_isometry(left, miss)
     return (None if left is None else Array(left), None if S is None else Array(S[:k]),
             None if right is None else Array(right))
 
