@@ -374,3 +374,70 @@ def test_materialize_of_a_high_rank_general_permutation():
     # a contiguous tensor and a plain transpose stay single-launch
     assert permute_modes(qb.asarray(z).t) == 1
     assert permute_modes(qb.asarray(z.reshape(2 ** 11, 2 ** 11)).t.t()) == 2
+
+
+@pytest.mark.parametrize("shape", [(300, 120), (128, 128), (64, 200), (257, 33)])
+@pytest.mark.parametrize("kind", ["full", "lowrank"])
+def test_fused_truncated_split_all_absorb_modes(shape, kind):
+    """qb_svd_trunc through split.svd_truncated for every absorb mode, tall /
+    square / wide, full and rank-deficient: the accumulation-free paths (left
+    family directly, right family natively for tall input and through the
+    transpose for square input) against the oracle's truncation of LAPACK's SVD
+    (decomp.py:829-1118): kept rank, singular values, products and the
+    isometry of whichever factor the mode leaves orthonormal."""
+    from oracle import decomp_np as dn
+    rng = np.random.default_rng(shape[0] * 7 + shape[1])
+    m, n = shape
+    if kind == "full":
+        x = rng.standard_normal((m, n))
+    else:
+        r = min(m, n) // 3
+        x = rng.standard_normal((m, r)) @ rng.standard_normal((r, n))
+    for absorb in (None, 2, -12, -11, -10, -1, 0, 1, 10, 11, 12):
+        for kw in (dict(cutoff=1e-3, cutoff_mode=4, max_bond=-1, renorm=0),
+                   dict(cutoff=0.0, cutoff_mode=3, max_bond=min(m, n) // 2, renorm=0),
+                   dict(cutoff=1e-2, cutoff_mode=3, max_bond=-1, renorm=2)):
+            info, oinfo = {"error": None}, {"error": None}
+            L, s, R = qb.svd_truncated(qb.asarray(x), absorb=absorb, info=info, **kw)
+            Lo, so, Ro = dn.svd_truncated(x, absorb=absorb, info=oinfo, **kw)
+            for got, ref in ((L, Lo), (s, so), (R, Ro)):
+                assert (got is None) == (ref is None), (absorb, kw)
+            if s is not None:
+                np.testing.assert_allclose(s.to_numpy(), so, rtol=0, atol=1e-11 * max(so.max(), 1e-300))
+            assert abs(info["error"] - oinfo["error"]) <= 1e-10 * max(1.0, oinfo["error"])
+            scale = np.linalg.norm(x, 2)
+            if L is not None and R is not None:
+                mid = np.diag(s.to_numpy()) if s is not None else None
+                rec = L.to_numpy() @ (mid @ R.to_numpy() if mid is not None else R.to_numpy())
+                reco = Lo @ (np.diag(so) @ Ro if so is not None else Ro)
+                assert np.abs(rec - reco).max() <= 1e-10 * scale, (absorb, kw)
+            # gauge-free checks of single factors: Gram matrices
+            if L is not None:
+                assert L.shape == Lo.shape
+                assert np.abs(L.to_numpy().T @ L.to_numpy() - Lo.T @ Lo).max() <= 1e-9 * max(1.0, scale ** 2), (absorb, kw)
+            if R is not None:
+                assert R.shape == Ro.shape
+                assert np.abs(R.to_numpy() @ R.to_numpy().T - Ro @ Ro.T).max() <= 1e-9 * max(1.0, scale ** 2), (absorb, kw)
+
+
+def test_zero_extent_contraction_into_a_strided_output():
+    """K = 0 with beta = 0 zero-fills exactly the (strided, possibly 8-byte
+    aligned) output view and nothing around it (the vector fill
+    ignored strides)."""
+    import torch
+    buf = torch.full((6, 10), 7.0, dtype=torch.float64, device="cuda")
+    out = buf[1:5, 1::2]                                   # strided, 8-byte aligned view
+    a = torch.zeros((4, 0), dtype=torch.float64, device="cuda")
+    b = torch.zeros((0, 5), dtype=torch.float64, device="cuda")
+    qb.contract_pair(a, [0, 1], b, [1, 2], [0, 2], out=out)
+    h = buf.cpu().numpy()
+    assert np.all(h[1:5, 1::2] == 0.0)
+    mask = np.ones_like(h, dtype=bool); mask[1:5, 1::2] = False
+    assert np.all(h[mask] == 7.0)
+    # complex, contiguous but offset by one element (16-byte aligned for c128)
+    cb = torch.full((9,), 1 + 2j, dtype=torch.complex128, device="cuda")
+    qb.contract_pair(torch.zeros((3, 0), dtype=torch.complex128, device="cuda"), [0, 1],
+                     torch.zeros((0, 2), dtype=torch.complex128, device="cuda"), [1, 2], [0, 2],
+                     out=cb[1:7].view(3, 2))
+    hc = cb.cpu().numpy()
+    assert np.all(hc[1:7] == 0) and hc[0] == 1 + 2j and np.all(hc[7:] == 1 + 2j)
