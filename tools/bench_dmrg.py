@@ -49,7 +49,7 @@ def main():
         args.no_cpu = True
 
     out = {"L": args.L, "chi": args.chi, "dtype": "f64"}
-    mpo = dm.mpo_heis(args.L)
+    mpo = qb.mpo_ham_heis(args.L)        # same arrays as the oracle's mpo_heis
     d = qb.DMRG2(mpo, args.chi, cutoffs=0.0, mpo_shape="lrdu", seed=2, shard=shard)
     if args.ncv:
         d.opts["device_eig_ncv"] = args.ncv
@@ -99,6 +99,7 @@ def main():
     }
     if shard is not None:
         out["shard"]["bytes_gathered"] = shard.bytes_gathered
+        out["shard"]["exchange"] = shard.exchange_name
     if rank == 0:
         print(json.dumps(out), flush=True)
     if not args.no_cpu:
