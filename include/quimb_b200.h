@@ -191,6 +191,10 @@ int qb_axpby(int dtype, int64_t n, const double alpha[2], const void *x,
 /* x *= alpha / (*dev_scalar)  (dev_scalar may be NULL); Lanczos normalise */
 int qb_scale(int dtype, int64_t n, const double alpha[2],
              const void *dev_div_scalar, void *x, void *stream);
+/* y = x * alpha / (*dev_div_scalar) (divisor optional; zero divisor -> zeros):
+ * the normalised copy of a Krylov residual in one pass. */
+int qb_scale_into(int dtype, int64_t n, double alpha, const void *dev_div_scalar,
+                  const void *x, void *y, void *stream);
 /* out[0] (device, same dtype as x; complex: conj(x).y) = <x|y>; deterministic
  * two-stage reduction; workspace >= qb_dot_workspace(n) bytes */
 int qb_dot(int dtype, int64_t n, const void *x, const void *y, void *out,

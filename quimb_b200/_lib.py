@@ -91,6 +91,7 @@ def load(build_if_missing=True):
     sig("qb_permute", ci, [T, T, ci, vp])
     sig("qb_axpby", ci, [ci, i64, dblp, vp, dblp, vp, vp])
     sig("qb_scale", ci, [ci, i64, dblp, vp, vp, vp])
+    sig("qb_scale_into", ci, [ci, i64, ctypes.c_double, vp, vp, vp, vp])
     sig("qb_dot", ci, [ci, i64, vp, vp, vp, vp, vp])
     sig("qb_dot_workspace", i64, [i64])
     sig("qb_scale_diag", ci, [ci, i64, i64, vp, vp, ci, ci, vp])

@@ -197,6 +197,20 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+template <typename R>
+__global__ void __launch_bounds__(256)
+    scale_into_kernel(int64_t nreal, R a, const R *__restrict__ div, const R *__restrict__ x,
+                      R *__restrict__ y) {
+  R f = a;
+  if (div) {
+    const R d = div[0];
+    f = (d == R(0)) ? R(0) : a / d;
+  }
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nreal;
+       i += (int64_t)gridDim.x * blockDim.x)
+    y[i] = x[i] * f;
+}
+
 // two-stage deterministic dot: stage 1 one partial per block (fixed grid),
 // stage 2 a single block sums the partials in a fixed order
 constexpr int DOT_BLOCKS = 592;  // 4 per SM
@@ -451,6 +465,24 @@ int qb_scale(int dtype, int64_t n, const double alpha[2],
     scale_kernel<float><<<ew_blocks(nreal), 256, 0, st>>>(
         nreal, (float)alpha[0], (float)alpha[1], (const float *)dev_div_scalar, cplx, (float *)x);
   else { set_error("qb_scale: bad dtype"); return -1; }
+  QB_LAUNCH_CHECK();
+  return 0;
+}
+
+// y = x * alpha / (*div)  (real factor; complex data as 2 n reals): the
+// normalised copy of a Krylov residual in one pass instead of copy + scale
+int qb_scale_into(int dtype, int64_t n, double alpha, const void *dev_div_scalar,
+                  const void *x, void *y, void *stream) {
+  if (n <= 0) return 0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t nreal = dtype_is_complex(dtype) ? 2 * n : n;
+  if (dtype == QB_F64 || dtype == QB_C128)
+    scale_into_kernel<double><<<ew_blocks(nreal), 256, 0, st>>>(
+        nreal, alpha, (const double *)dev_div_scalar, (const double *)x, (double *)y);
+  else if (dtype == QB_F32 || dtype == QB_C64)
+    scale_into_kernel<float><<<ew_blocks(nreal), 256, 0, st>>>(
+        nreal, (float)alpha, (const float *)dev_div_scalar, (const float *)x, (float *)y);
+  else { set_error("qb_scale_into: bad dtype"); return -1; }
   QB_LAUNCH_CHECK();
   return 0;
 }

@@ -76,7 +76,13 @@ class EffHam2:
                                  [W_, S_, T_, W2_, SB_, TB_], conj_a=W1.cj,
                                  conj_b=W2.cj)
 
-    def matvec(self, v):
+    supports_out = True      # matvec(v, out=flat tensor) writes the result in place
+
+    def _out_view(self, out, rows):
+        a, s, t, b = self.dims
+        return None if out is None else out.view(rows, s, t, self.R.shape[0])
+
+    def matvec(self, v, out=None):
         self.nmatvec += 1
         x = v.reshape(self.dims)
         # T1[a', w, s, t, b] = L[a', w, a] x[a, s, t, b]
@@ -87,7 +93,8 @@ class EffHam2:
                           [W_, S_, T_, W2_, SB_, TB_], [LB_, SB_, TB_, W2_, R_])
         # y[a', s', t', b'] = T3 R[b', w2, b]
         y = contract_pair(T, [LB_, SB_, TB_, W2_, R_], self.R.t,
-                          [RB_, W2_, R_], [LB_, SB_, TB_, RB_], conj_b=self.R.cj)
+                          [RB_, W2_, R_], [LB_, SB_, TB_, RB_], conj_b=self.R.cj,
+                          out=self._out_view(out, self.L.shape[0]))
         return Array(y).reshape(-1)
 
     __call__ = matvec
@@ -124,7 +131,7 @@ class ShardedEffHam2(EffHam2):
         return Array(self.shard.all_gather_rows(x, self.dims[0],
                                                 transient=transient)).reshape(-1)
 
-    def matvec(self, v_local):
+    def matvec(self, v_local, out=None):
         self.nmatvec += 1
         # the gathered vector is consumed by the first contraction below: the
         # peer-memory exchange may hand out its own buffer (no copy)
@@ -134,7 +141,8 @@ class ShardedEffHam2(EffHam2):
         T = contract_pair(T, [LB_, W_, S_, T_, R_], self.W12,
                           [W_, S_, T_, W2_, SB_, TB_], [LB_, SB_, TB_, W2_, R_])
         y = contract_pair(T, [LB_, SB_, TB_, W2_, R_], self.R.t,
-                          [RB_, W2_, R_], [LB_, SB_, TB_, RB_], conj_b=self.R.cj)
+                          [RB_, W2_, R_], [LB_, SB_, TB_, RB_], conj_b=self.R.cj,
+                          out=self._out_view(out, self.hi - self.lo))
         return Array(y).reshape(-1)
 
     __call__ = matvec

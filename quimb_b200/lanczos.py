@@ -98,16 +98,17 @@ def _orthogonalise(V, j, w, h, comm=None, keep=None):
     st = _lib.stream_ptr()
     ws = _md_ws(w.device).data_ptr()
     for it in range(2):
+        # the first pass writes its coefficients straight into ``keep`` (the
+        # caller's column of the projected matrix): no copy kernel
+        hc = keep if (it == 0 and keep is not None) else h
         for j0 in range(0, m, _MD_MAX):
             mm = min(_MD_MAX, m - j0)
             rc = lib.qb_multi_dot(_lib.QB_F64, mm, n, V[j0].data_ptr(), V.stride(0),
-                                  w.data_ptr(), h[j0:].data_ptr(), ws, st)
+                                  w.data_ptr(), hc[j0:].data_ptr(), ws, st)
             _lib.check(rc, "qb_multi_dot")
         if comm is not None:
-            comm.all_reduce_(h[:m])
-        if it == 0 and keep is not None:
-            keep[:m].copy_(h[:m])
-        _combine(V, m, h, w, -1.0)
+            comm.all_reduce_(hc[:m])
+        _combine(V, m, hc, w, -1.0)
 
 
 def eigh_lanczos(matvec, v0, which="SA", ncv=4, tol=1e-3, maxiter=None,
@@ -189,6 +190,9 @@ def eigh_lanczos(matvec, v0, which="SA", ncv=4, tol=1e-3, maxiter=None,
     eps23 = np.finfo(np.float64).eps ** (2.0 / 3.0)
     sign = 1.0 if which in ("SA", "SR") else -1.0
 
+    # operators of this package take ``out=`` (a flat float64 basis row); the
+    # real / single-precision wrappers above and foreign callables do not
+    out_ok = bool(getattr(matvec, "supports_out", False))
     nrm = _norm_c(v0, comm)
     V[0].copy_(v0.t)
     ops.scale_(Array(V[0]), 1.0, div_by=nrm)
@@ -223,9 +227,13 @@ def eigh_lanczos(matvec, v0, which="SA", ncv=4, tol=1e-3, maxiter=None,
         skip = 0
         est_prev = est = None
         for j in range(jstart, m):
-            Wj = matvec(Array(V[j]))
+            if out_ok:
+                # the operator writes H v_j straight into its basis slot
+                matvec(Array(V[j]), out=W[j])
+            else:
+                Wj = matvec(Array(V[j]))
+                W[j].copy_(ops.materialize(Wj).t.reshape(-1))
             nmv += 1
-            W[j].copy_(ops.materialize(Wj).t.reshape(-1))
             w.copy_(W[j])
             _orthogonalise(V, j, w, h, comm, keep=colbuf[j])
             bnorm = _norm_c(Array(w), comm)
@@ -234,8 +242,7 @@ def eigh_lanczos(matvec, v0, which="SA", ncv=4, tol=1e-3, maxiter=None,
                 # far from convergence (see below): keep the device busy, the
                 # columns of these steps are read together with the next one
                 skip -= 1
-                V[j + 1].copy_(w)
-                ops.scale_(Array(V[j + 1]), 1.0, div_by=bnorm)
+                ops.scale_into(Array(V[j + 1]), Array(w), 1.0, div_by=bnorm)
                 continue
             rows = colbuf[pending:j + 1, :j + 2].cpu().numpy()
             info["host_reads"] += 1
@@ -279,8 +286,7 @@ def eigh_lanczos(matvec, v0, which="SA", ncv=4, tol=1e-3, maxiter=None,
                     skip = int(min(2, math.log(est / (10.0 * thresh)) / -math.log(r)))
                 if nmv + skip + 1 < min_steps:
                     skip = max(skip, min(2, min_steps - nmv - 2))
-            V[j + 1].copy_(w)
-            ops.scale_(Array(V[j + 1]), 1.0, div_by=bnorm)
+            ops.scale_into(Array(V[j + 1]), Array(w), 1.0, div_by=bnorm)
         m = meff
 
         def ritz(yvec, out_v, out_w):

@@ -546,6 +546,21 @@ def scale_(x, alpha=1.0, div_by=None):
     return x
 
 
+def scale_into(y, x, alpha=1.0, div_by=None):
+    """y <- x * alpha / div_by (contiguous, same dtype / size; real factor);
+    returns y."""
+    lib = _lib.load()
+    if not (x.t.is_contiguous() and y.t.is_contiguous()) or x.cj or y.cj:
+        raise ValueError("scale_into needs contiguous, resolved operands")
+    if x.t.numel() != y.t.numel() or x.t.dtype != y.t.dtype:
+        raise ValueError("scale_into: size / dtype mismatch")
+    dptr = None if div_by is None else ctypes.c_void_p(div_by.t.data_ptr())
+    rc = lib.qb_scale_into(_lib.qb_dtype(x.t.dtype), x.t.numel(), float(alpha), dptr,
+                           x.t.data_ptr(), y.t.data_ptr(), _lib.stream_ptr())
+    _lib.check(rc, "qb_scale_into")
+    return y
+
+
 # --------------------------------- remaining names of the backend surface ---
 # (SURVEY 8(b): cold helpers quimb's drivers reach through ``do``; they
 # forward to torch on the wrapped tensor like the element-wise block above)

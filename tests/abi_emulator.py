@@ -236,6 +236,16 @@ class EmulatedLib:
             xv[...] = (xv * f).astype(xv.dtype)
         return 0
 
+    def qb_scale_into(self, dtype, n, alpha, div, x, y, stream):
+        self._tick("qb_scale_into")
+        f = float(alpha)
+        if _addr(div):
+            d = _flat(div, 1, _REAL[dtype])[0]
+            f = 0.0 if d == 0 else f / d
+        yv = _flat(y, n, _NP[dtype])
+        yv[...] = (_flat(x, n, _NP[dtype]) * f).astype(yv.dtype)
+        return 0
+
     def qb_dot(self, dtype, n, x, y, out, ws, stream):
         if not _addr(ws):
             return self._fail(-6, "qb_dot: workspace required")
