@@ -294,3 +294,41 @@ def test_planner_diagonal_and_summed_labels():
     # repeated label with different extents is an error
     with pytest.raises(ValueError):
         qb.plan_pair([4, 5], [5, 1], [0, 0], [], [], [], [4], [1], [0])
+
+
+def test_svd_trunc_and_p2p_argument_errors_without_a_device():
+    """Argument checks of the new entry points run before any CUDA call."""
+    import ctypes
+    lib = _lib.load()
+    nk, err, nn, sw = ctypes.c_int64(0), ctypes.c_double(0.0), ctypes.c_int64(0), ctypes.c_int(0)
+    args = lambda dt, m, n, mode, ws, wsb: (dt, m, n, None, 0.0, mode, -1, 0, 0, None, None, None,
+                                            ctypes.byref(nk), ctypes.byref(err), ctypes.byref(nn),
+                                            ws, wsb, ctypes.byref(sw), None)
+    assert lib.qb_svd_trunc(*args(_lib.QB_F32, 8, 4, 4, None, 0)) == -1       # f64 only
+    assert "only f64" in _lib.last_error()
+    assert lib.qb_svd_trunc(*args(_lib.QB_F64, 4, 8, 4, None, 0)) == -2       # m >= n
+    assert lib.qb_svd_trunc(*args(_lib.QB_F64, 8, 4, 4, None, 0)) == -8       # workspace
+    assert lib.qb_svd_workspace(_lib.QB_F64, 2048, 2048) > 0
+    assert lib.qb_svd_workspace(_lib.QB_F64, 20000, 64) < 0                  # beyond the register panels
+    assert lib.qb_p2p_block_bytes(32 << 20) >= (64 << 20) + 65536
+    assert lib.qb_p2p_data_offset(32 << 20, 1) - lib.qb_p2p_data_offset(32 << 20, 0) == 32 << 20
+    bufs = (ctypes.c_void_p * 2)(0, 0)
+    assert lib.qb_p2p_allgather(bufs, 2, 0, None, 16, 0, 1024, 1, None, None) == -2   # null peer
+    assert lib.qb_p2p_allgather(bufs, 40, 0, None, 16, 0, 1024, 1, None, None) == -1  # world > 16
+
+
+def test_path_to_sequence_linear_and_ssa():
+    from quimb_b200.compressed import path_to_sequence
+    # linear (opt_einsum) path over 4 tensors: contract (0,1) -> appended; then (0,1) again ...
+    assert path_to_sequence([(0, 1), (0, 1), (0, 1)], 4) == [(0, 1), (2, 3), (1, 3)]
+    # the same tree in SSA form: ids 4, 5, 6 are the intermediates
+    assert path_to_sequence([(0, 1), (2, 3), (4, 5)], 4) == [(0, 1), (2, 3), (1, 3)]
+
+
+def test_bond_shard_exchange_argument():
+    from quimb_b200.dist import BondShard
+    s = BondShard(rank=0, world_size=1)
+    assert not s.active and s.exchange_name == "none"
+    assert s.slab(10) == (0, 10)
+    with pytest.raises(ValueError):
+        BondShard(rank=0, world_size=1, exchange="mpi")
