@@ -245,10 +245,18 @@ class PeerExchange:
         if int(self.scratch[1].item()) != 0:
             raise RuntimeError("quimb_b200 peer exchange: timed out waiting for a peer's flag")
 
-    def close(self):
+    def close(self, collective=True):
+        """Unmap the peers' blocks, then free our own.  Collective by default:
+        an exporter must not free its block while a peer still has it mapped
+        (CUDA IPC), so all ranks pass a barrier between the two steps."""
         for p in self._imported:
             self.lib.qb_p2p_unimport(p)
         self._imported = []
+        if collective and dist.is_available() and dist.is_initialized():
+            try:
+                dist.barrier(group=self.group)
+            except Exception:  # noqa: BLE001  (process group already torn down)
+                pass
         if getattr(self, "local", None):
             self.lib.qb_p2p_free(self.local)
             self.local = None
