@@ -362,11 +362,17 @@ int qr_f64(int64_t m, int64_t n, const double *X, double *Q, double *R,
                                 cudaMemcpyDeviceToDevice, st));
   int rc;
   int64_t po = 0;
-  for (int64_t j0 = 0; j0 < k; j0 += QR_NBO, ++po) {
-    const int w = (int)std::min<int64_t>(QR_NBO, k - j0);   // outer panel width
+  // Aggregation pays when the trailing matrix does not stay in L2 (tall
+  // matrices: 16384 x 2048 went 179 -> 60 ms); for an L2-resident matrix the
+  // extra Gram GEMM + triangular inverse per outer panel cost more than the
+  // narrower updates save (2048 x 1024: 6.9 -> 8.7 ms), so there every inner
+  // panel is its own outer panel and its T is used as it comes.
+  const int64_t nbo = (m * n * 8 > (int64_t)64 << 20) ? QR_NBO : nb;
+  for (int64_t j0 = 0; j0 < k; j0 += nbo, ++po) {
+    const int w = (int)std::min<int64_t>(nbo, k - j0);   // outer panel width
     const int64_t mp = m - j0;
-    double *Vo = V + po * m * QR_NBO;   // (m - j0) x w, leading dimension w
-    double *To = TO + po * QR_NBO * QR_NBO;   // w x w, leading dimension w
+    double *Vo = V + j0 * m;            // (m - j0) x w slab, leading dimension w
+    double *To = TO + j0 * QR_NBO;      // w x w, leading dimension w
     double *Ti = T + (j0 / nb) * nb * nb;     // inner T's of this outer panel (w / nb of them)
     QB_CUDA_CHECK(cudaMemsetAsync(Vo, 0, sizeof(double) * mp * w, st));
     for (int ji = 0; ji < w; ji += nb) {
@@ -390,10 +396,17 @@ int qr_f64(int64_t m, int64_t n, const double *X, double *Q, double *R,
         if ((rc = gemm_f64(Vp, w, 1, W2, nti, 1, A2, n, 1, mpi, nti, nbw, -1.0, 1.0, st))) return rc;
       }
     }
-    // compact WY form of the whole outer panel: G = Vo^T Vo, T from its inverse
-    if ((rc = gemm_f64(Vo, 1, w, Vo, w, 1, G, w, 1, w, w, mp, 1.0, 0.0, st, SK, SKN, 16))) return rc;
-    wy_t_kernel<<<1, QR_NBO, (size_t)w * (w + 1) * 8, st>>>(G, w, Ti, nb, To);
-    QB_LAUNCH_CHECK();
+    if (w <= nb) {
+      // a single inner panel: its own T (nb x nb, leading dimension nb) is the
+      // outer T; copy the w x w block into the outer slot (leading dimension w)
+      QB_CUDA_CHECK(cudaMemcpy2DAsync(To, sizeof(double) * w, Ti, sizeof(double) * nb,
+                                      sizeof(double) * w, w, cudaMemcpyDeviceToDevice, st));
+    } else {
+      // compact WY form of the whole outer panel: G = Vo^T Vo, T from its inverse
+      if ((rc = gemm_f64(Vo, 1, w, Vo, w, 1, G, w, 1, w, w, mp, 1.0, 0.0, st, SK, SKN, 16))) return rc;
+      wy_t_kernel<<<1, QR_NBO, (size_t)w * (w + 1) * 8, st>>>(G, w, Ti, nb, To);
+      QB_LAUNCH_CHECK();
+    }
     const int64_t nt = n - (j0 + w);
     if (nt > 0) {
       double *C = F + j0 * n + j0 + w;
@@ -412,13 +425,13 @@ int qr_f64(int64_t m, int64_t n, const double *X, double *Q, double *R,
     set_identity_kernel<<<blocks, 256, 0, st>>>(Q, m, k);
     QB_LAUNCH_CHECK();
     // Q = H_1 ... H_p [I; 0], outer panels applied last to first on Q[j0:, j0:]
-    const int64_t nout = (k + QR_NBO - 1) / QR_NBO;
+    const int64_t nout = (k + nbo - 1) / nbo;
     for (int64_t pj = nout - 1; pj >= 0; --pj) {
-      const int64_t j0 = pj * QR_NBO;
-      const int w = (int)std::min<int64_t>(QR_NBO, k - j0);
+      const int64_t j0 = pj * nbo;
+      const int w = (int)std::min<int64_t>(nbo, k - j0);
       const int64_t mp = m - j0;
       const int64_t nq = k - j0;
-      double *Vo = V + pj * m * QR_NBO, *To = TO + pj * QR_NBO * QR_NBO;
+      double *Vo = V + j0 * m, *To = TO + j0 * QR_NBO;
       double *Qs = Q + j0 * k + j0;
       if ((rc = gemm_f64(Vo, 1, w, Qs, k, 1, W, nq, 1, w, nq, mp, 1.0, 0.0, st, SK, SKN, 16))) return rc;
       if ((rc = gemm_f64(To, w, 1, W, nq, 1, W2, nq, 1, w, nq, w, 1.0, 0.0, st))) return rc;
