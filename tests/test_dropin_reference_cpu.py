@@ -257,3 +257,34 @@ def test_reference_callers_either_side_of_the_path(env):
         np.testing.assert_allclose(np.asarray((_dev(p, qb) + _dev(q, qb)).to_dense()),
                                    (p + q).to_dense(), atol=1e-12)
         assert abs(float(_dev(p, qb).entropy(3)) - float(p.entropy(3))) < 1e-10
+
+
+def test_reference_compressed_contraction_runs_on_the_backend_and_matches_the_mirror(env):
+    """The reference's own ``_contract_compressed_tid_sequence`` (tensor_core.py:
+    8560-8780; 'basic' mode, and the default tree-gauged 'virtual-tree' mode the
+    array-level mirror does not duplicate) driven with device arrays: same
+    values as its numpy run, and -- for the mirrored mode -- as
+    ``quimb_b200.contract_compressed`` on the same sequence."""
+    qtn, qb, _ = env
+    tn = qtn.TN2D_rand(4, 4, D=3, seed=5)
+    tids = list(tn.tensor_map)
+    seq_pos = []
+    # a simple inward sequence: absorb the tensors row by row into the last one
+    order = list(range(len(tids)))
+    for i in range(len(order) - 1):
+        seq_pos.append((order[i], order[i + 1]))
+    seq = [(tids[a], tids[b]) for a, b in seq_pos]
+    for kw in (dict(max_bond=4, cutoff=0.0, tree_gauge_distance=0, compress_mode="basic"),
+               dict(max_bond=6, cutoff=1e-8, tree_gauge_distance=0, compress_mode="basic",
+                    compress_late=False),
+               dict(max_bond=5, cutoff=0.0)):                 # default: virtual-tree, gauge 1
+        ref = tn.copy()._contract_compressed_tid_sequence(seq, output_inds=(), **kw)
+        dev = _dev(tn, qb)._contract_compressed_tid_sequence(seq, output_inds=(), **kw)
+        dev = dev.item() if hasattr(dev, "item") else complex(dev)
+        assert abs(dev - ref) <= 1e-9 * abs(ref), kw
+        if kw.get("compress_mode") == "basic":
+            arrays = [qb.asarray(np.asarray(tn.tensor_map[t].data)) for t in tids]
+            inputs = [tuple(map(str, tn.tensor_map[t].inds)) for t in tids]
+            kw2 = {k: v for k, v in kw.items() if k not in ("tree_gauge_distance", "compress_mode")}
+            mir = qb.contract_compressed(arrays, inputs, (), seq_pos, **kw2)
+            assert abs(mir.item() - ref) <= 1e-9 * abs(ref), kw
