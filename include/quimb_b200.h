@@ -265,6 +265,12 @@ int64_t qb_svd_workspace(int dtype, int64_t m, int64_t n);
  * that are exactly zero (their rows of VH are zero: complete them if an
  * isometry is needed).  Workspace: qb_svd_workspace(dtype, m, n) bytes.
  */
+/* TEST / debug entry, host only: the sweep schedule of the Jacobi SVD (which
+ * column-block pairs rotate in which round of which stream); five int32 per
+ * pair: phase, group, round, p, q.  Returns the number of pairs. */
+int64_t qb_debug_jacobi_schedule(int nblk, int groups, int32_t *out,
+                                 int64_t capacity, int *groups_used);
+
 int qb_svd_trunc(int dtype, int64_t m, int64_t n, const void *X, double cutoff,
                  int cutoff_mode, int64_t max_bond, int absorb, int renorm,
                  void *U, void *S, void *VH, int64_t *n_keep,

@@ -107,6 +107,7 @@ def load(build_if_missing=True):
         ("qb_svd", ci, [ci, i64, i64, vp, vp, vp, vp, vp, ctypes.c_size_t,
                         P(ci), vp]),
         ("qb_svd_workspace", i64, [ci, i64, i64]),
+        ("qb_debug_jacobi_schedule", i64, [ci, ci, I32P, i64, P(ci)]),
         ("qb_svd_trunc", ci, [ci, i64, i64, vp, ctypes.c_double, ci, i64, ci, ci, vp, vp, vp,
                               P(i64), dblp, P(i64), vp, ctypes.c_size_t, P(ci), vp]),
         ("qb_svals_to_keep", ci, [dblp, i64, ctypes.c_double, ci, i64, ci,

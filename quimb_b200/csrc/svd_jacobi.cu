@@ -1135,6 +1135,31 @@ int qb_svd(int dtype, int64_t m, int64_t n, const void *X, void *U, void *S,
                         ws, sweeps_out, st);
 }
 
+// TEST / debug entry, host only: the sweep schedule of the Jacobi SVD for
+// `nblk` column blocks and `groups` independent streams.  Writes one record
+// (phase, group, round, p, q) of five int32 per column-block pair into `out`
+// (capacity in records) and returns the number of records (negative: capacity
+// too small).  `*groups_used` receives the group count actually used.
+int64_t qb_debug_jacobi_schedule(int nblk, int groups, int32_t *out, int64_t capacity,
+                                 int *groups_used) {
+  jac2::Schedule S;
+  jac2::build_schedule(nblk, groups, S);
+  if (groups_used) *groups_used = S.ngroups;
+  int64_t n = 0;
+  for (size_t ph = 0; ph < S.phases.size(); ++ph)
+    for (size_t g = 0; g < S.phases[ph].rounds.size(); ++g)
+      for (size_t r = 0; r < S.phases[ph].rounds[g].size(); ++r) {
+        const auto &rd = S.phases[ph].rounds[g][r];
+        for (int i = 0; i < rd.second; ++i) {
+          if (n >= capacity) return -1;
+          const int2 pr = S.pairs[rd.first + i];
+          int32_t *o = out + 5 * n++;
+          o[0] = (int32_t)ph; o[1] = (int32_t)g; o[2] = (int32_t)r; o[3] = pr.x; o[4] = pr.y;
+        }
+      }
+  return n;
+}
+
 int qb_svd_trunc(int dtype, int64_t m, int64_t n, const void *X, double cutoff,
                  int cutoff_mode, int64_t max_bond, int absorb, int renorm, void *U,
                  void *S, void *VH, int64_t *n_keep, double *trunc_error,
