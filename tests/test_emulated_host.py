@@ -88,3 +88,26 @@ def test_emu_blocked_qr_svd_for_tall_matrices(monkeypatch):
     np.testing.assert_allclose(Q.to_numpy() @ R.to_numpy(), z, atol=1e-12)
     with pytest.raises(ValueError):
         linalg.qr(qb.asarray(rng.standard_normal((100, 60))))
+
+
+def test_emu_inplace_arithmetic_updates_storage_and_refuses_widening():
+    """+= / -= / *= / /= mutate the array's own storage (views and
+    aliases see the update, as numpy's do) and raise on a dtype-widening result."""
+    import numpy as np
+    import quimb_b200 as qb
+    x = qb.asarray(np.arange(6.0).reshape(2, 3))
+    row = x[0]
+    row += 10.0
+    np.testing.assert_array_equal(x.to_numpy(), [[10.0, 11.0, 12.0], [3.0, 4.0, 5.0]])
+    alias = x
+    x *= 2.0
+    assert alias is x
+    np.testing.assert_array_equal(alias.to_numpy()[1], [6.0, 8.0, 10.0])
+    x -= qb.asarray(np.ones((2, 3)))
+    x /= 2.0
+    np.testing.assert_array_equal(x.to_numpy(), [[9.5, 10.5, 11.5], [2.5, 3.5, 4.5]])
+    with pytest.raises(TypeError):
+        x += 1j                       # real storage cannot take a complex result
+    z = qb.asarray(np.array([1 + 1j, 2 - 1j])).conj()      # lazy conjugation flag
+    z += 1.0
+    np.testing.assert_allclose(z.to_numpy(), [2 - 1j, 3 + 1j])
